@@ -1,0 +1,98 @@
+"""Pins the oracle: restatement vs the committed reference-generated fixtures (always) and vs
+the live reference modules (only where /root/reference exists).  CPU only."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_errs
+from oracle import cases, weights
+from oracle import estimator_ref as R
+
+# fp32 CPU kernels vs the same kernels: only summation-order noise is expected
+TOL = 2e-5
+
+_STATE = {}
+
+
+def state_for(n_mel):
+    if n_mel not in _STATE:
+        _STATE[n_mel] = weights.make_state(cases.WEIGHT_SEED, n_mel)
+    return _STATE[n_mel]
+
+
+def test_param_inventory():
+    st = state_for(80)
+    assert len(st) == 116
+    assert sum(v.numel() for v in st.values()) == 20_174_928
+    assert sum(v.numel() for v in state_for(128).values()) == 20_347_008
+
+
+@pytest.mark.parametrize("name", list(cases.ESTIMATOR_CASES))
+def test_estimator_vs_golden(name, golden_dir):
+    cs = cases.ESTIMATOR_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    st = state_for(cs["n_mel"])
+    assert abs(weights.checksum(st) - float(g["weight_checksum"])) < 1e-6 * abs(float(g["weight_checksum"])) + 1e-9, "RNG drift"
+    inp = weights.make_inputs(cs["seed"], cs["lengths"], cs["T"], cs["n_mel"],
+                              t_per_sample=cs.get("t_per_sample", False), t_value=cs.get("t_value", 0.37))
+    with torch.inference_mode():
+        out = R.estimator_forward(st, inp["t"], inp["x"], inp["mask"], inp["mu"], inp["c"])
+    ref = torch.from_numpy(g["out"])
+    assert out.shape == ref.shape
+    e_max, e_l2 = rel_errs(out, ref)
+    assert e_max < TOL and e_l2 < TOL, (e_max, e_l2)
+    # estimator output is exactly zero at masked frames
+    assert float((out * (1 - inp["mask"])).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("name", list(cases.SOLVE_CASES))
+def test_solve_vs_golden(name, golden_dir):
+    cs = cases.SOLVE_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    st = state_for(cs["n_mel"])
+    inp = weights.make_inputs(cs["seed"], cs["lengths"], cs["T"], cs["n_mel"])
+    fs, fc = weights.make_cfg_params(cases.CFG_SEED, cs["n_mel"])
+    cfg = None if cs["cfg"] is None else dict(fake_speaker=fs, fake_content=fc, cfg_strength=cs["cfg"])
+    torch.manual_seed(cs["seed"] + 1000)
+    z = torch.randn_like(inp["mu"])                          # models/flow_matching.py:45, temperature 1
+    out = R.cfm_forward(st, inp["mu"], inp["mask"], cs["steps"], z, inp["c"], cs["method"], cfg)
+    e_max, e_l2 = rel_errs(out, torch.from_numpy(g["out"]))
+    assert e_max < 1e-4 and e_l2 < 1e-4, (e_max, e_l2)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout only exists in the authoring container")
+def test_live_reference_modules():
+    sys.path.insert(0, "/root/reference")
+    if "torchdiffeq" not in sys.modules:
+        stub = types.ModuleType("torchdiffeq")
+        stub.odeint = lambda f, y0, t, method=None, rtol=None, atol=None: R.odeint_fixed(f, y0, t, method)[None]
+        sys.modules["torchdiffeq"] = stub
+    from models.estimator import Decoder
+    from models.diffusion_transformer import RotaryPositionalEmbeddings
+    dec = Decoder(80, 80, 256, 80, 1024, 0.1, 6, 4, 3, 256).eval()
+    st = state_for(80)
+    dec.load_state_dict(st, strict=True)
+    inp = weights.make_inputs(99, [70, 45], 70, 80, t_per_sample=True)
+    with torch.inference_mode():
+        ref = dec(inp["t"], inp["x"], inp["mask"], inp["mu"], inp["c"])
+        out = R.estimator_forward(st, inp["t"], inp["x"], inp["mask"], inp["mu"], inp["c"])
+    assert rel_errs(out, ref)[0] < TOL
+    # RoPE restatement is bit-exact against the module
+    q = torch.randn(2, 4, 37, 64)
+    assert torch.equal(R.rope_partial(q, 32), RotaryPositionalEmbeddings(32)(q))
+
+
+def test_padding_is_not_inert():
+    """values of x in the padded region leak into valid frames."""
+    st = state_for(80)
+    inp = weights.make_inputs(5, [40], 48, 80)
+    x2 = inp["x"].clone()
+    x2[:, :, 40:] = 7.0
+    with torch.inference_mode():
+        a = R.estimator_forward(st, inp["t"], inp["x"], inp["mask"], inp["mu"], inp["c"])
+        b = R.estimator_forward(st, inp["t"], x2, inp["mask"], inp["mu"], inp["c"])
+    assert float((a - b)[:, :, :40].abs().max()) > 1e-3
