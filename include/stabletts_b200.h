@@ -1,0 +1,127 @@
+/*
+ * stabletts_b200.h — C ABI of the B200-native CFM/DiT mel-denoiser (libstabletts_b200.so).
+ *
+ * The reference (KdaiP/StableTTS) has no FFI: its boundary for this path is a Python class
+ * surface.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes stub a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - every tensor argument is a raw DEVICE pointer to contiguous fp32 in the reference's own
+ *    boundary layout (B, C, T), T fastest, owned by the caller; the library never frees or
+ *    retains caller pointers past the call (weights are copied + repacked at load time);
+ *  - all work is enqueued on the `stream` passed (a cudaStream_t cast to void*); no entry point
+ *    except st_create / st_destroy / st_*_host synchronises the device;
+ *  - every function returns 0 on success, non-zero on failure; st_last_error() gives the text.
+ *    No exceptions cross the ABI.  There is NO CPU fallback: without a CUDA device st_create fails.
+ *  - `mask` is the reference's float prefix mask (B,1,T) == (B,T), values in {0,1}.
+ */
+#ifndef STABLETTS_B200_H_
+#define STABLETTS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct st_handle st_handle;
+
+/* Constructor arguments of models/estimator.py:66 `Decoder.__init__` (as built by
+ * models/flow_matching.py:22 from CFMDecoder's own arguments). */
+typedef struct st_dims {
+    int32_t n_mel;      /* noise_channels == cond_channels == out_channels (models/model.py:40) */
+    int32_t hidden;     /* hidden_channels, 256 (config.py:23) */
+    int32_t filter;     /* filter_channels, 1024 (config.py:24) */
+    int32_t n_heads;    /* 4 */
+    int32_t n_layers;   /* n_dec_layers, 6 (even: U-Net long skips, models/estimator.py:92) */
+    int32_t kernel;     /* kernel_size, 3 */
+    int32_t gin;        /* gin_channels, 256 (must equal hidden: adaLN_modulation.0 is Identity,
+                           models/diffusion_transformer.py:93) */
+} st_dims;
+
+/* ODE methods — the `solver` strings of models/flow_matching.py:54 / webui.py:110 that have a
+ * fixed grid; ST_DOPRI5_FIXED is the Dormand–Prince tableau stepped on the grid without error
+ * control (BASELINE.json cfg2's "dopri5-equiv"), NOT torchdiffeq's adaptive dopri5. */
+enum { ST_EULER = 0, ST_MIDPOINT = 1, ST_RK4 = 2, ST_DOPRI5_FIXED = 3 };
+
+/* GEMM engines (both hand-written sm_100a CUDA in this library; a debugging switch, not a
+ * backend dispatch): 0 = tcgen05/TMA split-bf16 tensor-core path (default), 1 = fp32 SIMT. */
+enum { ST_ENGINE_TCGEN05 = 0, ST_ENGINE_SIMT = 1 };
+
+/* Replaces: Decoder.__init__ (models/estimator.py:66-96).  Creates the per-device handle. */
+int st_create(const st_dims* dims, int device, st_handle** out);
+
+/* Replaces: nn.Module teardown. Frees packed weights and any internally owned workspace. */
+int st_destroy(st_handle* h);
+
+/* Last error text for this handle (or for st_create when h == NULL).  Never NULL. */
+const char* st_last_error(const st_handle* h);
+
+/* Library/ABI version (major*10000 + minor*100 + patch). */
+int st_version(void);
+
+/* Replaces: load_state_dict of the `decoder.estimator.*` tensors (api.py:49; inventory in
+ * models/estimator.py:66-96).  `name` is the reference key relative to `estimator.` (e.g.
+ * "blocks.3.block.mlp.conv_1.weight"); `data` is a device fp32 tensor in the reference layout
+ * with `numel` elements.  The library converts/packs into buffers it owns. */
+int st_load_weight(st_handle* h, const char* name, const float* data, int64_t numel, void* stream);
+
+/* Must be called after all 116 (for 6 layers) tensors are loaded; fails listing a missing key. */
+int st_finalize_weights(st_handle* h, void* stream);
+
+/* Selects the GEMM engine (see enum above).  Default ST_ENGINE_TCGEN05. */
+int st_set_engine(st_handle* h, int engine);
+
+/* Workspace: bytes needed for a (B, T) problem (cfg != 0 doubles the estimator batch), and
+ * attachment of a caller-owned device buffer of at least that size (e.g. a torch uint8 tensor).
+ * The buffer must stay alive until the next attach or st_destroy. */
+size_t st_workspace_bytes(const st_handle* h, int B, int T, int cfg);
+int st_attach_workspace(st_handle* h, void* dev_ptr, size_t bytes);
+
+/* Replaces: Decoder.forward(t, x, mask, mu, c) (models/estimator.py:103-137).
+ *   t: device fp32, t_count == 1 (the 0-dim t of odeint) or == B (training-style per-sample t)
+ *   x, mu, out: (B, n_mel, T);  mask: (B, T);  c: (B, gin). */
+int st_estimator_forward(st_handle* h, const float* t, int t_count, const float* x, const float* mask,
+                         const float* mu, const float* c, float* out, int B, int T, void* stream);
+
+/* Replaces: CFMDecoder.forward's `odeint(estimator | cfg_wrapper, z, t_span, method=solver)` and
+ * `trajectory[-1]` (models/flow_matching.py:46-55) together with cfg_wrapper (:58-67).
+ *   z_inout: (B, n_mel, T) — in: z = randn_like(mu)*temperature (UNMASKED, :45); out: the sample
+ *   fake_content (n_mel) / fake_speaker (gin): device, or NULL for no CFG (cfg_kwargs is None)
+ *   t_span_host: n_steps+1 fp32 values on the HOST (torch.linspace(0,1,n+1), :46)
+ * The whole solve is device-resident: no host synchronisation between steps. */
+int st_solve(st_handle* h, float* z_inout, const float* mu, const float* mask, const float* c,
+             const float* fake_content, const float* fake_speaker, float cfg_strength,
+             const float* t_span_host, int n_steps, int method, int B, int T, void* stream);
+
+/* Same as st_solve with HOST buffers: copies inputs host->device and the sample device->host on
+ * `stream` and synchronises it before returning (the end-to-end form bench.py's `e2e` times). */
+int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const float* mask_host,
+                  const float* c_host, const float* fake_content_host, const float* fake_speaker_host,
+                  float cfg_strength, const float* t_span_host, int n_steps, int method, int B, int T,
+                  void* stream);
+
+/* Number of kernels this library launched since the handle was created (bench.py gpu_launches). */
+int64_t st_launch_count(const st_handle* h);
+
+/* ---- kernel-level test hooks (used by tests/ only; same kernels the path uses) ------------- */
+
+/* out(R,N) = [silu]( A(R,K)·W(N,K)^T + bias ) through the selected engine's conv-GEMM with
+ * taps==1: exercises the tcgen05/TMA pipeline in isolation.  All device fp32, row-major. */
+int st_test_gemm(st_handle* h, const float* A, const float* W, const float* bias, float* out,
+                 int R, int K, int N, int silu, void* stream);
+
+/* k-tap conv1d, zero padded: x (B,Cin,T), w (Cout,Cin,k), out (B,Cout,T) — reference layouts. */
+int st_test_conv(st_handle* h, const float* x, const float* w, const float* bias, float* out,
+                 int B, int Cin, int Cout, int T, int k, void* stream);
+
+/* Masked multi-head attention with partial RoPE on packed qkv (B,T,3*hidden) -> (B,T,hidden). */
+int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* out, int B, int T,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STABLETTS_B200_H_ */

@@ -1,0 +1,71 @@
+"""ctypes binding of libstabletts_b200.so (C ABI: include/stabletts_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ST_EULER, ST_MIDPOINT, ST_RK4, ST_DOPRI5_FIXED = 0, 1, 2, 3
+ST_ENGINE_TCGEN05, ST_ENGINE_SIMT = 0, 1
+
+# every symbol include/stabletts_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "st_create", "st_destroy", "st_last_error", "st_version", "st_load_weight", "st_finalize_weights",
+    "st_set_engine", "st_workspace_bytes", "st_attach_workspace", "st_estimator_forward", "st_solve",
+    "st_solve_host", "st_launch_count", "st_test_gemm", "st_test_conv", "st_test_attention",
+]
+
+
+class StDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_mel", "hidden", "filter", "n_heads", "n_layers", "kernel", "gin")]
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libstabletts_b200.so")
+
+
+def load_library() -> C.CDLL:
+    """Loads the in-tree shared library; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). stabletts_b200 has no CPU/PyTorch fallback.")
+    lib = C.CDLL(path)
+    vp, f32p, i64, i32 = C.c_void_p, C.c_void_p, C.c_int64, C.c_int
+    lib.st_create.argtypes = [C.POINTER(StDims), i32, C.POINTER(vp)]
+    lib.st_destroy.argtypes = [vp]
+    lib.st_last_error.argtypes = [vp]
+    lib.st_last_error.restype = C.c_char_p
+    lib.st_version.restype = i32
+    lib.st_load_weight.argtypes = [vp, C.c_char_p, f32p, i64, vp]
+    lib.st_finalize_weights.argtypes = [vp, vp]
+    lib.st_set_engine.argtypes = [vp, i32]
+    lib.st_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.st_workspace_bytes.restype = C.c_size_t
+    lib.st_attach_workspace.argtypes = [vp, vp, C.c_size_t]
+    lib.st_estimator_forward.argtypes = [vp, f32p, i32, f32p, f32p, f32p, f32p, f32p, i32, i32, vp]
+    lib.st_solve.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, C.c_float, C.POINTER(C.c_float), i32, i32, i32, i32, vp]
+    lib.st_solve_host.argtypes = lib.st_solve.argtypes
+    lib.st_launch_count.argtypes = [vp]
+    lib.st_launch_count.restype = i64
+    lib.st_test_gemm.argtypes = [vp, f32p, f32p, f32p, f32p, i32, i32, i32, i32, vp]
+    lib.st_test_conv.argtypes = [vp, f32p, f32p, f32p, f32p, i32, i32, i32, i32, i32, vp]
+    lib.st_test_attention.argtypes = [vp, f32p, f32p, f32p, i32, i32, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("st_version",):
+            fn.restype = C.c_int
+    _LIB = lib
+    return lib
+
+
+def check(lib, handle, rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.st_last_error(handle)
+        raise RuntimeError(f"{what} failed: {msg.decode() if msg else 'unknown error'}")

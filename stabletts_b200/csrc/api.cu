@@ -1,0 +1,732 @@
+// C-ABI + host-side orchestration of the CFM/DiT hot path (see include/stabletts_b200.h).
+//
+// What runs where (reference: models/flow_matching.py:24-67, models/estimator.py:103-137):
+//   per solve   : layout change (B,C,T)->(B,T,C); cond_proj(mu) and cond_proj(fake_content) ONCE
+//                 (t-independent; exact hoist); in_proj's mu-half P = W_mu·mu' + b ONCE; adaLN(c)
+//                 ONCE; time-MLP + FiLM (gamma,beta) for every stage time of the grid up front.
+//   per eval    : in_proj x-half + P -> 6 x [ (lsc conv) FiLM·mask, LN, modulate, QKV, RoPE+masked
+//                 attention, O+gate+residual, LN, modulate, conv_1+SiLU, conv_2+gate+residual ]
+//                 -> final_proj.  With CFG the cond and uncond branches are ONE doubled batch.
+//   ODE driver  : explicit Runge–Kutta on the caller's grid, all device-resident: stage times are
+//                 baked into kernel arguments, nothing is copied or synchronised between steps.
+#include "common.cuh"
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <mutex>
+
+using namespace st;
+
+namespace {
+
+std::string g_create_error;
+std::mutex g_mutex;
+
+struct GemmW {           // one packed conv/linear weight
+    float* f32 = nullptr; bf16* hi = nullptr; bf16* lo = nullptr; float* bias = nullptr;
+    int taps = 1, N = 0, K = 0;
+};
+
+struct Act {             // an activation buffer: fp32 and/or split-bf16 planes, (batch, T, C)
+    float* f32 = nullptr; bf16* hi = nullptr; bf16* lo = nullptr; int C = 0;
+};
+
+struct Bump {
+    char* base; size_t off = 0, cap;
+    Bump(void* p, size_t c) : base((char*)p), cap(c) {}
+    template <class T> T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* r = base ? (T*)(base + off) : nullptr;
+        off += n * sizeof(T);
+        return r;
+    }
+};
+
+constexpr int MAX_EVAL_TABLE = 1024;
+
+struct Workspace {
+    int B = 0, T = 0, cfg = 0, BB = 0, Bc = 0, NT = 0;
+    Act xt, ytmp, xs, V, mut, C1, C2, C3, P, X[5], U, QKV, AO, Hid;
+    float* Kst[6] = {};
+    int* kvlen = nullptr;
+    float *rope_cs = nullptr, *temb = nullptr, *tmid = nullptr, *tvec = nullptr, *film = nullptr, *ada = nullptr;
+    float *cin = nullptr;    // (Bc, gin): c rows + fake_speaker row
+    // host staging for st_solve_host
+    float *h_z = nullptr, *h_mu = nullptr, *h_mask = nullptr, *h_c = nullptr, *h_fc = nullptr, *h_fs = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct st_handle {
+    st_dims d;
+    int device = 0, engine = ST_ENGINE_TCGEN05, num_sms = 148;
+    std::string err;
+    std::map<std::string, std::pair<float*, int64_t>> raw;   // name -> (device copy, numel)
+    bool finalized = false;
+    GemmW cond0, cond2, cond4, inmu, inx, fin;
+    std::vector<GemmW> qkv, wo, c1, c2, lsc;
+    std::vector<float*> film_w, film_b, ada_w, ada_b;
+    float *tm0_w = nullptr, *tm0_b = nullptr, *tm2_w = nullptr, *tm2_b = nullptr;
+    std::vector<void*> owned;
+    void* ws_ptr = nullptr; size_t ws_bytes = 0; bool ws_owned = false;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(st_handle* h, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return 1;
+}
+
+#define ST_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            char buf__[512];                                                                  \
+            snprintf(buf__, sizeof buf__, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
+                     cudaGetErrorString(e__));                                                \
+            return fail(h, buf__);                                                            \
+        }                                                                                     \
+    } while (0)
+
+#define ST_LAUNCH(call) do { h->launches++; ST_CUDA(call); } while (0)
+
+// ----- weight packing ---------------------------------------------------------------------------
+// in: (Nsrc, Csrc, k) reference Conv1d / Linear layout -> out[tap][n_off + n][c] for c in [c_off, c_off+Cc)
+__global__ void pack_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int Nsrc, int Csrc, int k,
+                                 int Ntot, int n_off, int c_off, int Cc) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = (long)k * Nsrc * Cc;
+    if (i >= total) return;
+    int c = (int)(i % Cc);
+    long r = i / Cc;
+    int n = (int)(r % Nsrc);
+    int tap = (int)(r / Nsrc);
+    out[((long)tap * Ntot + n_off + n) * Cc + c] = in[((long)n * Csrc + c_off + c) * k + tap];
+}
+
+struct TArr { float v[256]; };
+__global__ void time_embed_val_kernel(TArr t, int n_t, int H, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int half = H / 2;
+    if (i >= n_t * half) return;
+    int r = i / half, j = i - r * half;
+    float step = (float)(9.210340371976184 / (double)(half - 1));
+    float w = expf((float)j * -step);
+    float e = 1000.0f * t.v[r] * w;
+    out[(long)r * H + j] = sinf(e);
+    out[(long)r * H + half + j] = cosf(e);
+}
+
+template <class T> int dev_alloc(st_handle* h, T** p, size_t n) {
+    ST_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    h->owned.push_back(*p);
+    return 0;
+}
+
+int get_raw(st_handle* h, const std::string& name, int64_t expect, float** out) {
+    auto it = h->raw.find(name);
+    if (it == h->raw.end()) return fail(h, "missing weight: " + name);
+    if (it->second.second != expect) {
+        char b[256];
+        snprintf(b, sizeof b, "weight %s has %lld elements, expected %lld", name.c_str(), (long long)it->second.second,
+                 (long long)expect);
+        return fail(h, b);
+    }
+    *out = it->second.first;
+    return 0;
+}
+
+// Packs `parts` reference tensors (each (N_i, Csrc, k)) stacked along N, taking channels [c_off, c_off+Cc).
+int pack_gemm(st_handle* h, GemmW* w, const std::vector<std::string>& names, int N_each, int Csrc, int k, int c_off,
+              int Cc, bool with_bias, cudaStream_t s) {
+    int parts = (int)names.size();
+    w->taps = k; w->N = N_each * parts; w->K = Cc;
+    size_t n = (size_t)k * w->N * Cc;
+    if (dev_alloc(h, &w->f32, n)) return 1;
+    if (dev_alloc(h, &w->hi, n)) return 1;
+    if (dev_alloc(h, &w->lo, n)) return 1;
+    if (with_bias && dev_alloc(h, &w->bias, (size_t)w->N)) return 1;
+    for (int p = 0; p < parts; ++p) {
+        float* src;
+        if (get_raw(h, names[p] + ".weight", (int64_t)N_each * Csrc * k, &src)) return 1;
+        long total = (long)k * N_each * Cc;
+        pack_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, w->f32, N_each, Csrc, k, w->N, p * N_each,
+                                                                         c_off, Cc);
+        ST_CUDA(cudaGetLastError());
+        if (with_bias) {
+            float* bsrc;
+            if (get_raw(h, names[p] + ".bias", N_each, &bsrc)) return 1;
+            ST_CUDA(cudaMemcpyAsync(w->bias + (size_t)p * N_each, bsrc, sizeof(float) * N_each, cudaMemcpyDeviceToDevice, s));
+        }
+    }
+    ST_CUDA(launch_split(w->f32, w->hi, w->lo, (long)n, s));
+    return 0;
+}
+
+// ----- workspace ----------------------------------------------------------------------------------
+void layout_ws(const st_handle* h, Workspace& w, void* base, size_t cap, int B, int T, int cfg) {
+    const st_dims& d = h->d;
+    const bool tc = h->engine == ST_ENGINE_TCGEN05;
+    w.B = B; w.T = T; w.cfg = cfg; w.BB = cfg ? 2 * B : B; w.Bc = B + (cfg ? 1 : 0);
+    w.NT = std::max(MAX_EVAL_TABLE, B);
+    Bump bp(base, cap);
+    const size_t bt = (size_t)B * T, bbt = (size_t)w.BB * T, bct = (size_t)w.Bc * T;
+    auto mk = [&](Act& a, size_t rows, int C, bool f32, bool split) {
+        a.C = C;
+        a.f32 = f32 ? bp.take<float>(rows * C) : nullptr;
+        a.hi = split ? bp.take<bf16>(rows * C) : nullptr;
+        a.lo = split ? bp.take<bf16>(rows * C) : nullptr;
+    };
+    mk(w.xt, bt, d.n_mel, true, false);
+    mk(w.ytmp, bt, d.n_mel, true, false);
+    mk(w.xs, bt, d.n_mel, false, tc);
+    mk(w.V, bbt, d.n_mel, true, false);
+    for (int i = 0; i < 6; ++i) w.Kst[i] = bp.take<float>(bt * d.n_mel);
+    mk(w.mut, bct, d.n_mel, !tc, tc);
+    mk(w.C1, bct, d.filter, !tc, tc);
+    mk(w.C2, bct, d.filter, !tc, tc);
+    mk(w.C3, bct, d.hidden, !tc, tc);
+    mk(w.P, bct, d.hidden, true, false);
+    for (int i = 0; i < 5; ++i) mk(w.X[i], bbt, d.hidden, true, tc);
+    mk(w.U, bbt, d.hidden, !tc, tc);
+    mk(w.QKV, bbt, 3 * d.hidden, true, false);
+    mk(w.AO, bbt, d.hidden, !tc, tc);
+    mk(w.Hid, bbt, d.filter, !tc, tc);
+    w.kvlen = bp.take<int>(B);
+    w.rope_cs = bp.take<float>((size_t)T * 32);
+    w.temb = bp.take<float>((size_t)w.NT * d.hidden);
+    w.tmid = bp.take<float>((size_t)w.NT * d.filter);
+    w.tvec = bp.take<float>((size_t)w.NT * d.hidden);
+    w.film = bp.take<float>((size_t)w.NT * d.n_layers * 2 * d.hidden);
+    w.ada = bp.take<float>((size_t)w.Bc * d.n_layers * 6 * d.hidden);
+    w.cin = bp.take<float>((size_t)w.Bc * d.gin);
+    w.h_z = bp.take<float>(bt * d.n_mel);
+    w.h_mu = bp.take<float>(bt * d.n_mel);
+    w.h_mask = bp.take<float>(bt);
+    w.h_c = bp.take<float>((size_t)B * d.gin);
+    w.h_fc = bp.take<float>(d.n_mel);
+    w.h_fs = bp.take<float>(d.gin);
+    w.bytes = bp.off + 256;
+}
+
+int ensure_ws(st_handle* h, Workspace& w, int B, int T, int cfg) {
+    Workspace probe;
+    layout_ws(h, probe, nullptr, 0, B, T, cfg);
+    if (h->ws_ptr == nullptr || h->ws_bytes < probe.bytes) {
+        if (h->ws_ptr && !h->ws_owned)
+            return fail(h, "attached workspace too small: need " + std::to_string(probe.bytes) + " bytes");
+        if (h->ws_ptr) { cudaFree(h->ws_ptr); h->ws_ptr = nullptr; }
+        ST_CUDA(cudaMalloc(&h->ws_ptr, probe.bytes));
+        h->ws_bytes = probe.bytes; h->ws_owned = true;
+    }
+    layout_ws(h, w, h->ws_ptr, h->ws_bytes, B, T, cfg);
+    return 0;
+}
+
+// ----- GEMM dispatch -------------------------------------------------------------------------------
+int run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const Act* a1, const Act& out, cudaStream_t s) {
+    const bool tc = h->engine == ST_ENGINE_TCGEN05;
+    g.n_src = a1 ? 2 : 1;
+    const Act* as[2] = {a0, a1};
+    int ktot = 0;
+    for (int i = 0; i < g.n_src; ++i) {
+        g.A_f32[i] = as[i]->f32; g.A_hi[i] = as[i]->hi; g.A_lo[i] = as[i]->lo; g.Cs[i] = as[i]->C;
+        ktot += as[i]->C;
+        if (tc ? (!as[i]->hi) : (!as[i]->f32)) return fail(h, "internal: GEMM operand plane missing for engine");
+    }
+    if (ktot != w.K) return fail(h, "internal: GEMM K mismatch");
+    g.W_f32 = w.f32; g.W_hi = w.hi; g.W_lo = w.lo; g.bias = w.bias;
+    if ((g.flags & EPI_BIAS) && !w.bias) return fail(h, "internal: bias requested but absent");
+    g.taps = w.taps; g.N = w.N; g.Ktot = w.K;
+    g.out_f32 = out.f32; g.out_hi = out.hi; g.out_lo = out.lo;
+    if (out.C != w.N) return fail(h, "internal: GEMM N mismatch");
+    h->launches++;
+    if (tc) {
+        cudaError_t e = launch_gemm_tc(g, h->num_sms, s);
+        if (e != cudaSuccess) return fail(h, std::string("tcgen05 GEMM launch failed: ") + cudaGetErrorString(e) + " / " + gemm_tc_last_error());
+    } else {
+        cudaError_t e = launch_gemm_simt(g, s);
+        if (e != cudaSuccess) return fail(h, std::string("SIMT GEMM launch failed: ") + cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+// ----- per-solve precompute -------------------------------------------------------------------------
+// cond features (models/estimator.py:118) for B real rows + (cfg) the broadcast fake_content row;
+// P = W_in[:, M:]·mu' + b_in (models/estimator.py:120-121, mu-half); adaLN(c) (diffusion_transformer.py:110)
+int precompute_cond(st_handle* h, Workspace& w, const float* mu, const float* mask, const float* c,
+                    const float* fake_content, const float* fake_speaker, cudaStream_t s) {
+    const st_dims& d = h->d;
+    ST_LAUNCH(launch_bct_to_btc(mu, w.mut.f32, w.mut.hi, w.mut.lo, w.B, d.n_mel, w.T, w.cfg ? fake_content : nullptr, s));
+    ST_LAUNCH(launch_mask_lengths(mask, w.kvlen, w.B, w.T, s));
+    ST_LAUNCH(launch_rope_table(w.rope_cs, w.T, 32, s));
+    GemmArgs g;
+    g.BB = w.Bc; g.T = w.T; g.a_bmod = w.Bc; g.B = w.B; g.resid_clamp = w.Bc - 1;
+    g.flags = EPI_BIAS | EPI_SILU;
+    if (run_gemm(h, g, h->cond0, &w.mut, nullptr, w.C1, s)) return 1;
+    if (run_gemm(h, g, h->cond2, &w.C1, nullptr, w.C2, s)) return 1;
+    g.flags = EPI_BIAS;
+    if (run_gemm(h, g, h->cond4, &w.C2, nullptr, w.C3, s)) return 1;
+    if (run_gemm(h, g, h->inmu, &w.C3, nullptr, w.P, s)) return 1;
+    // adaLN: rows = c (B) [+ fake_speaker]
+    ST_CUDA(cudaMemcpyAsync(w.cin, c, sizeof(float) * (size_t)w.B * d.gin, cudaMemcpyDeviceToDevice, s));
+    if (w.cfg)
+        ST_CUDA(cudaMemcpyAsync(w.cin + (size_t)w.B * d.gin, fake_speaker, sizeof(float) * d.gin, cudaMemcpyDeviceToDevice, s));
+    for (int l = 0; l < d.n_layers; ++l)   // ada layout (Bc, L, 6H)
+        ST_LAUNCH(launch_gemv(w.cin, h->ada_w[l], h->ada_b[l], w.ada + (size_t)l * 6 * d.hidden, (long)d.n_layers * 6 * d.hidden,
+                              w.Bc, d.gin, 6 * d.hidden, 1, 0, s));
+    return 0;
+}
+
+// time-MLP + FiLM vectors for n_t times already embedded in w.temb (models/estimator.py:55-62,30-31)
+int precompute_film(st_handle* h, Workspace& w, int n_t, cudaStream_t s) {
+    const st_dims& d = h->d;
+    ST_LAUNCH(launch_gemv(w.temb, h->tm0_w, h->tm0_b, w.tmid, d.filter, n_t, d.hidden, d.filter, 0, 1, s));
+    ST_LAUNCH(launch_gemv(w.tmid, h->tm2_w, h->tm2_b, w.tvec, d.hidden, n_t, d.filter, d.hidden, 0, 0, s));
+    for (int l = 0; l < d.n_layers; ++l)   // film layout (n_t, L, 2H)
+        ST_LAUNCH(launch_gemv(w.tvec, h->film_w[l], h->film_b[l], w.film + (size_t)l * 2 * d.hidden, (long)d.n_layers * 2 * d.hidden,
+                              n_t, d.hidden, 2 * d.hidden, 0, 0, s));
+    return 0;
+}
+
+// ----- one estimator evaluation (models/estimator.py:120-137) ------------------------------------------
+// xin: (B, T, M) stage input (fp32 [+ split planes for the tensor engine]); writes w.V (BB, T, M).
+// film: table row for this eval, (L, 2H); film_bstride != 0 when t is per-sample.
+int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask, const float* film, long film_bstride,
+                   cudaStream_t s) {
+    const st_dims& d = h->d;
+    const int H = d.hidden, L = d.n_layers, n_lsc = L / 2;
+    const long ada_bs = (long)L * 6 * H;
+    auto base = [&](int flags) {
+        GemmArgs g;
+        g.BB = w.BB; g.T = w.T; g.a_bmod = w.BB; g.B = w.B; g.mask = mask; g.flags = flags;
+        g.c_clamp = w.B; g.resid_clamp = w.BB - 1; g.film_H = H; g.rope_cs = w.rope_cs;
+        return g;
+    };
+    // in_proj: x-half GEMM + hoisted P (cond rows P[b], uncond rows P[B])
+    {
+        GemmArgs g = base(EPI_RESID);
+        g.a_bmod = w.B; g.resid = w.P.f32; g.resid_clamp = w.B;
+        if (run_gemm(h, g, h->inx, &xin, nullptr, w.X[0], s)) return 1;
+    }
+    // buffer plan (skips are block INPUTS, models/estimator.py:128-131):
+    //   X0 = in_proj out (skip for block 5), X1 = block0 out (skip for block 4), X2 = block1 out (skip for block 3)
+    int cur = 0;
+    for (int l = 0; l < L; ++l) {
+        const float* film_l = film + (size_t)l * 2 * H;
+        const float* ada_l = w.ada + (size_t)l * 6 * H;
+        int xb;                        // buffer holding this block's residual stream
+        LnArgs ln;
+        ln.BB = w.BB; ln.T = w.T; ln.H = H; ln.mask = mask; ln.B = w.B; ln.c_clamp = w.B; ln.ada_bstride = ada_bs;
+        if (l < n_lsc) {
+            xb = cur + 1;              // FiLM·mask written to a fresh buffer so the block input survives as a skip
+            ln.xin = w.X[cur].f32; ln.xout = w.X[xb].f32; ln.has_film = 1; ln.film = film_l; ln.film_bstride = film_bstride;
+        } else {
+            // long skip: x = Conv1d(k=3)(cat(x, skip)) UNMASKED (models/estimator.py:131-132), FiLM·mask fused in the epilogue
+            const int sk = L - 1 - l;      // pop order: block-(L-1-l) input
+            xb = (cur == n_lsc) ? n_lsc + 1 : n_lsc;
+            GemmArgs g = base(EPI_BIAS | EPI_FILM | EPI_MASK);
+            g.film = film_l; g.film_bstride = film_bstride;
+            Act out = w.X[xb]; out.hi = nullptr; out.lo = nullptr;     // consumed by LN only
+            if (run_gemm(h, g, h->lsc[l - n_lsc], &w.X[cur], &w.X[sk], out, s)) return 1;
+            ln.xin = w.X[xb].f32; ln.has_film = 0;
+        }
+        ln.shift = ada_l; ln.scale = ada_l + H;
+        ln.u_f32 = w.U.f32; ln.u_hi = w.U.hi; ln.u_lo = w.U.lo;
+        ST_LAUNCH(launch_film_ln_mod(ln, s));
+        {   // q,k,v projections as one N=3H GEMM (models/diffusion_transformer.py:59-61)
+            GemmArgs g = base(EPI_BIAS);
+            if (run_gemm(h, g, h->qkv[l], &w.U, nullptr, w.QKV, s)) return 1;
+        }
+        {
+            AttnArgs a;
+            a.qkv = w.QKV.f32; a.rope_cs = w.rope_cs; a.mask = mask; a.kvlen = w.kvlen;
+            a.out_f32 = w.AO.f32; a.out_hi = w.AO.hi; a.out_lo = w.AO.lo;
+            a.BB = w.BB; a.B = w.B; a.T = w.T; a.H = H; a.n_heads = d.n_heads;
+            ST_LAUNCH(launch_attention_simt(a, s));
+        }
+        {   // x += gate_msa * conv_o(attn) * mask   (:65, :111)
+            GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
+            g.gate = ada_l + 2 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
+            Act out = w.X[xb]; out.hi = nullptr; out.lo = nullptr;
+            if (run_gemm(h, g, h->wo[l], &w.AO, nullptr, out, s)) return 1;
+        }
+        {   // LN2 + modulate, FFN input mask (:112, :26)
+            LnArgs l2 = ln;
+            l2.xin = w.X[xb].f32; l2.xout = nullptr; l2.has_film = 0; l2.mask_out = 1;
+            l2.shift = ada_l + 3 * H; l2.scale = ada_l + 4 * H;
+            ST_LAUNCH(launch_film_ln_mod(l2, s));
+        }
+        {   // conv_1 + SiLU, (h * mask) feeds conv_2 (:26-29)
+            GemmArgs g = base(EPI_BIAS | EPI_SILU | EPI_MASK);
+            if (run_gemm(h, g, h->c1[l], &w.U, nullptr, w.Hid, s)) return 1;
+        }
+        {   // x += gate_mlp * (conv_2(h) * mask)   (:29-30, :112)
+            GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
+            g.gate = ada_l + 5 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
+            if (run_gemm(h, g, h->c2[l], &w.Hid, nullptr, w.X[xb], s)) return 1;
+        }
+        cur = xb;
+    }
+    {   // final_proj(x * mask) * mask (:136-137); x is already masked at this point
+        GemmArgs g = base(EPI_BIAS | EPI_MASK);
+        if (run_gemm(h, g, h->fin, &w.X[cur], nullptr, w.V, s)) return 1;
+    }
+    return 0;
+}
+
+struct Tableau { int S; float c[6]; float a[6][5]; float b[6]; };
+
+Tableau tableau_for(int method) {
+    Tableau t{};
+    if (method == ST_EULER) { t.S = 1; t.b[0] = 1.f; }
+    else if (method == ST_MIDPOINT) { t.S = 2; t.c[1] = 0.5f; t.a[1][0] = 0.5f; t.b[1] = 1.f; }
+    else if (method == ST_RK4) {   // torchdiffeq "rk4" = 3/8 rule
+        t.S = 4; t.c[1] = 1.f / 3; t.c[2] = 2.f / 3; t.c[3] = 1.f;
+        t.a[1][0] = 1.f / 3; t.a[2][0] = -1.f / 3; t.a[2][1] = 1.f; t.a[3][0] = 1.f; t.a[3][1] = -1.f; t.a[3][2] = 1.f;
+        t.b[0] = 0.125f; t.b[1] = 0.375f; t.b[2] = 0.375f; t.b[3] = 0.125f;
+    } else {                       // Dormand–Prince 5(4) stages 1..6, 5th-order weights, no error control
+        t.S = 6;
+        const double c[6] = {0, 1. / 5, 3. / 10, 4. / 5, 8. / 9, 1};
+        const double a[6][5] = {{0}, {1. / 5}, {3. / 40, 9. / 40}, {44. / 45, -56. / 15, 32. / 9},
+                                {19372. / 6561, -25360. / 2187, 64448. / 6561, -212. / 729},
+                                {9017. / 3168, -355. / 33, 46732. / 5247, 49. / 176, -5103. / 18656}};
+        const double b[6] = {35. / 384, 0, 500. / 1113, 125. / 192, -2187. / 6784, 11. / 84};
+        for (int i = 0; i < 6; ++i) { t.c[i] = (float)c[i]; t.b[i] = (float)b[i]; for (int j = 0; j < 5; ++j) t.a[i][j] = (float)a[i][j]; }
+    }
+    return t;
+}
+
+int check_common(st_handle* h, int B, int T) {
+    if (!h) return 1;
+    if (!h->finalized) return fail(h, "weights not finalized (call st_finalize_weights)");
+    if (B <= 0 || T <= 0) return fail(h, "B and T must be positive");
+    if (B > 32767) return fail(h, "B too large");
+    ST_CUDA(cudaSetDevice(h->device));
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int st_version(void) { return 100; }
+
+const char* st_last_error(const st_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int st_create(const st_dims* dims, int device, st_handle** out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    st_handle* h = nullptr;
+    if (!dims || !out) return fail(nullptr, "null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, "bad device index");
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return fail(nullptr, "cudaGetDeviceProperties failed");
+    if (p.major != 10) return fail(nullptr, "device is not sm_100-class (Blackwell B200 required)");
+    if (dims->hidden != 256 || dims->n_heads * 64 != dims->hidden)
+        return fail(nullptr, "only hidden=256, head_dim=64 is built (reference ModelConfig, config.py:22-30)");
+    if (dims->gin != dims->hidden) return fail(nullptr, "gin_channels must equal hidden_channels");
+    if (dims->n_layers <= 0 || dims->n_layers % 2 || dims->n_layers > 6) return fail(nullptr, "n_layers must be even and <= 6");
+    if (dims->kernel != 3 && dims->kernel != 1) return fail(nullptr, "kernel_size must be 1 or 3");
+    if (dims->n_mel % 16 || dims->n_mel <= 0 || dims->n_mel > 256) return fail(nullptr, "n_mel must be a multiple of 16, <= 256");
+    if (dims->filter % 64 || dims->filter <= 0) return fail(nullptr, "filter_channels must be a multiple of 64");
+    h = new st_handle();
+    h->d = *dims; h->device = device; h->num_sms = p.multiProcessorCount;
+    *out = h;
+    return 0;
+}
+
+int st_destroy(st_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : h->raw) cudaFree(kv.second.first);
+    for (void* p : h->owned) cudaFree(p);
+    if (h->ws_ptr && h->ws_owned) cudaFree(h->ws_ptr);
+    delete h;
+    return 0;
+}
+
+int st_set_engine(st_handle* h, int engine) {
+    if (!h) return 1;
+    if (engine != ST_ENGINE_TCGEN05 && engine != ST_ENGINE_SIMT) return fail(h, "unknown engine");
+    h->engine = engine;
+    return 0;
+}
+
+int64_t st_launch_count(const st_handle* h) { return h ? h->launches : 0; }
+
+int st_load_weight(st_handle* h, const char* name, const float* data, int64_t numel, void* stream) {
+    if (!h || !name || !data || numel <= 0) return fail(h, "st_load_weight: bad argument");
+    ST_CUDA(cudaSetDevice(h->device));
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, data) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        return fail(h, std::string("st_load_weight: ") + name + " is not a device pointer (no CPU path)");
+    }
+    float* p;
+    ST_CUDA(cudaMalloc((void**)&p, sizeof(float) * numel));
+    ST_CUDA(cudaMemcpyAsync(p, data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    auto it = h->raw.find(name);
+    if (it != h->raw.end()) { cudaFree(it->second.first); }
+    h->raw[name] = {p, numel};
+    h->finalized = false;
+    return 0;
+}
+
+int st_finalize_weights(st_handle* h, void* stream) {
+    if (!h) return 1;
+    ST_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const st_dims& d = h->d;
+    const int H = d.hidden, F = d.filter, M = d.n_mel, k = d.kernel, L = d.n_layers;
+    for (void* p : h->owned) cudaFree(p);
+    h->owned.clear();
+    h->qkv.assign(L, GemmW()); h->wo.assign(L, GemmW()); h->c1.assign(L, GemmW()); h->c2.assign(L, GemmW());
+    h->lsc.assign(L / 2, GemmW());
+    h->film_w.assign(L, nullptr); h->film_b.assign(L, nullptr); h->ada_w.assign(L, nullptr); h->ada_b.assign(L, nullptr);
+    if (pack_gemm(h, &h->cond0, {"cond_proj.0"}, F, M, k, 0, M, true, s)) return 1;
+    if (pack_gemm(h, &h->cond2, {"cond_proj.2"}, F, F, k, 0, F, true, s)) return 1;
+    if (pack_gemm(h, &h->cond4, {"cond_proj.4"}, H, F, k, 0, F, true, s)) return 1;
+    // in_proj acts on cat(x, mu') (models/estimator.py:120): columns [0,M) multiply x, [M, M+H) multiply mu'
+    if (pack_gemm(h, &h->inx, {"in_proj"}, H, M + H, 1, 0, M, false, s)) return 1;
+    if (pack_gemm(h, &h->inmu, {"in_proj"}, H, M + H, 1, M, H, true, s)) return 1;
+    if (pack_gemm(h, &h->fin, {"final_proj"}, M, H, 1, 0, H, true, s)) return 1;
+    for (int l = 0; l < L; ++l) {
+        std::string p = "blocks." + std::to_string(l) + ".";
+        if (pack_gemm(h, &h->qkv[l], {p + "block.attn.conv_q", p + "block.attn.conv_k", p + "block.attn.conv_v"}, H, H, 1, 0, H, true, s)) return 1;
+        if (pack_gemm(h, &h->wo[l], {p + "block.attn.conv_o"}, H, H, 1, 0, H, true, s)) return 1;
+        if (pack_gemm(h, &h->c1[l], {p + "block.mlp.conv_1"}, F, H, k, 0, H, true, s)) return 1;
+        if (pack_gemm(h, &h->c2[l], {p + "block.mlp.conv_2"}, H, F, k, 0, F, true, s)) return 1;
+        if (get_raw(h, p + "time_fusion.film.weight", (int64_t)2 * H * H, &h->film_w[l])) return 1;
+        if (get_raw(h, p + "time_fusion.film.bias", 2 * H, &h->film_b[l])) return 1;
+        if (get_raw(h, p + "block.adaLN_modulation.2.weight", (int64_t)6 * H * H, &h->ada_w[l])) return 1;
+        if (get_raw(h, p + "block.adaLN_modulation.2.bias", 6 * H, &h->ada_b[l])) return 1;
+    }
+    for (int i = 0; i < L / 2; ++i)
+        if (pack_gemm(h, &h->lsc[i], {"lsc_layers." + std::to_string(i)}, H, 2 * H, k, 0, 2 * H, true, s)) return 1;
+    if (get_raw(h, "time_mlp.layer.0.weight", (int64_t)F * H, &h->tm0_w)) return 1;
+    if (get_raw(h, "time_mlp.layer.0.bias", F, &h->tm0_b)) return 1;
+    if (get_raw(h, "time_mlp.layer.2.weight", (int64_t)H * F, &h->tm2_w)) return 1;
+    if (get_raw(h, "time_mlp.layer.2.bias", H, &h->tm2_b)) return 1;
+    h->finalized = true;
+    return 0;
+}
+
+size_t st_workspace_bytes(const st_handle* h, int B, int T, int cfg) {
+    if (!h || B <= 0 || T <= 0) return 0;
+    Workspace w;
+    layout_ws(h, w, nullptr, 0, B, T, cfg);
+    return w.bytes;
+}
+
+int st_attach_workspace(st_handle* h, void* dev_ptr, size_t bytes) {
+    if (!h) return 1;
+    if (h->ws_ptr && h->ws_owned) { cudaSetDevice(h->device); cudaFree(h->ws_ptr); }
+    h->ws_ptr = dev_ptr; h->ws_bytes = dev_ptr ? bytes : 0; h->ws_owned = false;
+    return 0;
+}
+
+int st_estimator_forward(st_handle* h, const float* t, int t_count, const float* x, const float* mask, const float* mu,
+                         const float* c, float* out, int B, int T, void* stream) {
+    if (check_common(h, B, T)) return 1;
+    if (!t || !x || !mask || !mu || !c || !out) return fail(h, "st_estimator_forward: null pointer");
+    if (t_count != 1 && t_count != B) return fail(h, "t must have 1 or B elements (models/estimator.py:107)");
+    cudaStream_t s = (cudaStream_t)stream;
+    Workspace w;
+    if (ensure_ws(h, w, B, T, 0)) return 1;
+    const st_dims& d = h->d;
+    if (precompute_cond(h, w, mu, mask, c, nullptr, nullptr, s)) return 1;
+    ST_LAUNCH(launch_time_embed(t, t_count, d.hidden, w.temb, s));
+    if (precompute_film(h, w, t_count, s)) return 1;
+    ST_LAUNCH(launch_bct_to_btc(x, w.xt.f32, w.xs.hi, w.xs.lo, B, d.n_mel, T, nullptr, s));
+    Act xin = w.xt; xin.hi = w.xs.hi; xin.lo = w.xs.lo;
+    if (estimator_eval(h, w, xin, mask, w.film, t_count == 1 ? 0 : (long)d.n_layers * 2 * d.hidden, s)) return 1;
+    ST_LAUNCH(launch_btc_to_bct(w.V.f32, out, B, d.n_mel, T, s));
+    return 0;
+}
+
+int st_solve(st_handle* h, float* z_inout, const float* mu, const float* mask, const float* c, const float* fake_content,
+             const float* fake_speaker, float cfg_strength, const float* t_span_host, int n_steps, int method, int B, int T,
+             void* stream) {
+    if (check_common(h, B, T)) return 1;
+    if (!z_inout || !mu || !mask || !c || !t_span_host) return fail(h, "st_solve: null pointer");
+    if (n_steps <= 0) return fail(h, "n_timesteps must be positive");
+    if (method < ST_EULER || method > ST_DOPRI5_FIXED) return fail(h, "unknown ODE method");
+    const int cfg = (fake_content && fake_speaker) ? 1 : 0;
+    if (!cfg && (fake_content || fake_speaker)) return fail(h, "CFG needs both fake_content and fake_speaker");
+    cudaStream_t s = (cudaStream_t)stream;
+    Workspace w;
+    if (ensure_ws(h, w, B, T, cfg)) return 1;
+    const st_dims& d = h->d;
+    const Tableau tb = tableau_for(method);
+    const long numel = (long)B * T * d.n_mel;
+
+    if (precompute_cond(h, w, mu, mask, c, fake_content, fake_speaker, s)) return 1;
+    ST_LAUNCH(launch_bct_to_btc(z_inout, w.xt.f32, nullptr, nullptr, B, d.n_mel, T, nullptr, s));
+
+    // stage times, fp32 arithmetic as torchdiffeq's fixed-grid solvers evaluate them
+    std::vector<float> tv((size_t)n_steps * tb.S);
+    for (int i = 0; i < n_steps; ++i) {
+        const float t0 = t_span_host[i], t1 = t_span_host[i + 1], dt = t1 - t0;
+        for (int st = 0; st < tb.S; ++st) tv[(size_t)i * tb.S + st] = (tb.c[st] == 1.f) ? t1 : t0 + tb.c[st] * dt;
+    }
+    const int n_eval = n_steps * tb.S;
+    const long film_row = (long)d.n_layers * 2 * d.hidden;
+    int table_lo = 0, table_hi = 0;      // evals [lo, hi) currently in the FiLM table
+    for (int e = 0; e < n_eval; ++e) {
+        if (e >= table_hi) {             // (re)fill the t-conditioning table: no copies, times travel as kernel args
+            table_lo = e; table_hi = std::min(n_eval, e + MAX_EVAL_TABLE);
+            for (int off = table_lo; off < table_hi; off += 256) {
+                TArr ta; int n = std::min(256, table_hi - off);
+                for (int i = 0; i < n; ++i) ta.v[i] = tv[off + i];
+                int cnt = n * (d.hidden / 2);
+                h->launches++;
+                time_embed_val_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(ta, n, d.hidden, w.temb + (size_t)(off - table_lo) * d.hidden);
+                ST_CUDA(cudaGetLastError());
+            }
+            if (precompute_film(h, w, table_hi - table_lo, s)) return 1;
+        }
+        const int step = e / tb.S, st = e % tb.S;
+        const float dt = t_span_host[step + 1] - t_span_host[step];
+        Act xin = w.xt;
+        if (st > 0) {                    // stage input y + dt * sum_j a[st][j] K_j
+            float coef[6]; const float* Ks[6];
+            for (int j = 0; j < st; ++j) { coef[j] = dt * tb.a[st][j]; Ks[j] = w.Kst[j]; }
+            ST_LAUNCH(launch_lincomb(w.ytmp.f32, w.xt.f32, Ks, coef, st, numel, s));
+            xin = w.ytmp;
+        }
+        if (h->engine == ST_ENGINE_TCGEN05) {
+            ST_LAUNCH(launch_split(xin.f32, w.xs.hi, w.xs.lo, numel, s));
+            xin.hi = w.xs.hi; xin.lo = w.xs.lo;
+        }
+        if (estimator_eval(h, w, xin, mask, w.film + (size_t)(e - table_lo) * film_row, 0, s)) return 1;
+        ST_LAUNCH(launch_cfg_combine(w.V.f32, w.Kst[st], B, (long)T * d.n_mel, cfg, cfg_strength, s));
+        if (st == tb.S - 1) {            // y += dt * sum_j b_j K_j
+            float coef[6]; const float* Ks[6]; int n = 0;
+            for (int j = 0; j < tb.S; ++j) if (tb.b[j] != 0.f) { coef[n] = dt * tb.b[j]; Ks[n] = w.Kst[j]; ++n; }
+            ST_LAUNCH(launch_lincomb(w.xt.f32, w.xt.f32, Ks, coef, n, numel, s));
+        }
+    }
+    ST_LAUNCH(launch_btc_to_bct(w.xt.f32, z_inout, B, d.n_mel, T, s));
+    return 0;
+}
+
+int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const float* mask_host, const float* c_host,
+                  const float* fake_content_host, const float* fake_speaker_host, float cfg_strength,
+                  const float* t_span_host, int n_steps, int method, int B, int T, void* stream) {
+    if (check_common(h, B, T)) return 1;
+    if (!z_inout_host || !mu_host || !mask_host || !c_host) return fail(h, "st_solve_host: null pointer");
+    const int cfg = (fake_content_host && fake_speaker_host) ? 1 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    Workspace w;
+    if (ensure_ws(h, w, B, T, cfg)) return 1;
+    const st_dims& d = h->d;
+    const size_t n = (size_t)B * T * d.n_mel;
+    ST_CUDA(cudaMemcpyAsync(w.h_z, z_inout_host, n * 4, cudaMemcpyHostToDevice, s));
+    ST_CUDA(cudaMemcpyAsync(w.h_mu, mu_host, n * 4, cudaMemcpyHostToDevice, s));
+    ST_CUDA(cudaMemcpyAsync(w.h_mask, mask_host, (size_t)B * T * 4, cudaMemcpyHostToDevice, s));
+    ST_CUDA(cudaMemcpyAsync(w.h_c, c_host, (size_t)B * d.gin * 4, cudaMemcpyHostToDevice, s));
+    if (cfg) {
+        ST_CUDA(cudaMemcpyAsync(w.h_fc, fake_content_host, (size_t)d.n_mel * 4, cudaMemcpyHostToDevice, s));
+        ST_CUDA(cudaMemcpyAsync(w.h_fs, fake_speaker_host, (size_t)d.gin * 4, cudaMemcpyHostToDevice, s));
+    }
+    if (st_solve(h, w.h_z, w.h_mu, w.h_mask, w.h_c, cfg ? w.h_fc : nullptr, cfg ? w.h_fs : nullptr, cfg_strength, t_span_host,
+                 n_steps, method, B, T, stream))
+        return 1;
+    ST_CUDA(cudaMemcpyAsync(z_inout_host, w.h_z, n * 4, cudaMemcpyDeviceToHost, s));
+    ST_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ---- kernel-level test hooks ------------------------------------------------------------------------
+int st_test_conv(st_handle* h, const float* x, const float* wgt, const float* bias, float* out, int B, int Cin, int Cout,
+                 int T, int k, void* stream) {
+    if (!h) return 1;
+    ST_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool tc = h->engine == ST_ENGINE_TCGEN05;
+    const size_t nx = (size_t)B * T * Cin, nw = (size_t)k * Cout * Cin, no = (size_t)B * T * Cout;
+    float *xt, *wp, *ot; bf16 *xh, *xl, *wh, *wl;
+    ST_CUDA(cudaMalloc(&xt, nx * 4)); ST_CUDA(cudaMalloc(&wp, nw * 4)); ST_CUDA(cudaMalloc(&ot, no * 4));
+    ST_CUDA(cudaMalloc(&xh, nx * 2)); ST_CUDA(cudaMalloc(&xl, nx * 2)); ST_CUDA(cudaMalloc(&wh, nw * 2)); ST_CUDA(cudaMalloc(&wl, nw * 2));
+    int rc = 0;
+    do {
+        if (launch_bct_to_btc(x, xt, xh, xl, B, Cin, T, nullptr, s) != cudaSuccess) { rc = fail(h, "transpose failed"); break; }
+        long total = (long)k * Cout * Cin;
+        pack_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wgt, wp, Cout, Cin, k, Cout, 0, 0, Cin);
+        if (launch_split(wp, wh, wl, (long)nw, s) != cudaSuccess) { rc = fail(h, "split failed"); break; }
+        GemmArgs g;
+        g.BB = B; g.T = T; g.a_bmod = B; g.B = B; g.resid_clamp = B - 1; g.flags = bias ? EPI_BIAS : 0;
+        GemmW w; w.f32 = wp; w.hi = wh; w.lo = wl; w.bias = const_cast<float*>(bias); w.taps = k; w.N = Cout; w.K = Cin;
+        Act a; a.C = Cin; a.f32 = xt; a.hi = tc ? xh : nullptr; a.lo = tc ? xl : nullptr;
+        Act o; o.C = Cout; o.f32 = ot;
+        if (run_gemm(h, g, w, &a, nullptr, o, s)) { rc = 1; break; }
+        if (launch_btc_to_bct(ot, out, B, Cout, T, s) != cudaSuccess) { rc = fail(h, "transpose failed"); break; }
+    } while (0);
+    cudaStreamSynchronize(s);
+    cudaError_t e = cudaGetLastError();
+    if (!rc && e != cudaSuccess) rc = fail(h, std::string("st_test_conv: ") + cudaGetErrorString(e));
+    cudaFree(xt); cudaFree(wp); cudaFree(ot); cudaFree(xh); cudaFree(xl); cudaFree(wh); cudaFree(wl);
+    return rc;
+}
+
+int st_test_gemm(st_handle* h, const float* A, const float* W, const float* bias, float* out, int R, int K, int N, int silu,
+                 void* stream) {
+    if (!h) return 1;
+    ST_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool tc = h->engine == ST_ENGINE_TCGEN05;
+    const size_t na = (size_t)R * K, nw = (size_t)N * K;
+    bf16 *ah, *al, *wh, *wl;
+    ST_CUDA(cudaMalloc(&ah, na * 2)); ST_CUDA(cudaMalloc(&al, na * 2)); ST_CUDA(cudaMalloc(&wh, nw * 2)); ST_CUDA(cudaMalloc(&wl, nw * 2));
+    int rc = 0;
+    do {
+        if (launch_split(A, ah, al, (long)na, s) != cudaSuccess || launch_split(W, wh, wl, (long)nw, s) != cudaSuccess) {
+            rc = fail(h, "split failed"); break;
+        }
+        GemmArgs g;   // one "utterance" of R frames
+        g.BB = 1; g.T = R; g.a_bmod = 1; g.B = 1; g.resid_clamp = 0; g.flags = (bias ? EPI_BIAS : 0) | (silu ? EPI_SILU : 0);
+        GemmW w; w.f32 = const_cast<float*>(W); w.hi = wh; w.lo = wl; w.bias = const_cast<float*>(bias); w.taps = 1; w.N = N; w.K = K;
+        Act a; a.C = K; a.f32 = const_cast<float*>(A); a.hi = tc ? ah : nullptr; a.lo = tc ? al : nullptr;
+        Act o; o.C = N; o.f32 = out;
+        if (run_gemm(h, g, w, &a, nullptr, o, s)) { rc = 1; break; }
+    } while (0);
+    cudaStreamSynchronize(s);
+    cudaError_t e = cudaGetLastError();
+    if (!rc && e != cudaSuccess) rc = fail(h, std::string("st_test_gemm: ") + cudaGetErrorString(e));
+    cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl);
+    return rc;
+}
+
+int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* out, int B, int T, void* stream) {
+    if (!h) return 1;
+    ST_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int* kvlen; float* cs;
+    ST_CUDA(cudaMalloc(&kvlen, sizeof(int) * B)); ST_CUDA(cudaMalloc(&cs, sizeof(float) * T * 32));
+    int rc = 0;
+    do {
+        if (launch_mask_lengths(mask, kvlen, B, T, s) != cudaSuccess || launch_rope_table(cs, T, 32, s) != cudaSuccess) {
+            rc = fail(h, "attention prep failed"); break;
+        }
+        AttnArgs a;
+        a.qkv = qkv; a.rope_cs = cs; a.mask = mask; a.kvlen = kvlen; a.out_f32 = out;
+        a.BB = B; a.B = B; a.T = T; a.H = h->d.hidden; a.n_heads = h->d.n_heads;
+        if (launch_attention_simt(a, s) != cudaSuccess) { rc = fail(h, "attention launch failed"); break; }
+    } while (0);
+    cudaStreamSynchronize(s);
+    cudaError_t e = cudaGetLastError();
+    if (!rc && e != cudaSuccess) rc = fail(h, std::string("st_test_attention: ") + cudaGetErrorString(e));
+    cudaFree(kvlen); cudaFree(cs);
+    return rc;
+}
+
+}  // extern "C"

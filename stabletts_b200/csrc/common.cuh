@@ -1,0 +1,129 @@
+// Shared declarations for libstabletts_b200.so (sm_100a only).
+//
+// Internal data layout: every activation is TOKEN-MAJOR (B, T, C) with C contiguous — one mel
+// frame is one GEMM row — while the C-ABI boundary keeps the reference's channel-major (B, C, T).
+// Tensor-core GEMM operands are carried as split-bf16 plane pairs (hi = bf16(x), lo = bf16(x - hi))
+// because plain bf16 operands cannot meet the 1e-3 parity bar.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/stabletts_b200.h"
+
+namespace st {
+
+typedef __nv_bfloat16 bf16;
+
+// ----------------------------------------------------------------------------------------------
+// conv-GEMM problem:  out[bb, t, n] = epi( sum_{tap, src, k} A_src[bb % a_bmod, t + tap - taps/2, k]
+//                                                          * W[tap][n][koff_src + k] )
+// rows outside [0, T) read as zero (the reference's Conv1d zero padding at TENSOR edges).
+// ----------------------------------------------------------------------------------------------
+enum : int {
+    EPI_BIAS  = 1 << 0,   // v += bias[n]
+    EPI_SILU  = 1 << 1,   // v = v * sigmoid(v)
+    EPI_FILM  = 1 << 2,   // v = gamma[n] * v + beta[n]
+    EPI_MASK  = 1 << 3,   // v *= mask[bb % B, t]
+    EPI_GATE  = 1 << 4,   // v *= gate[min(bb, c_clamp), n]
+    EPI_RESID = 1 << 5,   // v += resid[min(bb, resid_clamp), t, n]
+    EPI_ROPE  = 1 << 6,   // partial RoPE on q/k column blocks (QKV projection only; TC engine)
+};
+
+struct GemmArgs {
+    // A: n_src sources concatenated along channels, each (a_batches, T, Cs[i]) token-major.
+    const float* A_f32[2] = {nullptr, nullptr};   // SIMT engine
+    const bf16*  A_hi[2]  = {nullptr, nullptr};   // tcgen05 engine: split planes
+    const bf16*  A_lo[2]  = {nullptr, nullptr};
+    int Cs[2] = {0, 0};
+    int n_src = 1;
+    int a_bmod = 0;                               // A batch index = bb % a_bmod
+    // W: packed [taps][N][Ktot], K contiguous
+    const float* W_f32 = nullptr;
+    const bf16*  W_hi = nullptr;
+    const bf16*  W_lo = nullptr;
+    const float* bias = nullptr;
+    int taps = 1, N = 0, Ktot = 0;
+    int BB = 0, T = 0;
+    // epilogue
+    int flags = 0;
+    const float* mask = nullptr; int B = 1;       // (B, T)
+    const float* film = nullptr; long film_bstride = 0; int film_H = 0;   // gamma[n], beta[film_H + n]
+    const float* gate = nullptr; long gate_bstride = 0; int c_clamp = 0;
+    const float* resid = nullptr; int resid_clamp = 0;
+    const float* rope_cs = nullptr;               // (T, 16, 2) cos/sin table (EPI_ROPE)
+    float* out_f32 = nullptr;
+    bf16*  out_hi = nullptr;
+    bf16*  out_lo = nullptr;
+};
+
+// engines
+cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t s);
+// returns cudaErrorNotSupported if the tensor-map driver entry point is unavailable
+cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s);
+const char* gemm_tc_last_error();
+
+// ----------------------------------------------------------------------------------------------
+// elementwise / reduction kernels (elementwise.cu)
+// ----------------------------------------------------------------------------------------------
+// (B, C, T) -> (B', T, C) with optional extra broadcast row: if bcast != null, batch index B is
+// filled with bcast[c] for every t (the CFG fake_content, models/flow_matching.py:60).
+cudaError_t launch_bct_to_btc(const float* in, float* out_f32, bf16* out_hi, bf16* out_lo, int B, int C, int T,
+                              const float* bcast, cudaStream_t s);
+cudaError_t launch_btc_to_bct(const float* in, float* out, int B, int C, int T, cudaStream_t s);
+
+struct LnArgs {
+    const float* xin = nullptr;   // (BB, T, H)
+    float* xout = nullptr;        // residual stream written when has_film (may alias xin)
+    const float* film = nullptr; long film_bstride = 0;     // gamma[0..H), beta[H..2H)
+    const float* shift = nullptr; const float* scale = nullptr; long ada_bstride = 0; int c_clamp = 0;
+    const float* mask = nullptr; int B = 1;
+    int has_film = 0;             // x = (gamma*xin+beta)*mask  (models/estimator.py:16)
+    int mask_out = 0;             // u *= mask (FFN input, models/diffusion_transformer.py:26)
+    float* u_f32 = nullptr; bf16* u_hi = nullptr; bf16* u_lo = nullptr;
+    int BB = 0, T = 0, H = 0;
+};
+cudaError_t launch_film_ln_mod(const LnArgs& a, cudaStream_t s);
+
+// y[r * y_rstride + n] = post( bias[n] + sum_k pre(x[r, k]) * W[n, k] ),  pre/post in {none, silu}
+cudaError_t launch_gemv(const float* x, const float* W, const float* bias, float* y, long y_rstride, int R, int K, int N,
+                        int silu_in, int silu_out, cudaStream_t s);
+// sinusoidal embedding of n_t times (models/estimator.py:41-49): out (n_t, H)
+cudaError_t launch_time_embed(const float* t, int n_t, int H, float* out, cudaStream_t s);
+// cos/sin table (T, 16, 2) of models/diffusion_transformer.py:150-171 with d = 32
+cudaError_t launch_rope_table(float* cs, int T, int d_rot, cudaStream_t s);
+// kv_len[b] = 1 + last index with mask != 0 (0 if none)
+cudaError_t launch_mask_lengths(const float* mask, int* kvlen, int B, int T, cudaStream_t s);
+// K_out = uncond + s*(cond - uncond) (models/flow_matching.py:66) or copy when !cfg
+cudaError_t launch_cfg_combine(const float* V, float* K_out, int B, long per_batch, int cfg, float s_cfg, cudaStream_t s);
+// dst = y + sum_i coef[i] * K[i]   (n <= 6)
+cudaError_t launch_lincomb(float* dst, const float* y, const float* const* K, const float* coef, int n, long numel,
+                           cudaStream_t s);
+// fp32 -> split bf16 planes
+cudaError_t launch_split(const float* in, bf16* hi, bf16* lo, long numel, cudaStream_t s);
+
+// ----------------------------------------------------------------------------------------------
+// attention (attention.cu): qkv (BB, T, 3H) fp32 -> out (BB, T, H); partial RoPE fused on load.
+// ----------------------------------------------------------------------------------------------
+struct AttnArgs {
+    const float* qkv = nullptr;
+    const float* rope_cs = nullptr;   // (T, 16, 2)
+    const float* mask = nullptr;      // (B, T)
+    const int* kvlen = nullptr;       // (B)
+    float* out_f32 = nullptr; bf16* out_hi = nullptr; bf16* out_lo = nullptr;
+    int BB = 0, B = 1, T = 0, H = 0, n_heads = 0;
+};
+cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t s);
+
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+}  // namespace st

@@ -1,0 +1,301 @@
+// HBM-bound glue kernels of the CFM/DiT path: layout changes at the boundary, mask·FiLM →
+// LayerNorm → adaLN-modulate (one pass, warp-shuffle reductions), tiny GEMVs for the
+// t-/c-conditioning vectors, CFG combine and Runge–Kutta linear combinations.
+#include "common.cuh"
+
+namespace st {
+
+// ---------------------------------------------------------------------------------------------
+// (B, C, T) <-> (B, T, C) tiled transposes (32x32 smem tile, +1 padding: conflict-free)
+// ---------------------------------------------------------------------------------------------
+__global__ void bct_to_btc_kernel(const float* __restrict__ in, float* __restrict__ out_f32, bf16* __restrict__ out_hi,
+                                  bf16* __restrict__ out_lo, int B, int C, int T, const float* __restrict__ bcast) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const bool is_bcast = (b == B);
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, t = t0 + threadIdx.x;
+        float v = 0.f;
+        if (c < C && t < T) v = is_bcast ? bcast[c] : in[((long)b * C + c) * T + t];
+        tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int t = t0 + i, c = c0 + threadIdx.x;
+        if (c < C && t < T) {
+            float v = tile[threadIdx.x][i];
+            long o = ((long)b * T + t) * C + c;
+            if (out_f32) out_f32[o] = v;
+            if (out_hi) { bf16 h, l; split_bf16(v, h, l); out_hi[o] = h; out_lo[o] = l; }
+        }
+    }
+}
+
+cudaError_t launch_bct_to_btc(const float* in, float* out_f32, bf16* out_hi, bf16* out_lo, int B, int C, int T,
+                              const float* bcast, cudaStream_t s) {
+    dim3 grid((T + 31) / 32, (C + 31) / 32, B + (bcast ? 1 : 0)), block(32, 8);
+    bct_to_btc_kernel<<<grid, block, 0, s>>>(in, out_f32, out_hi, out_lo, B, C, T, bcast);
+    return cudaGetLastError();
+}
+
+__global__ void btc_to_bct_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int T) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int t = t0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && t < T) ? in[((long)b * T + t) * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, t = t0 + threadIdx.x;
+        if (c < C && t < T) out[((long)b * C + c) * T + t] = tile[threadIdx.x][i];
+    }
+}
+
+cudaError_t launch_btc_to_bct(const float* in, float* out, int B, int C, int T, cudaStream_t s) {
+    dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    btc_to_bct_kernel<<<grid, block, 0, s>>>(in, out, B, C, T);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// mask·FiLM → LayerNorm(C, no affine, eps 1e-5) → modulate.   One warp per frame (row); H = 256
+// → 8 channels per lane as two float4; mean / variance by warp shuffles (two-pass, in registers).
+// Reference: models/estimator.py:16,30-33 (FiLM), models/diffusion_transformer.py:106,111-112,
+// 119-121 (x*mask, LN, modulate), :26 (FFN input mask).
+// ---------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(256) film_ln_mod_kernel(LnArgs a) {
+    constexpr int V = H / 32;          // channels per lane
+    static_assert(V % 4 == 0, "H must be a multiple of 128");
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long rows = (long)a.BB * a.T;
+    if (warp >= rows) return;
+    const int bb = warp / a.T, t = warp - bb * a.T;
+    const float m = a.mask[(long)(bb % a.B) * a.T + t];
+    const int cb = min(bb, a.c_clamp);
+    const float* xr = a.xin + (long)warp * H;
+    float x[V];
+#pragma unroll
+    for (int j = 0; j < V / 4; ++j) {
+        float4 v = *reinterpret_cast<const float4*>(xr + (j * 32 + lane) * 4);
+        x[j * 4 + 0] = v.x; x[j * 4 + 1] = v.y; x[j * 4 + 2] = v.z; x[j * 4 + 3] = v.w;
+    }
+    if (a.has_film) {
+        const float* f = a.film + (long)(bb % a.B) * a.film_bstride;
+#pragma unroll
+        for (int j = 0; j < V / 4; ++j) {
+            int c = (j * 32 + lane) * 4;
+            float4 g = *reinterpret_cast<const float4*>(f + c);
+            float4 be = *reinterpret_cast<const float4*>(f + H + c);
+            x[j * 4 + 0] = (g.x * x[j * 4 + 0] + be.x) * m;
+            x[j * 4 + 1] = (g.y * x[j * 4 + 1] + be.y) * m;
+            x[j * 4 + 2] = (g.z * x[j * 4 + 2] + be.z) * m;
+            x[j * 4 + 3] = (g.w * x[j * 4 + 3] + be.w) * m;
+        }
+        float* xo = a.xout + (long)warp * H;
+#pragma unroll
+        for (int j = 0; j < V / 4; ++j)
+            *reinterpret_cast<float4*>(xo + (j * 32 + lane) * 4) =
+                make_float4(x[j * 4 + 0], x[j * 4 + 1], x[j * 4 + 2], x[j * 4 + 3]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) sum += x[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / H);
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) { float d = x[j] - mean; var += d * d; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var * (1.0f / H) + 1e-5f);
+    const float* sh = a.shift + (long)cb * a.ada_bstride;
+    const float* sc = a.scale + (long)cb * a.ada_bstride;
+    const float mo = a.mask_out ? m : 1.0f;
+#pragma unroll
+    for (int j = 0; j < V / 4; ++j) {
+        int c = (j * 32 + lane) * 4;
+        float4 s4 = *reinterpret_cast<const float4*>(sh + c);
+        float4 c4 = *reinterpret_cast<const float4*>(sc + c);
+        float u0 = ((x[j * 4 + 0] - mean) * rstd * (1.f + c4.x) + s4.x) * mo;
+        float u1 = ((x[j * 4 + 1] - mean) * rstd * (1.f + c4.y) + s4.y) * mo;
+        float u2 = ((x[j * 4 + 2] - mean) * rstd * (1.f + c4.z) + s4.z) * mo;
+        float u3 = ((x[j * 4 + 3] - mean) * rstd * (1.f + c4.w) + s4.w) * mo;
+        long o = (long)warp * H + c;
+        if (a.u_f32) *reinterpret_cast<float4*>(a.u_f32 + o) = make_float4(u0, u1, u2, u3);
+        if (a.u_hi) {
+            bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+            split_bf16(u0, h0, l0); split_bf16(u1, h1, l1); split_bf16(u2, h2, l2); split_bf16(u3, h3, l3);
+            __nv_bfloat162 hp0 = __halves2bfloat162(h0, h1), hp1 = __halves2bfloat162(h2, h3);
+            __nv_bfloat162 lp0 = __halves2bfloat162(l0, l1), lp1 = __halves2bfloat162(l2, l3);
+            uint2 hv, lv;
+            hv.x = *reinterpret_cast<uint32_t*>(&hp0); hv.y = *reinterpret_cast<uint32_t*>(&hp1);
+            lv.x = *reinterpret_cast<uint32_t*>(&lp0); lv.y = *reinterpret_cast<uint32_t*>(&lp1);
+            *reinterpret_cast<uint2*>(a.u_hi + o) = hv;
+            *reinterpret_cast<uint2*>(a.u_lo + o) = lv;
+        }
+    }
+}
+
+cudaError_t launch_film_ln_mod(const LnArgs& a, cudaStream_t s) {
+    if (a.H != 256) return cudaErrorInvalidValue;
+    long rows = (long)a.BB * a.T;
+    if (rows == 0) return cudaSuccess;
+    int blocks = (int)((rows * 32 + 255) / 256);
+    film_ln_mod_kernel<256><<<blocks, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// small GEMV batch: one warp per (row r, output n)
+// ---------------------------------------------------------------------------------------------
+__global__ void gemv_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                            float* __restrict__ y, long y_rstride, int R, int K, int N, int silu_in, int silu_out) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= R * N) return;
+    const int r = gw / N, n = gw - r * N;
+    const float* xr = x + (long)r * K;
+    const float* wr = W + (long)n * K;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        float xv = xr[k];
+        if (silu_in) xv = xv / (1.0f + expf(-xv));
+        acc = fmaf(xv, wr[k], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        float v = acc + (bias ? bias[n] : 0.f);
+        if (silu_out) v = v / (1.0f + expf(-v));
+        y[(long)r * y_rstride + n] = v;
+    }
+}
+
+cudaError_t launch_gemv(const float* x, const float* W, const float* bias, float* y, long y_rstride, int R, int K, int N,
+                        int silu_in, int silu_out, cudaStream_t s) {
+    long warps = (long)R * N;
+    if (warps == 0) return cudaSuccess;
+    int blocks = (int)((warps * 32 + 255) / 256);
+    gemv_kernel<<<blocks, 256, 0, s>>>(x, W, bias, y, y_rstride, R, K, N, silu_in, silu_out);
+    return cudaGetLastError();
+}
+
+// models/estimator.py:41-49: emb = 1000 * t * exp(-i * ln(1e4)/(half-1)); cat(sin, cos)
+__global__ void time_embed_kernel(const float* __restrict__ t, int n_t, int H, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int half = H / 2;
+    if (i >= n_t * half) return;
+    int r = i / half, j = i - r * half;
+    float step = (float)(9.210340371976184 / (double)(half - 1));     // ln(10000)/(half-1)
+    float w = expf((float)j * -step);
+    float e = 1000.0f * t[r] * w;
+    out[(long)r * H + j] = sinf(e);
+    out[(long)r * H + half + j] = cosf(e);
+}
+
+cudaError_t launch_time_embed(const float* t, int n_t, int H, float* out, cudaStream_t s) {
+    int n = n_t * (H / 2);
+    time_embed_kernel<<<(n + 127) / 128, 128, 0, s>>>(t, n_t, H, out);
+    return cudaGetLastError();
+}
+
+// models/diffusion_transformer.py:157-171: theta_i = 1/base^(2i/d); angle = pos * theta_i
+__global__ void rope_table_kernel(float* __restrict__ cs, int T, int d_rot) {
+    int half = d_rot / 2;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * half) return;
+    int pos = i / half, j = i - pos * half;
+    float theta = 1.0f / powf(10000.0f, (float)(2 * j) / (float)d_rot);
+    float ang = (float)pos * theta;
+    cs[(long)i * 2 + 0] = (float)cos((double)ang);
+    cs[(long)i * 2 + 1] = (float)sin((double)ang);
+}
+
+cudaError_t launch_rope_table(float* cs, int T, int d_rot, cudaStream_t s) {
+    int n = T * (d_rot / 2);
+    if (n == 0) return cudaSuccess;
+    rope_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(cs, T, d_rot);
+    return cudaGetLastError();
+}
+
+__global__ void mask_lengths_kernel(const float* __restrict__ mask, int* __restrict__ kvlen, int B, int T) {
+    int b = blockIdx.x;
+    int best = 0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x)
+        if (mask[(long)b * T + t] != 0.f) best = max(best, t + 1);
+    __shared__ int red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (threadIdx.x == 0) kvlen[b] = v;
+    }
+}
+
+cudaError_t launch_mask_lengths(const float* mask, int* kvlen, int B, int T, cudaStream_t s) {
+    mask_lengths_kernel<<<B, 256, 0, s>>>(mask, kvlen, B, T);
+    return cudaGetLastError();
+}
+
+__global__ void cfg_combine_kernel(const float* __restrict__ V, float* __restrict__ K, long n, int cfg, float s_cfg) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float c = V[i];
+    if (cfg) { float u = V[n + i]; c = u + s_cfg * (c - u); }
+    K[i] = c;
+}
+
+cudaError_t launch_cfg_combine(const float* V, float* K_out, int B, long per_batch, int cfg, float s_cfg, cudaStream_t s) {
+    long n = (long)B * per_batch;
+    if (n == 0) return cudaSuccess;
+    cfg_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(V, K_out, n, cfg, s_cfg);
+    return cudaGetLastError();
+}
+
+struct LinArgs { const float* K[6]; float coef[6]; int n; };
+
+__global__ void lincomb_kernel(float* __restrict__ dst, const float* __restrict__ y, LinArgs a, long numel) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numel) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) if (j < a.n) acc = fmaf(a.coef[j], a.K[j][i], acc);
+    dst[i] = y[i] + acc;
+}
+
+cudaError_t launch_lincomb(float* dst, const float* y, const float* const* K, const float* coef, int n, long numel,
+                           cudaStream_t s) {
+    if (n > 6) return cudaErrorInvalidValue;
+    if (numel == 0) return cudaSuccess;
+    LinArgs a;
+    for (int j = 0; j < 6; ++j) { a.K[j] = j < n ? K[j] : nullptr; a.coef[j] = j < n ? coef[j] : 0.f; }
+    a.n = n;
+    lincomb_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, s>>>(dst, y, a, numel);
+    return cudaGetLastError();
+}
+
+__global__ void split_kernel(const float* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bf16 h, l;
+    split_bf16(in[i], h, l);
+    hi[i] = h; lo[i] = l;
+}
+
+cudaError_t launch_split(const float* in, bf16* hi, bf16* lo, long numel, cudaStream_t s) {
+    if (numel == 0) return cudaSuccess;
+    split_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, s>>>(in, hi, lo, numel);
+    return cudaGetLastError();
+}
+
+}  // namespace st

@@ -1,0 +1,99 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the drop-in modules expose the reference's parameter inventory, and there is no CPU
+fallback (everything raises off-GPU)."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import weights
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    from stabletts_b200 import _lib
+    return _lib
+
+
+def test_library_exports_header_symbols(built):
+    lib = built.load_library()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "stabletts_b200.h")).read()
+    declared = set(re.findall(r"\b(st_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(built.EXPORTS), declared ^ set(built.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.st_version() >= 100
+
+
+def test_create_fails_loudly_without_gpu(built):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ctypes as C
+    lib = built.load_library()
+    dims = built.StDims(80, 256, 1024, 4, 6, 3, 256)
+    h = C.c_void_p()
+    assert lib.st_create(C.byref(dims), 0, C.byref(h)) != 0
+    assert b"no CUDA device" in lib.st_last_error(None)
+
+
+def test_state_dict_matches_reference_inventory(built):
+    from stabletts_b200 import CFMDecoder
+    for n_mel, total in ((80, 20_174_928), (128, 20_347_008)):
+        m = CFMDecoder(n_mel, n_mel, 256, n_mel, 1024, 4, 6, 3, 0.1, 256)
+        sd = m.state_dict()
+        ref = weights.estimator_param_shapes(n_mel)
+        assert list(sd.keys()) == ["estimator." + k for k in ref]
+        assert all(tuple(sd["estimator." + k].shape) == v for k, v in ref.items())
+        assert sum(v.numel() for v in sd.values()) == total
+        m.estimator.load_state_dict(weights.make_state(0, n_mel), strict=True)
+        # adaLN-zero init of the reference (models/estimator.py:98-101)
+        fresh = CFMDecoder(n_mel, n_mel, 256, n_mel, 1024, 4, 6, 3, 0.1, 256)
+        assert float(fresh.state_dict()["estimator.blocks.0.block.adaLN_modulation.2.weight"].abs().max()) == 0.0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout only in the authoring container")
+def test_state_dict_keys_equal_live_reference(built):
+    import sys
+    sys.path.insert(0, "/root/reference")
+    from models.estimator import Decoder as RefDecoder
+    from stabletts_b200 import Decoder
+    a = RefDecoder(80, 80, 256, 80, 1024, 0.1, 6, 4, 3, 256).state_dict()
+    b = Decoder(80, 80, 256, 80, 1024, 0.1, 6, 4, 3, 256).state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape for k in a)
+
+
+def test_no_cpu_fallback(built):
+    from stabletts_b200 import CFMDecoder
+    m = CFMDecoder(80, 80, 256, 80, 1024, 4, 6, 3, 0.1, 256).eval()
+    inp = weights.make_inputs(1, [8], 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.estimator(inp["t"], inp["x"], inp["mask"], inp["mu"], inp["c"])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(inp["mu"], inp["mask"], 2, 1.0, inp["c"], "euler")
+    with pytest.raises(NotImplementedError):
+        m.compute_loss(inp["x"], inp["mask"], inp["mu"], inp["c"])
+
+
+def test_solver_names():
+    from stabletts_b200.flow_matching import _method_id
+    from stabletts_b200 import _lib
+    assert _method_id("euler") == _lib.ST_EULER and _method_id("midpoint") == _lib.ST_MIDPOINT
+    assert _method_id("rk4") == _lib.ST_RK4
+    with pytest.warns(UserWarning):
+        assert _method_id(None) == _lib.ST_DOPRI5_FIXED
+    with pytest.raises(ValueError):
+        _method_id("bosh3")
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "stabletts_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
