@@ -106,6 +106,14 @@ int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const
 /* Number of kernels this library launched since the handle was created (bench.py gpu_launches). */
 int64_t st_launch_count(const st_handle* h);
 
+/* Per-kernel-class CUDA-event profiling (bench.py's roofline): between begin and end every launch of
+ * the listed classes is bracketed by events on the launching stream.  st_profile_end synchronises
+ * the device and fills four arrays of ST_PROF_NCAT entries: summed milliseconds, algorithmic FLOPs,
+ * algorithmic bytes and launch counts per class. */
+enum { ST_PROF_GEMM = 0, ST_PROF_ATTN = 1, ST_PROF_LN = 2, ST_PROF_NCAT = 3 };
+int st_profile_begin(st_handle* h);
+int st_profile_end(st_handle* h, double* ms, double* flops, double* bytes, int64_t* launches);
+
 /* ---- kernel-level test hooks (used by tests/ only; same kernels the path uses) ------------- */
 
 /* out(R,N) = [silu]( A(R,K)·W(N,K)^T + bias ) through the selected engine's conv-GEMM with

@@ -9,12 +9,13 @@ _LIB = None
 
 ST_EULER, ST_MIDPOINT, ST_RK4, ST_DOPRI5_FIXED = 0, 1, 2, 3
 ST_ENGINE_TCGEN05, ST_ENGINE_SIMT = 0, 1
+ST_PROF_GEMM, ST_PROF_ATTN, ST_PROF_LN, ST_PROF_NCAT = 0, 1, 2, 3
 
 # every symbol include/stabletts_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "st_create", "st_destroy", "st_last_error", "st_version", "st_load_weight", "st_finalize_weights",
     "st_set_engine", "st_workspace_bytes", "st_attach_workspace", "st_estimator_forward", "st_solve",
-    "st_solve_host", "st_launch_count", "st_test_gemm", "st_test_conv", "st_test_attention",
+    "st_solve_host", "st_launch_count", "st_profile_begin", "st_profile_end", "st_test_gemm", "st_test_conv", "st_test_attention",
 ]
 
 
@@ -54,6 +55,8 @@ def load_library() -> C.CDLL:
     lib.st_solve_host.argtypes = lib.st_solve.argtypes
     lib.st_launch_count.argtypes = [vp]
     lib.st_launch_count.restype = i64
+    lib.st_profile_begin.argtypes = [vp]
+    lib.st_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.st_test_gemm.argtypes = [vp, f32p, f32p, f32p, f32p, i32, i32, i32, i32, vp]
     lib.st_test_conv.argtypes = [vp, f32p, f32p, f32p, f32p, i32, i32, i32, i32, i32, vp]
     lib.st_test_attention.argtypes = [vp, f32p, f32p, f32p, i32, i32, vp]

@@ -71,6 +71,15 @@ struct st_handle {
     std::vector<void*> owned;
     void* ws_ptr = nullptr; size_t ws_bytes = 0; bool ws_owned = false;
     int64_t launches = 0;
+    // optional per-launch CUDA-event profiling (bench.py roofline): category, flops, bytes, event pair
+    bool prof_on = false;
+    struct ProfRec { int cat; double flops, bytes; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+    cudaEvent_t take_event() {
+        if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+        return ev_pool[ev_used++];
+    }
 };
 
 namespace {
@@ -92,6 +101,16 @@ int fail(st_handle* h, const std::string& msg) {
     } while (0)
 
 #define ST_LAUNCH(call) do { h->launches++; ST_CUDA(call); } while (0)
+
+// profiled launch: brackets `call` with events on the launching stream when profiling is enabled
+#define ST_LAUNCH_P(cat, flops_, bytes_, s_, call)                                             \
+    do {                                                                                      \
+        st_handle::ProfRec pr__{cat, (double)(flops_), (double)(bytes_), nullptr, nullptr};   \
+        if (h->prof_on) { pr__.e0 = h->take_event(); pr__.e1 = h->take_event(); cudaEventRecord(pr__.e0, s_); } \
+        h->launches++;                                                                        \
+        ST_CUDA(call);                                                                        \
+        if (h->prof_on) { cudaEventRecord(pr__.e1, s_); h->prof.push_back(pr__); }            \
+    } while (0)
 
 // ----- weight packing ---------------------------------------------------------------------------
 // in: (Nsrc, Csrc, k) reference Conv1d / Linear layout -> out[tap][n_off + n][c] for c in [c_off, c_off+Cc)
@@ -243,6 +262,9 @@ int run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const Act
     g.taps = w.taps; g.N = w.N; g.Ktot = w.K;
     g.out_f32 = out.f32; g.out_hi = out.hi; g.out_lo = out.lo;
     if (out.C != w.N) return fail(h, "internal: GEMM N mismatch");
+    st_handle::ProfRec pr{ST_PROF_GEMM, 2.0 * g.BB * g.T * (double)g.N * g.Ktot * g.taps,
+                          (double)g.BB * g.T * ((double)g.Ktot * 4 + (double)g.N * ((out.f32 ? 4 : 0) + (out.hi ? 4 : 0))), nullptr, nullptr};
+    if (h->prof_on) { pr.e0 = h->take_event(); pr.e1 = h->take_event(); cudaEventRecord(pr.e0, s); }
     h->launches++;
     if (tc) {
         cudaError_t e = launch_gemm_tc(g, h->num_sms, s);
@@ -251,6 +273,7 @@ int run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const Act
         cudaError_t e = launch_gemm_simt(g, s);
         if (e != cudaSuccess) return fail(h, std::string("SIMT GEMM launch failed: ") + cudaGetErrorString(e));
     }
+    if (h->prof_on) { cudaEventRecord(pr.e1, s); h->prof.push_back(pr); }
     return 0;
 }
 
@@ -336,7 +359,7 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
         }
         ln.shift = ada_l; ln.scale = ada_l + H;
         ln.u_f32 = w.U.f32; ln.u_hi = w.U.hi; ln.u_lo = w.U.lo;
-        ST_LAUNCH(launch_film_ln_mod(ln, s));
+        ST_LAUNCH_P(ST_PROF_LN, 0, (double)w.BB * w.T * H * (4 + (ln.has_film ? 4 : 0) + 4), s, launch_film_ln_mod(ln, s));
         {   // q,k,v projections as one N=3H GEMM (models/diffusion_transformer.py:59-61)
             GemmArgs g = base(EPI_BIAS);
             if (run_gemm(h, g, h->qkv[l], &w.U, nullptr, w.QKV, s)) return 1;
@@ -346,7 +369,7 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
             a.qkv = w.QKV.f32; a.rope_cs = w.rope_cs; a.mask = mask; a.kvlen = w.kvlen;
             a.out_f32 = w.AO.f32; a.out_hi = w.AO.hi; a.out_lo = w.AO.lo;
             a.BB = w.BB; a.B = w.B; a.T = w.T; a.H = H; a.n_heads = d.n_heads;
-            ST_LAUNCH(launch_attention_simt(a, s));
+            ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_simt(a, s));
         }
         {   // x += gate_msa * conv_o(attn) * mask   (:65, :111)
             GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
@@ -358,7 +381,7 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
             LnArgs l2 = ln;
             l2.xin = w.X[xb].f32; l2.xout = nullptr; l2.has_film = 0; l2.mask_out = 1;
             l2.shift = ada_l + 3 * H; l2.scale = ada_l + 4 * H;
-            ST_LAUNCH(launch_film_ln_mod(l2, s));
+            ST_LAUNCH_P(ST_PROF_LN, 0, (double)w.BB * w.T * H * 8, s, launch_film_ln_mod(l2, s));
         }
         {   // conv_1 + SiLU, (h * mask) feeds conv_2 (:26-29)
             GemmArgs g = base(EPI_BIAS | EPI_SILU | EPI_MASK);
@@ -449,6 +472,7 @@ int st_destroy(st_handle* h) {
     cudaDeviceSynchronize();
     for (auto& kv : h->raw) cudaFree(kv.second.first);
     for (void* p : h->owned) cudaFree(p);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->ws_ptr && h->ws_owned) cudaFree(h->ws_ptr);
     delete h;
     return 0;
@@ -462,6 +486,27 @@ int st_set_engine(st_handle* h, int engine) {
 }
 
 int64_t st_launch_count(const st_handle* h) { return h ? h->launches : 0; }
+
+int st_profile_begin(st_handle* h) {
+    if (!h) return 1;
+    h->prof.clear(); h->ev_used = 0; h->prof_on = true;
+    return 0;
+}
+
+int st_profile_end(st_handle* h, double* ms, double* flops, double* bytes, int64_t* launches) {
+    if (!h) return 1;
+    h->prof_on = false;
+    ST_CUDA(cudaSetDevice(h->device));
+    ST_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < ST_PROF_NCAT; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+    for (auto& r : h->prof) {
+        float t = 0.f;
+        ST_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms[r.cat] += t; flops[r.cat] += r.flops; bytes[r.cat] += r.bytes; launches[r.cat] += 1;
+    }
+    h->prof.clear(); h->ev_used = 0;
+    return 0;
+}
 
 int st_load_weight(st_handle* h, const char* name, const float* data, int64_t numel, void* stream) {
     if (!h || !name || !data || numel <= 0) return fail(h, "st_load_weight: bad argument");
