@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — mel-frames/sec through the CFM DiT estimator (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg1|cfg2|cfg3|cfg4] [--impl reference]
+
+A "step" is one complete ``CFMDecoder.forward`` ODE solve over one batch of synthetic inputs
+(SURVEY.md §8d): weights = reference-style init under manual_seed(0) with the adaLN gates re-drawn
+N(0, 0.3²); inputs under manual_seed(1); z unmasked; CFG strength 3.
+  value  : frames/s with inputs already resident in HBM (device timed, max over ranks)
+  e2e    : the same metric through the public module call with PINNED HOST inputs — H2D copies of
+           (mu, mask, c, z) and the D2H read of the mel are inside the timed region
+  roofline: the tcgen05 conv-GEMM class (dominant kernel): algorithmic FLOPs / CUDA-event time of
+           every launch in one instrumented solve, against MEASURED_PEAKS.json's sustained bf16 peak
+  cpu_baseline / --impl reference: the oracle port of the reference's PyTorch path on host cores
+           (bounded sample), the only place this file executes anything under oracle/.
+Multi-GPU (torchrun, one rank per GPU): weak scaling, the per-GPU batch is fixed; rank 0 owns the
+global batch, scatters (mu, mask, c, z) and gathers the mel over NCCL inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: per-GPU batch, T, steps, method, cfg, description (BASELINE.json configs[1..4])
+    "cfg1": dict(B=32, T=1000, n_steps=10, method="euler", cfg=3.0, lengths=None,
+                 desc="batch=32/GPU, n_mel=80, T=1000, 10-step Euler + CFG"),
+    "cfg2": dict(B=256, T=500, n_steps=25, method="dopri5_fixed", cfg=None, lengths=None,
+                 desc="batch=256, n_mel=80, T=500, 25 fixed Dormand-Prince steps (6 evals/step, NFE=150), no CFG"),
+    "cfg3": dict(B=128, T=None, n_steps=10, method="euler", cfg=None, lengths="uniform200-2000",
+                 desc="bucketed variable-length batch=128 (T in [200,2000]), 10-step Euler, masked attention"),
+    "cfg4": dict(B=128, T=1000, n_steps=10, method="euler", cfg=3.0, lengths=None,
+                 desc="batch=128/GPU (1024 over 8 GPUs), n_mel=80, T=1000, 10-step Euler + CFG"),
+}
+N_MEL = 80
+NFE_PER_STEP = {"euler": 1, "midpoint": 2, "rk4": 4, "dopri5_fixed": 6}
+
+
+def flops_per_frame_call(T: int, n_mel: int = N_MEL) -> float:
+    """F_call(T) = 32.948e6 + 6144·T for M=80 (2·MAC)."""
+    H, F, L = 256, 1024, 6
+    return 2.0 * ((3 * n_mel * F + 3 * F * F + 3 * F * H) + (n_mel + H) * H + L * (4 * H * H + 2 * T * H + 6 * H * F)
+                  + 3 * (6 * H * H) + H * n_mel)
+
+
+COND_FLOPS = 2.0 * (3 * N_MEL * 1024 + 3 * 1024 * 1024 + 3 * 1024 * 256)    # 8.356 MFLOP/frame, hoistable
+
+
+def make_model(device):
+    from stabletts_b200 import CFMDecoder
+    torch.manual_seed(0)
+    m = CFMDecoder(N_MEL, N_MEL, 256, N_MEL, 1024, 4, 6, 3, 0.1, 256).eval()
+    with torch.no_grad():
+        for i in range(6):
+            node = m.estimator._modules["blocks"]._modules[str(i)]._modules["block"]._modules["adaLN_modulation"]._modules["2"]
+            torch.nn.init.normal_(node.weight, std=0.3)
+            torch.nn.init.normal_(node.bias, std=0.3)
+    return m.to(device) if device is not None else m
+
+
+def make_inputs(cfgd, B, seed=1):
+    """CPU tensors (global generator, manual_seed(seed)) in the reference's boundary layout."""
+    torch.manual_seed(seed)
+    if cfgd["lengths"] is None:
+        T = cfgd["T"]
+        lens = torch.full((B,), T, dtype=torch.long)
+    else:
+        lens = torch.randint(200, 2001, (B,))
+        lens, _ = torch.sort(lens)
+        T = int(lens.max())
+    mask = (torch.arange(T)[None, :] < lens[:, None]).float().unsqueeze(1)
+    mu = torch.randn(B, N_MEL, T) * mask
+    c = torch.randn(B, 256)
+    z = torch.randn(B, N_MEL, T)
+    fs, fc = torch.randn(1, 256), torch.randn(1, N_MEL, 1)
+    return dict(mu=mu, mask=mask, c=c, z=z, fs=fs, fc=fc, lens=lens, T=T)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = []
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) >= 9 and p[1].isdigit():
+                    rows.append(p)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        if rows:
+            clocks = [int(r[1]) for r in rows]
+            busy = [c for c, r in zip(clocks, rows) if float(r[3]) > 250.0] or clocks
+            out["sm_mhz"] = statistics.median(busy)
+            out["sm_max_mhz"] = int(rows[0][2])
+            out["power_w_max"] = max(float(r[3]) for r in rows)
+            out["samples"] = len(rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for j, n in enumerate(names):
+                if any(r[5 + j].lower().startswith("active") for r in rows):
+                    out["reasons"].append(n)
+        return out
+
+
+def cpu_reference_solve(state, inp, cfgd, B):
+    """The oracle port (reference's own PyTorch CPU path restated) on a bounded B-utterance sample."""
+    from oracle import estimator_ref as R
+    sl = slice(0, B)
+    kw = None if cfgd["cfg"] is None else dict(fake_speaker=inp["fs"], fake_content=inp["fc"], cfg_strength=cfgd["cfg"])
+    t0 = time.perf_counter()
+    out = R.cfm_forward(state, inp["mu"][sl], inp["mask"][sl], cfgd["n_steps"], inp["z"][sl], inp["c"][sl], cfgd["method"], kw)
+    return out, time.perf_counter() - t0
+
+
+def run_reference(args, cfgd, rank):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    model = make_model(None)
+    state = {k: v.detach().clone() for k, v in model.estimator.state_dict().items()}
+    Bs = 1
+    inp = make_inputs(cfgd, max(Bs, 2))
+    frames = int(inp["lens"][:Bs].sum())
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_solve(state, inp, cfgd, Bs)
+    t = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_reference_solve(state, inp, cfgd, Bs)
+        t += dt
+    val = frames * args.steps / t
+    sample = f"B={Bs} utterance(s) of the workload at T={inp['T']}, full NFE, per step"
+    line = {"impl": "reference", "metric": "mel-frames/sec through CFM DiT estimator", "value": val, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {cfgd['desc']} (CPU sample: {sample})"},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg1", choices=list(CONFIGS))
+    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfgd = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, cfgd, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from stabletts_b200 import _lib, shard
+
+    model = make_model(dev)
+    model.estimator.set_engine(args.engine)
+    Bper = cfgd["B"]
+    Bglob = Bper * world
+    inp = make_inputs(cfgd, Bglob) if rank == 0 else None
+    T = cfgd["T"] if cfgd["lengths"] is None else None
+    if world > 1:
+        hdr = torch.tensor([inp["T"] if rank == 0 else 0], device=dev)
+        dist.broadcast(hdr, 0)
+        T = int(hdr.item())
+    else:
+        T = inp["T"]
+    kw = None
+    fs_d, fc_d = None, None
+    if cfgd["cfg"] is not None:
+        # fake_* are model parameters (models/model.py:43-44): replicated like the weights
+        torch.manual_seed(2)
+        fs_d, fc_d = torch.randn(1, 256).to(dev), torch.randn(1, N_MEL, 1).to(dev)
+        if rank == 0:
+            inp["fs"], inp["fc"] = fs_d.cpu(), fc_d.cpu()
+        kw = dict(fake_speaker=fs_d, fake_content=fc_d, cfg_strength=cfgd["cfg"])
+
+    def solve(mu, mask, c, z):
+        return model(mu, mask, cfgd["n_steps"], 1.0, c, cfgd["method"], kw, z=z)
+
+    # device-resident global inputs on rank 0
+    if rank == 0:
+        g = {k: inp[k].to(dev) for k in ("mu", "mask", "c", "z")}
+        pinned = {k: inp[k].pin_memory() for k in ("mu", "mask", "c", "z")}
+        frames_global = int(inp["lens"].sum())
+    else:
+        g, pinned, frames_global = None, None, 0
+
+    def step_device():
+        if world == 1:
+            return solve(g["mu"], g["mask"], g["c"], g["z"])
+        return shard.sharded_solve(solve, *((g["mu"], g["mask"], g["c"], g["z"]) if rank == 0 else (None,) * 4), device=dev,
+                                   batch=Bglob, n_mel=N_MEL, T=T, gin=256)
+
+    def step_e2e():
+        if rank == 0:
+            d = {k: pinned[k].to(dev, non_blocking=True) for k in pinned}
+        if world == 1:
+            out = solve(d["mu"], d["mask"], d["c"], d["z"])
+        else:
+            out = shard.sharded_solve(solve, *((d["mu"], d["mask"], d["c"], d["z"]) if rank == 0 else (None,) * 4), device=dev,
+                                      batch=Bglob, n_mel=N_MEL, T=T, gin=256)
+        return out.cpu() if rank == 0 else None
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            flush.zero_()
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = model.estimator.launch_count()
+    ms_dev, out_dev = timed(step_device, args.steps)
+    launches = model.estimator.launch_count() - l0
+    for _ in range(1):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # instrumented solve: per-class CUDA-event timing of every launch (roofline)
+    lib, h = _lib.load_library(), model.estimator._handle
+    prof = None
+    if rank == 0 or world == 1:
+        lib.st_profile_begin(h)
+        if world == 1:
+            step_device()
+        else:
+            sl = slice(0, Bper)
+            solve(g["mu"][sl].contiguous(), g["mask"][sl].contiguous(), g["c"][sl].contiguous(), g["z"][sl].contiguous())
+        n = _lib.ST_PROF_NCAT
+        ms_a, fl_a, by_a, ln_a = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+        lib.st_profile_end(h, ms_a, fl_a, by_a, ln_a)
+        prof = {name: dict(ms=ms_a[i], flops=fl_a[i], bytes=by_a[i], launches=int(ln_a[i]))
+                for i, name in enumerate(("gemm", "attention", "ln"))}
+    if world > 1:
+        # non-root ranks must take part in nothing here; keep ranks aligned
+        dist.barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    gm = prof["gemm"]
+    ach_tf = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
+    nfe = cfgd["n_steps"] * NFE_PER_STEP[cfgd["method"]] * (2 if cfgd["cfg"] is not None else 1)
+    lens = inp["lens"].double()
+    hoisted = float(((nfe * (32.948e6 - COND_FLOPS) + COND_FLOPS) * lens + nfe * 6144.0 * lens * lens).sum())
+    faithful = float((nfe * (32.948e6 * lens + 6144.0 * lens * lens)).sum())
+    sec_step = ms_dev * 1e-3 / args.steps
+    value = frames_global * args.steps / (ms_dev * 1e-3)
+    e2e_val = frames_global * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(pinned[k].numel() * 4 for k in pinned)
+    d2h = Bglob * N_MEL * T * 4
+
+    cpu_baseline = None
+    parity = None
+    if not args.no_cpu_baseline and world == 1:
+        torch.set_num_threads(os.cpu_count())
+        state = {k: v.detach().cpu().clone() for k, v in model.estimator.state_dict().items()}
+        Bs = 2
+        ref, dt = cpu_reference_solve(state, inp, cfgd, Bs)
+        fr = int(inp["lens"][:Bs].sum())
+        cpu_baseline = {"value": fr / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"first {Bs} utterances of the batch at T={T}, full NFE={nfe}, {dt:.1f} s"}
+        d = (out_dev[:Bs].cpu().double() - ref.double())
+        parity = {"max_rel": float(d.abs().max() / ref.abs().max()), "l2_rel": float(d.norm() / ref.double().norm()),
+                  "vs": "oracle port on the same inputs, first 2 utterances, full solve"}
+
+    line = {
+        "metric": "mel-frames/sec through CFM DiT estimator (ODE solve, all evaluations)",
+        "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sec_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (split-bf16x3 tensor-core operands, fp32 accumulate)" if args.engine == "tcgen05" else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.config}: {cfgd['desc']}", "global_batch": Bglob, "T": T, "nfe": nfe,
+                   "frames_per_step": frames_global, "parallelism": f"batch-shard x{world}",
+                   "l2": "256 MiB flush between steps; per-eval working set (~1.5 GB) exceeds the 126 MB L2",
+                   "engine": args.engine},
+        "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                   "samples": clocks["samples"], "power_w_max": clocks.get("power_w_max")},
+        "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 split-bf16 conv-GEMM, all launches of one solve)",
+                     "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
+                     "peak_source": peak_src, "launches": gm["launches"], "kernel_ms_per_step": gm["ms"],
+                     "note": "algorithmic FLOPs (2*rows*N*K*taps); the bf16x3 split issues 3 MMAs per algorithmic MAC"},
+        "breakdown_ms_per_step": {k: v["ms"] for k, v in prof.items()},
+        "attention": {"tflops": prof["attention"]["flops"] / max(prof["attention"]["ms"], 1e-9) / 1e9},
+        "work": {"hoisted_tflop_per_step": hoisted / 1e12, "faithful_tflop_per_step": faithful / 1e12,
+                 "whole_solve_tflops_hoisted": hoisted / 1e12 / sec_step / max(world, 1) * 1.0},
+        "cpu_baseline": cpu_baseline, "parity": parity,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
