@@ -48,7 +48,8 @@ struct Workspace {
     int B = 0, T = 0, cfg = 0, BB = 0, Bc = 0, NT = 0;
     Act xt, ytmp, xs, V, mut, C1, C2, C3, P, X[5], U, QKV, AO, Hid;
     float* Kst[6] = {};
-    int* kvlen = nullptr;
+    int* kvlen = nullptr; int* prefix = nullptr;
+    AttnTcScratch att;
     float *rope_cs = nullptr, *temb = nullptr, *tmid = nullptr, *tvec = nullptr, *film = nullptr, *ada = nullptr;
     float *cin = nullptr;    // (Bc, gin): c rows + fake_speaker row
     // host staging for st_solve_host
@@ -215,6 +216,13 @@ void layout_ws(const st_handle* h, Workspace& w, void* base, size_t cap, int B, 
     mk(w.AO, bbt, d.hidden, !tc, tc);
     mk(w.Hid, bbt, d.filter, !tc, tc);
     w.kvlen = bp.take<int>(B);
+    w.prefix = bp.take<int>(B);
+    if (tc) {
+        const size_t qk = bbt * d.hidden, vt = attention_tc_scratch_elems(w.BB, T, d.hidden);
+        w.att.q_hi = bp.take<bf16>(qk); w.att.q_lo = bp.take<bf16>(qk);
+        w.att.k_hi = bp.take<bf16>(qk); w.att.k_lo = bp.take<bf16>(qk);
+        w.att.vt_hi = bp.take<bf16>(vt); w.att.vt_lo = bp.take<bf16>(vt);
+    }
     w.rope_cs = bp.take<float>((size_t)T * 32);
     w.temb = bp.take<float>((size_t)w.NT * d.hidden);
     w.tmid = bp.take<float>((size_t)w.NT * d.filter);
@@ -284,7 +292,7 @@ int precompute_cond(st_handle* h, Workspace& w, const float* mu, const float* ma
                     const float* fake_content, const float* fake_speaker, cudaStream_t s) {
     const st_dims& d = h->d;
     ST_LAUNCH(launch_bct_to_btc(mu, w.mut.f32, w.mut.hi, w.mut.lo, w.B, d.n_mel, w.T, w.cfg ? fake_content : nullptr, s));
-    ST_LAUNCH(launch_mask_lengths(mask, w.kvlen, w.B, w.T, s));
+    ST_LAUNCH(launch_mask_lengths(mask, w.kvlen, w.prefix, w.B, w.T, s));
     ST_LAUNCH(launch_rope_table(w.rope_cs, w.T, 32, s));
     GemmArgs g;
     g.BB = w.Bc; g.T = w.T; g.a_bmod = w.Bc; g.B = w.B; g.resid_clamp = w.Bc - 1;
@@ -366,10 +374,15 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
         }
         {
             AttnArgs a;
-            a.qkv = w.QKV.f32; a.rope_cs = w.rope_cs; a.mask = mask; a.kvlen = w.kvlen;
+            a.qkv = w.QKV.f32; a.rope_cs = w.rope_cs; a.mask = mask; a.kvlen = w.kvlen; a.prefix = w.prefix;
             a.out_f32 = w.AO.f32; a.out_hi = w.AO.hi; a.out_lo = w.AO.lo;
             a.BB = w.BB; a.B = w.B; a.T = w.T; a.H = H; a.n_heads = d.n_heads;
-            ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_simt(a, s));
+            if (h->engine == ST_ENGINE_TCGEN05) {
+                h->launches++;     // prep kernel (the attention kernel is counted by ST_LAUNCH_P)
+                ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_tc(a, w.att, s));
+            } else {
+                ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_simt(a, s));
+            }
         }
         {   // x += gate_msa * conv_o(attn) * mask   (:65, :111)
             GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
@@ -755,22 +768,32 @@ int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* 
     if (!h) return 1;
     ST_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
-    int* kvlen; float* cs;
-    ST_CUDA(cudaMalloc(&kvlen, sizeof(int) * B)); ST_CUDA(cudaMalloc(&cs, sizeof(float) * T * 32));
+    const bool tc = h->engine == ST_ENGINE_TCGEN05;
+    int *kvlen, *prefix; float* cs;
+    ST_CUDA(cudaMalloc(&kvlen, sizeof(int) * B)); ST_CUDA(cudaMalloc(&prefix, sizeof(int) * B));
+    ST_CUDA(cudaMalloc(&cs, sizeof(float) * T * 32));
+    AttnTcScratch sc;
+    const size_t qk = (size_t)B * T * h->d.hidden, vt = attention_tc_scratch_elems(B, T, h->d.hidden);
+    if (tc) {
+        ST_CUDA(cudaMalloc(&sc.q_hi, qk * 2)); ST_CUDA(cudaMalloc(&sc.q_lo, qk * 2)); ST_CUDA(cudaMalloc(&sc.k_hi, qk * 2));
+        ST_CUDA(cudaMalloc(&sc.k_lo, qk * 2)); ST_CUDA(cudaMalloc(&sc.vt_hi, vt * 2)); ST_CUDA(cudaMalloc(&sc.vt_lo, vt * 2));
+    }
     int rc = 0;
     do {
-        if (launch_mask_lengths(mask, kvlen, B, T, s) != cudaSuccess || launch_rope_table(cs, T, 32, s) != cudaSuccess) {
+        if (launch_mask_lengths(mask, kvlen, prefix, B, T, s) != cudaSuccess || launch_rope_table(cs, T, 32, s) != cudaSuccess) {
             rc = fail(h, "attention prep failed"); break;
         }
         AttnArgs a;
-        a.qkv = qkv; a.rope_cs = cs; a.mask = mask; a.kvlen = kvlen; a.out_f32 = out;
+        a.qkv = qkv; a.rope_cs = cs; a.mask = mask; a.kvlen = kvlen; a.prefix = prefix; a.out_f32 = out;
         a.BB = B; a.B = B; a.T = T; a.H = h->d.hidden; a.n_heads = h->d.n_heads;
-        if (launch_attention_simt(a, s) != cudaSuccess) { rc = fail(h, "attention launch failed"); break; }
+        cudaError_t e = tc ? launch_attention_tc(a, sc, s) : launch_attention_simt(a, s);
+        if (e != cudaSuccess) { rc = fail(h, std::string("attention launch failed: ") + cudaGetErrorString(e) + " / " + attention_tc_last_error()); break; }
     } while (0);
     cudaStreamSynchronize(s);
     cudaError_t e = cudaGetLastError();
     if (!rc && e != cudaSuccess) rc = fail(h, std::string("st_test_attention: ") + cudaGetErrorString(e));
-    cudaFree(kvlen); cudaFree(cs);
+    cudaFree(kvlen); cudaFree(prefix); cudaFree(cs);
+    if (tc) { cudaFree(sc.q_hi); cudaFree(sc.q_lo); cudaFree(sc.k_hi); cudaFree(sc.k_lo); cudaFree(sc.vt_hi); cudaFree(sc.vt_lo); }
     return rc;
 }
 

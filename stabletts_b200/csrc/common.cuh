@@ -95,8 +95,8 @@ cudaError_t launch_gemv(const float* x, const float* W, const float* bias, float
 cudaError_t launch_time_embed(const float* t, int n_t, int H, float* out, cudaStream_t s);
 // cos/sin table (T, 16, 2) of models/diffusion_transformer.py:150-171 with d = 32
 cudaError_t launch_rope_table(float* cs, int T, int d_rot, cudaStream_t s);
-// kv_len[b] = 1 + last index with mask != 0 (0 if none)
-cudaError_t launch_mask_lengths(const float* mask, int* kvlen, int B, int T, cudaStream_t s);
+// kvlen[b] = 1 + last index with mask != 0 (0 if none); prefix[b] = first index with mask == 0 (T if none)
+cudaError_t launch_mask_lengths(const float* mask, int* kvlen, int* prefix, int B, int T, cudaStream_t s);
 // K_out = uncond + s*(cond - uncond) (models/flow_matching.py:66) or copy when !cfg
 cudaError_t launch_cfg_combine(const float* V, float* K_out, int B, long per_batch, int cfg, float s_cfg, cudaStream_t s);
 // dst = y + sum_i coef[i] * K[i]   (n <= 6)
@@ -112,11 +112,21 @@ struct AttnArgs {
     const float* qkv = nullptr;
     const float* rope_cs = nullptr;   // (T, 16, 2)
     const float* mask = nullptr;      // (B, T)
-    const int* kvlen = nullptr;       // (B)
+    const int* kvlen = nullptr;       // (B) 1 + last index with mask != 0
+    const int* prefix = nullptr;      // (B) first index with mask == 0 (T if none): keys below it need no mask test
     float* out_f32 = nullptr; bf16* out_hi = nullptr; bf16* out_lo = nullptr;
     int BB = 0, B = 1, T = 0, H = 0, n_heads = 0;
 };
 cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t s);
+
+// tcgen05 engine (attention_tc.cu): per-head split-bf16 operand planes produced by its prep kernel
+struct AttnTcScratch {
+    bf16 *q_hi = nullptr, *q_lo = nullptr, *k_hi = nullptr, *k_lo = nullptr;   // [BB*nh][T][64]
+    bf16 *vt_hi = nullptr, *vt_lo = nullptr;                                    // [BB*nh][64][Tpad]
+};
+size_t attention_tc_scratch_elems(int BB, int T, int H);    // elements per plane (covers Tpad)
+cudaError_t launch_attention_tc(const AttnArgs& a, const AttnTcScratch& sc, cudaStream_t s);
+const char* attention_tc_last_error();
 
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }

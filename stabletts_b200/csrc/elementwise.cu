@@ -224,26 +224,35 @@ cudaError_t launch_rope_table(float* cs, int T, int d_rot, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-__global__ void mask_lengths_kernel(const float* __restrict__ mask, int* __restrict__ kvlen, int B, int T) {
+__global__ void mask_lengths_kernel(const float* __restrict__ mask, int* __restrict__ kvlen, int* __restrict__ prefix, int B, int T) {
     int b = blockIdx.x;
-    int best = 0;
-    for (int t = threadIdx.x; t < T; t += blockDim.x)
+    int best = 0, first0 = T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
         if (mask[(long)b * T + t] != 0.f) best = max(best, t + 1);
-    __shared__ int red[32];
+        else first0 = min(first0, t);
+    }
+    __shared__ int red[32], red2[32];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    for (int o = 16; o > 0; o >>= 1) {
+        best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+        first0 = min(first0, __shfl_xor_sync(0xffffffffu, first0, o));
+    }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = best; red2[threadIdx.x >> 5] = first0; }
     __syncthreads();
     if (threadIdx.x < 32) {
         int v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0;
+        int w = threadIdx.x < (blockDim.x >> 5) ? red2[threadIdx.x] : T;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (threadIdx.x == 0) kvlen[b] = v;
+        for (int o = 16; o > 0; o >>= 1) {
+            v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+            w = min(w, __shfl_xor_sync(0xffffffffu, w, o));
+        }
+        if (threadIdx.x == 0) { kvlen[b] = v; prefix[b] = w; }
     }
 }
 
-cudaError_t launch_mask_lengths(const float* mask, int* kvlen, int B, int T, cudaStream_t s) {
-    mask_lengths_kernel<<<B, 256, 0, s>>>(mask, kvlen, B, T);
+cudaError_t launch_mask_lengths(const float* mask, int* kvlen, int* prefix, int B, int T, cudaStream_t s) {
+    mask_lengths_kernel<<<B, 256, 0, s>>>(mask, kvlen, prefix, B, T);
     return cudaGetLastError();
 }
 

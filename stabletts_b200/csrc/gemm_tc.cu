@@ -434,6 +434,14 @@ cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t s) {
 
 const char* gemm_tc_last_error() { return g_err.c_str(); }
 
+// shared with attention_tc.cu (cached, mutex-free: callers serialise through their own launch mutex)
+bool tmap_encode_bf16(const void* ptr, int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                      CUtensorMap* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!ensure_encode()) return false;
+    return get_map(ptr, rank, d0, d1, d2, b0, b1, out);
+}
+
 cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g.BB == 0 || g.T == 0) return cudaSuccess;
@@ -450,7 +458,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s) {
     if (g.N > 128) {
         const long t256 = m_tiles * ((g.N + 255) / 256), t128 = m_tiles * ((g.N + 127) / 128);
         const long w256 = (t256 + num_sms - 1) / num_sms * 2, w128 = (t128 + num_sms - 1) / num_sms;
-        use256 = w256 <= w128 + w128 / 8;
+        use256 = false && (w256 <= w128 + w128 / 8);   // 128x256 with 2 stages is TMA-latency bound (profiles/r1a); 2-CTA 256x256 is the planned wide tile
     }
     return use256 ? launch_bn<256>(g, num_sms, s) : launch_bn<128>(g, num_sms, s);
 }

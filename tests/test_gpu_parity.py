@@ -103,15 +103,16 @@ def test_kernel_gemm_and_conv(engine, dev):
         assert e_max < 5e-5 and e_l2 < 5e-5, (engine, B, Cin, Cout, T, k, e_max, e_l2)
 
 
-def test_kernel_attention(dev):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_kernel_attention(engine, dev):
     """masked RoPE attention vs the oracle's restatement of models/diffusion_transformer.py:58-79."""
     from stabletts_b200 import _lib
-    m = model_for(80, "simt", dev)
+    m = model_for(80, engine, dev)
     m.estimator._prepare(torch.zeros(1, device=dev), 1, 8, 0)
     lib, h = _lib.load_library(), m.estimator._handle
     s = torch.cuda.current_stream().cuda_stream
     g = torch.Generator().manual_seed(9)
-    for lens, T in [([300, 211], 300), ([1], 1), ([33, 0, 40], 40), ([129], 129)]:
+    for lens, T in [([300, 211], 300), ([1], 1), ([33, 0, 40], 40), ([129], 129), ([1000, 517], 1000), ([64, 63, 65], 70)]:
         B = len(lens)
         qkv = torch.randn(B, T, 768, generator=g)
         mask = (torch.arange(T)[None] < torch.tensor(lens)[:, None]).float()
@@ -124,7 +125,8 @@ def test_kernel_attention(dev):
         ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=am).transpose(1, 2).reshape(B, T, 256)
         ref = ref * mask[:, :, None]
         e_max, e_l2 = rel_errs(out, ref)
-        assert e_max < 2e-5 and e_l2 < 2e-5, (lens, e_max, e_l2)
+        tol = 2e-5 if engine == "simt" else 1e-4
+        assert e_max < tol and e_l2 < tol, (engine, lens, e_max, e_l2)
 
 
 def test_properties_at_benchmark_shape(dev):
