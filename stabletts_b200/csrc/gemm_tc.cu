@@ -145,7 +145,7 @@ template <int BN> struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (BN == 256) ? 2 : 3;
     static constexpr int TMEM_COLS = 2 * BN;                 // two accumulator stages (power of 2 >= 32)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 4096 /*epilogue staging*/;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -246,82 +246,90 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
     } else if (warp >= 4) {
         // ================= epilogue (4 warps = 128 TMEM lanes = 128 frames) =================
+        // Phase A: tcgen05.ld (thread = row, 32 columns) -> swizzled smem staging, no math.
+        // Phase B: lane = (4 rows x 8 float4 columns): every global access is a coalesced 128-byte row
+        //          segment (residual read, fp32 / split-bf16 writes); per-column vectors (bias, gate,
+        //          FiLM) live in registers for the whole chunk, per-row mask for the whole tile.
         const int wq = warp & 3;                       // TMEM lane quarter this warp may access
-        const int r = wq * 32 + lane;                  // row inside the tile
+        float4* stg = reinterpret_cast<float4*>(smem + C::STAGES * C::STAGE_BYTES + 256) + wq * 256;   // 4 KB per warp
+        const int rs = lane >> 3, c4 = lane & 7;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
-            const int bb = m_tile / p.m_tiles_per_b, t = (m_tile % p.m_tiles_per_b) * BLOCK_M + r;
+            const int bb = m_tile / p.m_tiles_per_b, t0 = (m_tile % p.m_tiles_per_b) * BLOCK_M + wq * 32;
             const int n0 = n_tile * BN;
-            const bool row_ok = t < p.T;
             const int mb = bb % p.B;
-            const float m = (p.flags & EPI_MASK) && row_ok ? p.mask[(long)mb * p.T + t] : 1.f;
-            const float* film = (p.flags & EPI_FILM) ? p.film + (long)mb * p.film_bstride : nullptr;
-            const float* gate = (p.flags & EPI_GATE) ? p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride : nullptr;
-            const float* resid = (p.flags & EPI_RESID) ? p.resid + ((long)min(bb, p.resid_clamp) * p.T + t) * p.N : nullptr;
-            const long orow = ((long)bb * p.T + t) * p.N;
+            float mrow[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int t = t0 + it * 4 + rs;
+                mrow[it] = ((p.flags & EPI_MASK) && t < p.T) ? __ldg(p.mask + (long)mb * p.T + t) : 1.f;
+            }
+            const float* film = p.film + (long)mb * p.film_bstride;
+            const float* gate = p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride;
+            const float* resid = p.resid + (long)min(bb, p.resid_clamp) * p.T * p.N;
+            const long obase = (long)bb * p.T * p.N;
 
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 if (n0 + c0 >= p.N) break;             // warp-uniform
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                tmem_ld_wait();
-                if (row_ok) {
-                    float f[32];
+                {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = n0 + c0 + j;
-                        float x = __uint_as_float(v[j]);
-                        if (n < p.N) {
-                            if (p.flags & EPI_BIAS) x += __ldg(p.bias + n);
-                            if (p.flags & EPI_SILU) x = silu_f(x);
-                            if (p.flags & EPI_FILM) x = __ldg(film + n) * x + __ldg(film + p.film_H + n);
-                            if (p.flags & EPI_MASK) x *= m;
-                            if (p.flags & EPI_GATE) x *= __ldg(gate + n);
+                    for (int q = 0; q < 8; ++q)
+                        stg[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                                                       __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                }
+                __syncwarp();
+                const int n = n0 + c0 + c4 * 4;
+                if (n < p.N) {                         // N % 4 == 0: a float4 column group is all-in or all-out
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = b4;
+                    if (p.flags & EPI_BIAS) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    if (p.flags & EPI_GATE) g4 = __ldg(reinterpret_cast<const float4*>(gate + n));
+                    if (p.flags & EPI_FILM) {
+                        fg = __ldg(reinterpret_cast<const float4*>(film + n));
+                        fb = __ldg(reinterpret_cast<const float4*>(film + p.film_H + n));
+                    }
+                    float4 sv[8], rv[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rl = it * 4 + rs;
+                        sv[it] = stg[rl * 8 + (c4 ^ (rl & 7))];
+                        rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if ((p.flags & EPI_RESID) && t0 + rl < p.T)
+                            rv[it] = __ldg(reinterpret_cast<const float4*>(resid + (long)(t0 + rl) * p.N + n));
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int t = t0 + it * 4 + rs;
+                        if (t >= p.T) continue;
+                        float x[4] = {sv[it].x + b4.x, sv[it].y + b4.y, sv[it].z + b4.z, sv[it].w + b4.w};
+                        if (p.flags & EPI_SILU) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
                         }
-                        f[j] = x;
-                    }
-                    const int nb = n0 + c0;
-                    const bool full = nb + 32 <= p.N;  // N is a multiple of 16 everywhere on this path
-                    if (p.flags & EPI_RESID) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            if (full || nb + q * 4 + 4 <= p.N) {
-                                float4 rv = *reinterpret_cast<const float4*>(resid + nb + q * 4);
-                                f[q * 4 + 0] += rv.x; f[q * 4 + 1] += rv.y; f[q * 4 + 2] += rv.z; f[q * 4 + 3] += rv.w;
-                            }
-                        }
-                    }
-                    if (p.out_f32) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (full || nb + q * 4 + 4 <= p.N)
-                                *reinterpret_cast<float4*>(p.out_f32 + orow + nb + q * 4) =
-                                    make_float4(f[q * 4 + 0], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
-                    }
-                    if (p.out_hi) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (full || nb + q * 8 + 8 <= p.N) {
-                                uint32_t hw[4], lw[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    bf16 h0, l0, h1, l1;
-                                    split_bf16(f[q * 8 + e * 2], h0, l0);
-                                    split_bf16(f[q * 8 + e * 2 + 1], h1, l1);
-                                    __nv_bfloat162 hp = __halves2bfloat162(h0, h1), lp = __halves2bfloat162(l0, l1);
-                                    hw[e] = *reinterpret_cast<uint32_t*>(&hp);
-                                    lw[e] = *reinterpret_cast<uint32_t*>(&lp);
-                                }
-                                *reinterpret_cast<uint4*>(p.out_hi + orow + nb + q * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                                *reinterpret_cast<uint4*>(p.out_lo + orow + nb + q * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                            }
+                        const float m = mrow[it];
+                        x[0] = (fg.x * x[0] + fb.x) * m * g4.x + rv[it].x;
+                        x[1] = (fg.y * x[1] + fb.y) * m * g4.y + rv[it].y;
+                        x[2] = (fg.z * x[2] + fb.z) * m * g4.z + rv[it].z;
+                        x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[it].w;
+                        const long o = obase + (long)t * p.N + n;
+                        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
+                        if (p.out_hi) {
+                            bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+                            split_bf16(x[0], h0, l0); split_bf16(x[1], h1, l1); split_bf16(x[2], h2, l2); split_bf16(x[3], h3, l3);
+                            __nv_bfloat162 ha = __halves2bfloat162(h0, h1), hb = __halves2bfloat162(h2, h3);
+                            __nv_bfloat162 la = __halves2bfloat162(l0, l1), lb = __halves2bfloat162(l2, l3);
+                            *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
+                            *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
                         }
                     }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
