@@ -125,6 +125,11 @@ int st_test_gemm(st_handle* h, const float* A, const float* W, const float* bias
 int st_test_conv(st_handle* h, const float* x, const float* w, const float* bias, float* out,
                  int B, int Cin, int Cout, int T, int k, void* stream);
 
+/* Times `reps` launches of the selected engine's conv-GEMM on device-generated synthetic operands:
+ * (B,T,Cin) x [k][Cout][Cin] -> (B,T,Cout); epi != 0 uses the conv_2-style epilogue (bias, mask, gate,
+ * residual, fp32 + split-bf16 outputs), epi == 0 bias + split-bf16 output.  *ms_out = ms per launch. */
+int st_bench_conv(st_handle* h, int B, int Cin, int Cout, int T, int k, int epi, int reps, float* ms_out);
+
 /* Masked multi-head attention with partial RoPE on packed qkv (B,T,3*hidden) -> (B,T,hidden). */
 int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* out, int B, int T,
                       void* stream);

@@ -15,7 +15,7 @@ ST_PROF_GEMM, ST_PROF_ATTN, ST_PROF_LN, ST_PROF_NCAT = 0, 1, 2, 3
 EXPORTS = [
     "st_create", "st_destroy", "st_last_error", "st_version", "st_load_weight", "st_finalize_weights",
     "st_set_engine", "st_workspace_bytes", "st_attach_workspace", "st_estimator_forward", "st_solve",
-    "st_solve_host", "st_launch_count", "st_profile_begin", "st_profile_end", "st_test_gemm", "st_test_conv", "st_test_attention",
+    "st_solve_host", "st_launch_count", "st_profile_begin", "st_profile_end", "st_test_gemm", "st_test_conv", "st_test_attention", "st_bench_conv",
 ]
 
 
@@ -59,6 +59,7 @@ def load_library() -> C.CDLL:
     lib.st_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.st_test_gemm.argtypes = [vp, f32p, f32p, f32p, f32p, i32, i32, i32, i32, vp]
     lib.st_test_conv.argtypes = [vp, f32p, f32p, f32p, f32p, i32, i32, i32, i32, i32, vp]
+    lib.st_bench_conv.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float)]
     lib.st_test_attention.argtypes = [vp, f32p, f32p, f32p, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)

@@ -764,6 +764,63 @@ int st_test_gemm(st_handle* h, const float* A, const float* W, const float* bias
     return rc;
 }
 
+__global__ void fill_pattern_kernel(float* p, long n, uint32_t seed) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x = (uint32_t)i * 2654435761u + seed;
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    p[i] = ((float)(x & 0xFFFF) / 32768.0f - 1.0f);
+}
+
+// Times `reps` launches of the selected engine's conv-GEMM on synthetic data (token-major operands are
+// generated on the device): (B, T, Cin) x [k][Cout][Cin] -> (B, T, Cout) with the conv_2-style epilogue
+// when epi != 0 (bias, mask, gate, residual, fp32 + split outputs) or bias-only split output otherwise.
+int st_bench_conv(st_handle* h, int B, int Cin, int Cout, int T, int k, int epi, int reps, float* ms_out) {
+    if (!h || !ms_out) return 1;
+    ST_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = 0;
+    const bool tc = h->engine == ST_ENGINE_TCGEN05;
+    const size_t nx = (size_t)B * T * Cin, nw = (size_t)k * Cout * Cin, no = (size_t)B * T * Cout;
+    float *xf, *wf, *of, *bias, *mask, *gate; bf16 *xh, *xl, *wh, *wl, *oh, *ol;
+    ST_CUDA(cudaMalloc(&xf, nx * 4)); ST_CUDA(cudaMalloc(&wf, nw * 4)); ST_CUDA(cudaMalloc(&of, no * 4));
+    ST_CUDA(cudaMalloc(&xh, nx * 2)); ST_CUDA(cudaMalloc(&xl, nx * 2)); ST_CUDA(cudaMalloc(&wh, nw * 2)); ST_CUDA(cudaMalloc(&wl, nw * 2));
+    ST_CUDA(cudaMalloc(&oh, no * 2)); ST_CUDA(cudaMalloc(&ol, no * 2));
+    ST_CUDA(cudaMalloc(&bias, Cout * 4)); ST_CUDA(cudaMalloc(&gate, (size_t)B * Cout * 4)); ST_CUDA(cudaMalloc(&mask, (size_t)B * T * 4));
+    fill_pattern_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, s>>>(xf, (long)nx, 1u);
+    fill_pattern_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(wf, (long)nw, 2u);
+    fill_pattern_kernel<<<(unsigned)((no + 255) / 256), 256, 0, s>>>(of, (long)no, 3u);
+    fill_pattern_kernel<<<(Cout + 255) / 256, 256, 0, s>>>(bias, Cout, 4u);
+    fill_pattern_kernel<<<(unsigned)(((size_t)B * Cout + 255) / 256), 256, 0, s>>>(gate, (long)B * Cout, 5u);
+    ST_CUDA(cudaMemsetAsync(mask, 0x3f, (size_t)B * T * 4, s));       // 0.747 everywhere: a non-trivial multiplier
+    int rc = 0;
+    do {
+        if (launch_split(xf, xh, xl, (long)nx, s) != cudaSuccess || launch_split(wf, wh, wl, (long)nw, s) != cudaSuccess) { rc = fail(h, "split failed"); break; }
+        GemmArgs g;
+        g.BB = B; g.T = T; g.a_bmod = B; g.B = B; g.resid_clamp = B - 1; g.c_clamp = B - 1; g.mask = mask;
+        g.flags = epi ? (EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID) : EPI_BIAS;
+        g.gate = gate; g.gate_bstride = Cout; g.resid = of;
+        GemmW w; w.f32 = wf; w.hi = wh; w.lo = wl; w.bias = bias; w.taps = k; w.N = Cout; w.K = Cin;
+        Act a; a.C = Cin; a.f32 = xf; a.hi = tc ? xh : nullptr; a.lo = tc ? xl : nullptr;
+        Act o; o.C = Cout; o.f32 = epi ? of : nullptr; o.hi = oh; o.lo = ol;
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int i = 0; i < 2 && !rc; ++i) rc = run_gemm(h, g, w, &a, nullptr, o, s);
+        if (rc) break;
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < reps && !rc; ++i) rc = run_gemm(h, g, w, &a, nullptr, o, s);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        *ms_out = ms / (reps > 0 ? reps : 1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    } while (0);
+    cudaStreamSynchronize(s);
+    cudaError_t e = cudaGetLastError();
+    if (!rc && e != cudaSuccess) rc = fail(h, std::string("st_bench_conv: ") + cudaGetErrorString(e));
+    cudaFree(xf); cudaFree(wf); cudaFree(of); cudaFree(xh); cudaFree(xl); cudaFree(wh); cudaFree(wl); cudaFree(oh); cudaFree(ol);
+    cudaFree(bias); cudaFree(gate); cudaFree(mask);
+    return rc;
+}
+
 int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* out, int B, int T, void* stream) {
     if (!h) return 1;
     ST_CUDA(cudaSetDevice(h->device));

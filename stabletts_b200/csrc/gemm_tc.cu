@@ -21,6 +21,8 @@
 #include <mutex>
 #include <unordered_map>
 #include <string>
+#include <cstring>
+#include <cstdlib>
 
 namespace st {
 
@@ -450,9 +452,33 @@ bool tmap_encode_bf16(const void* ptr, int rank, uint64_t d0, uint64_t d1, uint6
     return get_map(ptr, rank, d0, d1, d2, b0, b1, out);
 }
 
+bool gemm_tc2_eligible(const GemmArgs& g, int num_sms);
+cudaError_t launch_gemm_tc2(const GemmArgs& g, int num_sms, cudaStream_t s);
+const char* gemm_tc2_last_error();
+
+// 0 = 1-CTA kernel only, 1 = 2-CTA kernel where eligible (default), 2 = 2-CTA whenever shapes allow (tests)
+static int tc2_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("STABLETTS_B200_TC2");
+        mode = !e ? 1 : (!strcmp(e, "force") ? 2 : (!strcmp(e, "0") ? 0 : 1));
+    }
+    return mode;
+}
+
 cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s) {
-    std::lock_guard<std::mutex> lk(g_mu);
     if (g.BB == 0 || g.T == 0) return cudaSuccess;
+    {
+        const int mode = tc2_mode();
+        bool ok = g.A_hi[0] && g.W_hi && g.N >= 256 && g.N % 128 == 0 && g.Ktot % 8 == 0 && g.Cs[0] % 8 == 0 &&
+                  (g.n_src == 1 || (g.Cs[0] % BLOCK_K == 0 && g.Cs[1] % 8 == 0 && g.A_hi[1]));
+        if (mode && ok && (mode == 2 || gemm_tc2_eligible(g, num_sms))) {
+            cudaError_t e = launch_gemm_tc2(g, num_sms, s);
+            if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(g_mu); g_err = std::string("2-CTA kernel: ") + gemm_tc2_last_error(); }
+            return e;
+        }
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
     if (!ensure_encode()) return cudaErrorNotSupported;
     for (int i = 0; i < g.n_src; ++i) {
         if (!g.A_hi[i] || !g.A_lo[i]) { g_err = "split-bf16 A planes missing"; return cudaErrorInvalidValue; }

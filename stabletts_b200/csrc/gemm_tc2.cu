@@ -1,0 +1,289 @@
+// 2-CTA (cta_group::2) variant of the tcgen05 conv-GEMM engine: a CTA pair (one TPC, cluster of 2)
+// computes a 256-frame x 256-channel tile with ONE tcgen05.mma.cta_group::2 stream issued by the
+// leader CTA.  Each CTA stages only its own 128 A rows and HALF of the B tile (128 of the 256 output
+// channels), so shared-memory fill traffic per MMA cycle is 42.7 B/clk/SM instead of 85 B/clk/SM for
+// the 1-CTA 128x128 tile — the 1-CTA kernel is L2->SM bandwidth bound at ~50 % tensor-pipe
+// utilisation with split-bf16 operands (profiles/r1a_gemm_tc_full.csv), this one is not.
+//
+// Same GemmArgs contract, same fused epilogue as gemm_tc.cu.  Barrier wiring:
+//   full[s]        leader only   count 1: leader's producer arrive.expect_tx(2 x stage bytes); BOTH CTAs'
+//                                TMA loads complete_tx on the leader's barrier (cta_group::2 TMA form)
+//   empty[s]       each CTA      count 1: tcgen05.commit.cta_group::2 multicast from the leader's MMA thread
+//   tmem_full[a]   each CTA      count 1: multicast commit after a tile's last k-block
+//   tmem_empty[a]  leader only   count 8: 4 epilogue warps of each CTA (the peer arrives remotely, mapa)
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <string>
+
+namespace st {
+
+bool tmap_encode_bf16(const void* ptr, int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                      CUtensorMap* out);
+const char* gemm_tc_last_error();
+
+namespace {
+
+using namespace ptx;
+
+constexpr int BM = 128;                 // rows per CTA (pair tile: 256)
+constexpr int BN2 = 256;                // pair tile width; each CTA stages 128 B rows
+constexpr int BK = 64;
+constexpr int UK = 16;
+constexpr int THREADS = 256;
+constexpr int TILE_BYTES = 128 * BK * 2;            // 16 KB: A plane tile and B-half plane tile
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, Bh_hi, Bh_lo = 64 KB
+constexpr int STAGES = 3;
+constexpr int TMEM_COLS = 512;                      // two 256-column accumulator stages
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * 4096;
+
+struct Maps2 { CUtensorMap a_hi[2], a_lo[2], w_hi, w_lo; };
+
+struct Params2 {
+    int n_src, Cs0, Cs1, taps, N, a_bmod, BB, T;
+    int m_tiles_per_b, n_tiles, total_tiles;
+    int flags, B, film_H, c_clamp, resid_clamp;
+    long film_bstride, gate_bstride;
+    const float *bias, *mask, *film, *gate, *resid;
+    float* out_f32; bf16* out_hi; bf16* out_lo;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int kb0 = (p.Cs0 + BK - 1) / BK;
+    const int kb1 = p.n_src > 1 ? (p.Cs1 + BK - 1) / BK : 0;
+    const int kb_per_tap = kb0 + kb1;
+    const int num_kb = p.taps * kb_per_tap;
+    const int pad = p.taps / 2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.a_hi[0]); prefetch_tmap(&maps.a_lo[0]); prefetch_tmap(&maps.w_hi); prefetch_tmap(&maps.w_lo);
+        if (p.n_src > 1) { prefetch_tmap(&maps.a_hi[1]); prefetch_tmap(&maps.a_lo[1]); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc_2sm<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    cluster_sync();                    // peer barriers initialised, both TMEM allocations done
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+                const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+                const int bb = m_tile / p.m_tiles_per_b, t0 = (m_tile % p.m_tiles_per_b) * (2 * BM) + (int)rank * BM;
+                const int ab = bb % p.a_bmod, n0 = n_tile * BN2 + (int)rank * 128;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    for (int kb = 0; kb < kb_per_tap; ++kb) {
+                        const int src = kb >= kb0 ? 1 : 0;
+                        const int kc = (src ? kb - kb0 : kb) * BK;
+                        const int kw = (src ? p.Cs0 : 0) + kc;
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* s = smem + stage * STAGE_BYTES;
+                        if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                        tma_load_3d_2sm(&maps.a_hi[src], &full_bar[stage], s, kc, t0 + tap - pad, ab);
+                        tma_load_3d_2sm(&maps.a_lo[src], &full_bar[stage], s + TILE_BYTES, kc, t0 + tap - pad, ab);
+                        tma_load_2d_2sm(&maps.w_hi, &full_bar[stage], s + 2 * TILE_BYTES, kw, tap * p.N + n0);
+                        tma_load_2d_2sm(&maps.w_lo, &full_bar[stage], s + 3 * TILE_BYTES, kw, tap * p.N + n0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN2);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN2;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + TILE_BYTES);
+                        const uint64_t b_hi = make_sw128_desc(sa + 2 * TILE_BYTES), b_lo = make_sw128_desc(sa + 3 * TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k) {
+                            const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);
+                            umma_bf16_2sm(tmem_d, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+                            umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+                        }
+                        umma_commit_2sm(&empty_bar[stage], 0b11);                       // both CTAs' stage s may be refilled
+                        if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[acc], 0b11);   // both epilogues may drain
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue (both CTAs, own 128 rows) =================
+        const int wq = warp & 3;
+        float4* stg = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES + 256) + wq * 256;
+        const int rs = lane >> 3, c4 = lane & 7;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+            const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+            const int bb = m_tile / p.m_tiles_per_b;
+            const int t0 = (m_tile % p.m_tiles_per_b) * (2 * BM) + (int)rank * BM + wq * 32;
+            const int n0 = n_tile * BN2;
+            const int mb = bb % p.B;
+            float mrow[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int t = t0 + it * 4 + rs;
+                mrow[it] = ((p.flags & EPI_MASK) && t < p.T) ? __ldg(p.mask + (long)mb * p.T + t) : 1.f;
+            }
+            const float* film = p.film + (long)mb * p.film_bstride;
+            const float* gate = p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride;
+            const float* resid = p.resid + (long)min(bb, p.resid_clamp) * p.T * p.N;
+            const long obase = (long)bb * p.T * p.N;
+
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN2; c0 += 32) {
+                if (n0 + c0 >= p.N) break;
+                {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN2 + c0), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        stg[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                                                       __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                }
+                __syncwarp();
+                const int n = n0 + c0 + c4 * 4;
+                if (n < p.N) {
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = b4;
+                    if (p.flags & EPI_BIAS) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    if (p.flags & EPI_GATE) g4 = __ldg(reinterpret_cast<const float4*>(gate + n));
+                    if (p.flags & EPI_FILM) {
+                        fg = __ldg(reinterpret_cast<const float4*>(film + n));
+                        fb = __ldg(reinterpret_cast<const float4*>(film + p.film_H + n));
+                    }
+                    float4 sv[8], rv[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rl = it * 4 + rs;
+                        sv[it] = stg[rl * 8 + (c4 ^ (rl & 7))];
+                        rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if ((p.flags & EPI_RESID) && t0 + rl < p.T)
+                            rv[it] = __ldg(reinterpret_cast<const float4*>(resid + (long)(t0 + rl) * p.N + n));
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int t = t0 + it * 4 + rs;
+                        if (t >= p.T) continue;
+                        float x[4] = {sv[it].x + b4.x, sv[it].y + b4.y, sv[it].z + b4.z, sv[it].w + b4.w};
+                        if (p.flags & EPI_SILU) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
+                        }
+                        const float m = mrow[it];
+                        x[0] = (fg.x * x[0] + fb.x) * m * g4.x + rv[it].x;
+                        x[1] = (fg.y * x[1] + fb.y) * m * g4.y + rv[it].y;
+                        x[2] = (fg.z * x[2] + fb.z) * m * g4.z + rv[it].z;
+                        x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[it].w;
+                        const long o = obase + (long)t * p.N + n;
+                        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
+                        if (p.out_hi) {
+                            bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+                            split_bf16(x[0], h0, l0); split_bf16(x[1], h1, l1); split_bf16(x[2], h2, l2); split_bf16(x[3], h3, l3);
+                            __nv_bfloat162 ha = __halves2bfloat162(h0, h1), hb = __halves2bfloat162(h2, h3);
+                            __nv_bfloat162 la = __halves2bfloat162(l0, l1), lb = __halves2bfloat162(l2, l3);
+                            *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
+                            *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);      // the LEADER's barrier gates the next MMA
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync();                    // nobody exits (or frees TMEM) while the peer can still signal it
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+    }
+}
+
+bool g_attr2 = false;
+std::string g_err2;
+
+}  // namespace
+
+const char* gemm_tc2_last_error() { return g_err2.c_str(); }
+
+// eligibility: wide outputs and enough pair tiles to fill the 74 TPCs
+bool gemm_tc2_eligible(const GemmArgs& g, int num_sms) {
+    if (g.N < 256 || g.N % 128) return false;
+    const long pair_tiles = (long)g.BB * ((g.T + 255) / 256) * ((g.N + 255) / 256);
+    return pair_tiles >= (num_sms / 2);
+}
+
+cudaError_t launch_gemm_tc2(const GemmArgs& g, int num_sms, cudaStream_t s) {
+    Maps2 maps;
+    for (int i = 0; i < g.n_src; ++i) {
+        if (!tmap_encode_bf16(g.A_hi[i], 3, (uint64_t)g.Cs[i], (uint64_t)g.T, (uint64_t)g.a_bmod, BK, BM, &maps.a_hi[i]) ||
+            !tmap_encode_bf16(g.A_lo[i], 3, (uint64_t)g.Cs[i], (uint64_t)g.T, (uint64_t)g.a_bmod, BK, BM, &maps.a_lo[i])) {
+            g_err2 = gemm_tc_last_error(); return cudaErrorInvalidValue;
+        }
+    }
+    if (g.n_src == 1) { maps.a_hi[1] = maps.a_hi[0]; maps.a_lo[1] = maps.a_lo[0]; }
+    if (!tmap_encode_bf16(g.W_hi, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BK, 128, &maps.w_hi) ||
+        !tmap_encode_bf16(g.W_lo, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BK, 128, &maps.w_lo)) {
+        g_err2 = gemm_tc_last_error(); return cudaErrorInvalidValue;
+    }
+    Params2 p;
+    p.n_src = g.n_src; p.Cs0 = g.Cs[0]; p.Cs1 = g.Cs[1]; p.taps = g.taps; p.N = g.N; p.a_bmod = g.a_bmod; p.BB = g.BB; p.T = g.T;
+    p.m_tiles_per_b = (g.T + 2 * BM - 1) / (2 * BM);
+    p.n_tiles = (g.N + BN2 - 1) / BN2;
+    p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
+    p.flags = g.flags; p.B = g.B; p.film_H = g.film_H; p.c_clamp = g.c_clamp; p.resid_clamp = g.resid_clamp;
+    p.film_bstride = g.film_bstride; p.gate_bstride = g.gate_bstride;
+    p.bias = g.bias; p.mask = g.mask; p.film = g.film; p.gate = g.gate; p.resid = g.resid;
+    p.out_f32 = g.out_f32; p.out_hi = g.out_hi; p.out_lo = g.out_lo;
+    if (!g_attr2) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) { g_err2 = "cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc2_kernel"; return e; }
+        g_attr2 = true;
+    }
+    const int pairs = num_sms / 2;
+    const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
+    gemm_tc2_kernel<<<2 * clusters, THREADS, SMEM_BYTES, s>>>(maps, p);
+    return cudaGetLastError();
+}
+
+}  // namespace st
