@@ -333,7 +333,8 @@ def main():
         ms_a, fl_a, by_a, ln_a = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
         lib.st_profile_end(h, ms_a, fl_a, by_a, ln_a)
         prof = {name: dict(ms=ms_a[i], flops=fl_a[i], bytes=by_a[i], launches=int(ln_a[i]))
-                for i, name in enumerate(("gemm", "attention", "ln"))}
+                for i, name in enumerate(_lib.ST_PROF_NAMES)}
+        prof["gemm"] = {k: sum(v[k] for n_, v in prof.items() if n_.startswith("gemm_")) for k in ("ms", "flops", "bytes", "launches")}
     if world > 1:
         # non-root ranks must take part in nothing here; keep ranks aligned
         dist.barrier()
@@ -397,7 +398,8 @@ def main():
                      "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
                      "peak_source": peak_src, "launches": gm["launches"], "kernel_ms_per_step": gm["ms"],
                      "note": "algorithmic FLOPs (2*rows*N*K*taps); the bf16x3 split issues 3 MMAs per algorithmic MAC"},
-        "breakdown_ms_per_step": {k: v["ms"] for k, v in prof.items()},
+        "breakdown_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
+        "breakdown_tflops": {k: round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1) for k, v in prof.items() if v["flops"] > 0},
         "attention": {"tflops": prof["attention"]["flops"] / max(prof["attention"]["ms"], 1e-9) / 1e9},
         "work": {"hoisted_tflop_per_step": hoisted / 1e12, "faithful_tflop_per_step": faithful / 1e12,
                  "whole_solve_tflops_hoisted": hoisted / 1e12 / sec_step / max(world, 1) * 1.0},

@@ -110,7 +110,9 @@ int64_t st_launch_count(const st_handle* h);
  * the listed classes is bracketed by events on the launching stream.  st_profile_end synchronises
  * the device and fills four arrays of ST_PROF_NCAT entries: summed milliseconds, algorithmic FLOPs,
  * algorithmic bytes and launch counts per class. */
-enum { ST_PROF_GEMM = 0, ST_PROF_ATTN = 1, ST_PROF_LN = 2, ST_PROF_NCAT = 3 };
+enum { ST_PROF_GEMM = 0 /* in_proj, final_proj, test hooks */, ST_PROF_ATTN = 1 /* prep + attention */, ST_PROF_LN = 2,
+       ST_PROF_GEMM_QKV = 3, ST_PROF_GEMM_O = 4, ST_PROF_GEMM_C1 = 5, ST_PROF_GEMM_C2 = 6, ST_PROF_GEMM_LSC = 7,
+       ST_PROF_GEMM_COND = 8 /* per-solve cond_proj + in_proj mu-half */, ST_PROF_NCAT = 9 };
 int st_profile_begin(st_handle* h);
 int st_profile_end(st_handle* h, double* ms, double* flops, double* bytes, int64_t* launches);
 

@@ -9,7 +9,8 @@ _LIB = None
 
 ST_EULER, ST_MIDPOINT, ST_RK4, ST_DOPRI5_FIXED = 0, 1, 2, 3
 ST_ENGINE_TCGEN05, ST_ENGINE_SIMT = 0, 1
-ST_PROF_GEMM, ST_PROF_ATTN, ST_PROF_LN, ST_PROF_NCAT = 0, 1, 2, 3
+ST_PROF_NAMES = ("gemm_other", "attention", "ln", "gemm_qkv", "gemm_o", "gemm_conv1", "gemm_conv2", "gemm_lsc", "gemm_cond")
+ST_PROF_NCAT = len(ST_PROF_NAMES)
 
 # every symbol include/stabletts_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [

@@ -254,7 +254,8 @@ int ensure_ws(st_handle* h, Workspace& w, int B, int T, int cfg) {
 }
 
 // ----- GEMM dispatch -------------------------------------------------------------------------------
-int run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const Act* a1, const Act& out, cudaStream_t s) {
+int run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const Act* a1, const Act& out, cudaStream_t s,
+             int prof_cat = ST_PROF_GEMM) {
     const bool tc = h->engine == ST_ENGINE_TCGEN05;
     g.n_src = a1 ? 2 : 1;
     const Act* as[2] = {a0, a1};
@@ -270,7 +271,7 @@ int run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const Act
     g.taps = w.taps; g.N = w.N; g.Ktot = w.K;
     g.out_f32 = out.f32; g.out_hi = out.hi; g.out_lo = out.lo;
     if (out.C != w.N) return fail(h, "internal: GEMM N mismatch");
-    st_handle::ProfRec pr{ST_PROF_GEMM, 2.0 * g.BB * g.T * (double)g.N * g.Ktot * g.taps,
+    st_handle::ProfRec pr{prof_cat, 2.0 * g.BB * g.T * (double)g.N * g.Ktot * g.taps,
                           (double)g.BB * g.T * ((double)g.Ktot * 4 + (double)g.N * ((out.f32 ? 4 : 0) + (out.hi ? 4 : 0))), nullptr, nullptr};
     if (h->prof_on) { pr.e0 = h->take_event(); pr.e1 = h->take_event(); cudaEventRecord(pr.e0, s); }
     h->launches++;
@@ -297,11 +298,11 @@ int precompute_cond(st_handle* h, Workspace& w, const float* mu, const float* ma
     GemmArgs g;
     g.BB = w.Bc; g.T = w.T; g.a_bmod = w.Bc; g.B = w.B; g.resid_clamp = w.Bc - 1;
     g.flags = EPI_BIAS | EPI_SILU;
-    if (run_gemm(h, g, h->cond0, &w.mut, nullptr, w.C1, s)) return 1;
-    if (run_gemm(h, g, h->cond2, &w.C1, nullptr, w.C2, s)) return 1;
+    if (run_gemm(h, g, h->cond0, &w.mut, nullptr, w.C1, s, ST_PROF_GEMM_COND)) return 1;
+    if (run_gemm(h, g, h->cond2, &w.C1, nullptr, w.C2, s, ST_PROF_GEMM_COND)) return 1;
     g.flags = EPI_BIAS;
-    if (run_gemm(h, g, h->cond4, &w.C2, nullptr, w.C3, s)) return 1;
-    if (run_gemm(h, g, h->inmu, &w.C3, nullptr, w.P, s)) return 1;
+    if (run_gemm(h, g, h->cond4, &w.C2, nullptr, w.C3, s, ST_PROF_GEMM_COND)) return 1;
+    if (run_gemm(h, g, h->inmu, &w.C3, nullptr, w.P, s, ST_PROF_GEMM_COND)) return 1;
     // adaLN: rows = c (B) [+ fake_speaker]
     ST_CUDA(cudaMemcpyAsync(w.cin, c, sizeof(float) * (size_t)w.B * d.gin, cudaMemcpyDeviceToDevice, s));
     if (w.cfg)
@@ -362,7 +363,7 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
             GemmArgs g = base(EPI_BIAS | EPI_FILM | EPI_MASK);
             g.film = film_l; g.film_bstride = film_bstride;
             Act out = w.X[xb]; out.hi = nullptr; out.lo = nullptr;     // consumed by LN only
-            if (run_gemm(h, g, h->lsc[l - n_lsc], &w.X[cur], &w.X[sk], out, s)) return 1;
+            if (run_gemm(h, g, h->lsc[l - n_lsc], &w.X[cur], &w.X[sk], out, s, ST_PROF_GEMM_LSC)) return 1;
             ln.xin = w.X[xb].f32; ln.has_film = 0;
         }
         ln.shift = ada_l; ln.scale = ada_l + H;
@@ -370,7 +371,7 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
         ST_LAUNCH_P(ST_PROF_LN, 0, (double)w.BB * w.T * H * (4 + (ln.has_film ? 4 : 0) + 4), s, launch_film_ln_mod(ln, s));
         {   // q,k,v projections as one N=3H GEMM (models/diffusion_transformer.py:59-61)
             GemmArgs g = base(EPI_BIAS);
-            if (run_gemm(h, g, h->qkv[l], &w.U, nullptr, w.QKV, s)) return 1;
+            if (run_gemm(h, g, h->qkv[l], &w.U, nullptr, w.QKV, s, ST_PROF_GEMM_QKV)) return 1;
         }
         {
             AttnArgs a;
@@ -388,7 +389,7 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
             GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
             g.gate = ada_l + 2 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
             Act out = w.X[xb]; out.hi = nullptr; out.lo = nullptr;
-            if (run_gemm(h, g, h->wo[l], &w.AO, nullptr, out, s)) return 1;
+            if (run_gemm(h, g, h->wo[l], &w.AO, nullptr, out, s, ST_PROF_GEMM_O)) return 1;
         }
         {   // LN2 + modulate, FFN input mask (:112, :26)
             LnArgs l2 = ln;
@@ -398,12 +399,12 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
         }
         {   // conv_1 + SiLU, (h * mask) feeds conv_2 (:26-29)
             GemmArgs g = base(EPI_BIAS | EPI_SILU | EPI_MASK);
-            if (run_gemm(h, g, h->c1[l], &w.U, nullptr, w.Hid, s)) return 1;
+            if (run_gemm(h, g, h->c1[l], &w.U, nullptr, w.Hid, s, ST_PROF_GEMM_C1)) return 1;
         }
         {   // x += gate_mlp * (conv_2(h) * mask)   (:29-30, :112)
             GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
             g.gate = ada_l + 5 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
-            if (run_gemm(h, g, h->c2[l], &w.Hid, nullptr, w.X[xb], s)) return 1;
+            if (run_gemm(h, g, h->c2[l], &w.Hid, nullptr, w.X[xb], s, ST_PROF_GEMM_C2)) return 1;
         }
         cur = xb;
     }

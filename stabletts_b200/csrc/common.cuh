@@ -129,7 +129,16 @@ cudaError_t launch_attention_tc(const AttnArgs& a, const AttnTcScratch& sc, cuda
 const char* attention_tc_last_error();
 
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+// two floats -> packed (hi0,hi1) and (lo0,lo1) bf16x2 words: one cvt.rn.bf16x2 per plane
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xFFFF0000u);
+    __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
 
 __device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
     hi = __float2bfloat16_rn(v);

@@ -31,7 +31,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;             // bf16 elements = 128 bytes = one SW128 row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;            // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KB
 
 struct TcMaps {
@@ -147,7 +147,7 @@ template <int BN> struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (BN == 256) ? 2 : 3;
     static constexpr int TMEM_COLS = 2 * BN;                 // two accumulator stages (power of 2 >= 32)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 4096 /*epilogue staging*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -176,7 +176,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -253,7 +253,8 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         //          segment (residual read, fp32 / split-bf16 writes); per-column vectors (bias, gate,
         //          FiLM) live in registers for the whole chunk, per-row mask for the whole tile.
         const int wq = warp & 3;                       // TMEM lane quarter this warp may access
-        float4* stg = reinterpret_cast<float4*>(smem + C::STAGES * C::STAGE_BYTES + 256) + wq * 256;   // 4 KB per warp
+        float4* stg = reinterpret_cast<float4*>(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 4) * 256;   // 4 KB per warp
+        const int eh = (warp - 4) >> 2;                // two warps share a lane quarter: even / odd 32-column chunks
         const int rs = lane >> 3, c4 = lane & 7;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -275,7 +276,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = eh * 32; c0 < BN; c0 += 64) {
                 if (n0 + c0 >= p.N) break;             // warp-uniform
                 {
                     uint32_t v[32];
@@ -296,38 +297,40 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         fg = __ldg(reinterpret_cast<const float4*>(film + n));
                         fb = __ldg(reinterpret_cast<const float4*>(film + p.film_H + n));
                     }
-                    float4 sv[8], rv[8];
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rl = it * 4 + rs;
-                        sv[it] = stg[rl * 8 + (c4 ^ (rl & 7))];
-                        rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if ((p.flags & EPI_RESID) && t0 + rl < p.T)
-                            rv[it] = __ldg(reinterpret_cast<const float4*>(resid + (long)(t0 + rl) * p.N + n));
-                    }
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float4 sv[4], rv[4];
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int t = t0 + it * 4 + rs;
-                        if (t >= p.T) continue;
-                        float x[4] = {sv[it].x + b4.x, sv[it].y + b4.y, sv[it].z + b4.z, sv[it].w + b4.w};
-                        if (p.flags & EPI_SILU) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
+                        for (int i = 0; i < 4; ++i) {
+                            const int rl = (hf * 4 + i) * 4 + rs;
+                            sv[i] = stg[rl * 8 + (c4 ^ (rl & 7))];
+                            rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if ((p.flags & EPI_RESID) && t0 + rl < p.T)
+                                rv[i] = __ldg(reinterpret_cast<const float4*>(resid + (long)(t0 + rl) * p.N + n));
                         }
-                        const float m = mrow[it];
-                        x[0] = (fg.x * x[0] + fb.x) * m * g4.x + rv[it].x;
-                        x[1] = (fg.y * x[1] + fb.y) * m * g4.y + rv[it].y;
-                        x[2] = (fg.z * x[2] + fb.z) * m * g4.z + rv[it].z;
-                        x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[it].w;
-                        const long o = obase + (long)t * p.N + n;
-                        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
-                        if (p.out_hi) {
-                            bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-                            split_bf16(x[0], h0, l0); split_bf16(x[1], h1, l1); split_bf16(x[2], h2, l2); split_bf16(x[3], h3, l3);
-                            __nv_bfloat162 ha = __halves2bfloat162(h0, h1), hb = __halves2bfloat162(h2, h3);
-                            __nv_bfloat162 la = __halves2bfloat162(l0, l1), lb = __halves2bfloat162(l2, l3);
-                            *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
-                            *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int it = hf * 4 + i;
+                            const int t = t0 + it * 4 + rs;
+                            if (t >= p.T) continue;
+                            float x[4] = {sv[i].x + b4.x, sv[i].y + b4.y, sv[i].z + b4.z, sv[i].w + b4.w};
+                            if (p.flags & EPI_SILU) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
+                            }
+                            const float m = mrow[it];
+                            x[0] = (fg.x * x[0] + fb.x) * m * g4.x + rv[i].x;
+                            x[1] = (fg.y * x[1] + fb.y) * m * g4.y + rv[i].y;
+                            x[2] = (fg.z * x[2] + fb.z) * m * g4.z + rv[i].z;
+                            x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[i].w;
+                            const long o = obase + (long)t * p.N + n;
+                            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
+                            if (p.out_hi) {
+                                uint32_t h01, l01, h23, l23;
+                                split_bf16x2(x[0], x[1], h01, l01); split_bf16x2(x[2], x[3], h23, l23);
+                                *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(h01, h23);
+                                *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(l01, l23);
+                            }
                         }
                     }
                 }

@@ -10,7 +10,7 @@
 //                                TMA loads complete_tx on the leader's barrier (cta_group::2 TMA form)
 //   empty[s]       each CTA      count 1: tcgen05.commit.cta_group::2 multicast from the leader's MMA thread
 //   tmem_full[a]   each CTA      count 1: multicast commit after a tile's last k-block
-//   tmem_empty[a]  leader only   count 8: 4 epilogue warps of each CTA (the peer arrives remotely, mapa)
+//   tmem_empty[a]  leader only   count 16: 8 epilogue warps of each CTA (the peer arrives remotely, mapa)
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <string>
@@ -29,12 +29,12 @@ constexpr int BM = 128;                 // rows per CTA (pair tile: 256)
 constexpr int BN2 = 256;                // pair tile width; each CTA stages 128 B rows
 constexpr int BK = 64;
 constexpr int UK = 16;
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;            // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue
 constexpr int TILE_BYTES = 128 * BK * 2;            // 16 KB: A plane tile and B-half plane tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, Bh_hi, Bh_lo = 64 KB
 constexpr int STAGES = 3;
 constexpr int TMEM_COLS = 512;                      // two 256-column accumulator stages
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * 4096;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 4096;
 
 struct Maps2 { CUtensorMap a_hi[2], a_lo[2], w_hi, w_lo; };
 
@@ -73,7 +73,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 16); }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc_2sm<TMEM_COLS>(tmem_slot);
@@ -143,7 +143,8 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
     } else if (warp >= 4) {
         // ================= epilogue (both CTAs, own 128 rows) =================
         const int wq = warp & 3;
-        float4* stg = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES + 256) + wq * 256;
+        float4* stg = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 4) * 256;
+        const int eh = (warp - 4) >> 2;                // two warps share a lane quarter: even / odd 32-column chunks
         const int rs = lane >> 3, c4 = lane & 7;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
@@ -166,7 +167,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN2; c0 += 32) {
+            for (int c0 = eh * 32; c0 < BN2; c0 += 64) {
                 if (n0 + c0 >= p.N) break;
                 {
                     uint32_t v[32];
@@ -179,7 +180,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
                 }
                 __syncwarp();
                 const int n = n0 + c0 + c4 * 4;
-                if (n < p.N) {
+                if (n < p.N) {                         // N % 4 == 0: a float4 column group is all-in or all-out
                     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = b4;
                     if (p.flags & EPI_BIAS) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
                     if (p.flags & EPI_GATE) g4 = __ldg(reinterpret_cast<const float4*>(gate + n));
@@ -187,38 +188,40 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
                         fg = __ldg(reinterpret_cast<const float4*>(film + n));
                         fb = __ldg(reinterpret_cast<const float4*>(film + p.film_H + n));
                     }
-                    float4 sv[8], rv[8];
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rl = it * 4 + rs;
-                        sv[it] = stg[rl * 8 + (c4 ^ (rl & 7))];
-                        rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if ((p.flags & EPI_RESID) && t0 + rl < p.T)
-                            rv[it] = __ldg(reinterpret_cast<const float4*>(resid + (long)(t0 + rl) * p.N + n));
-                    }
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float4 sv[4], rv[4];
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int t = t0 + it * 4 + rs;
-                        if (t >= p.T) continue;
-                        float x[4] = {sv[it].x + b4.x, sv[it].y + b4.y, sv[it].z + b4.z, sv[it].w + b4.w};
-                        if (p.flags & EPI_SILU) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
+                        for (int i = 0; i < 4; ++i) {
+                            const int rl = (hf * 4 + i) * 4 + rs;
+                            sv[i] = stg[rl * 8 + (c4 ^ (rl & 7))];
+                            rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if ((p.flags & EPI_RESID) && t0 + rl < p.T)
+                                rv[i] = __ldg(reinterpret_cast<const float4*>(resid + (long)(t0 + rl) * p.N + n));
                         }
-                        const float m = mrow[it];
-                        x[0] = (fg.x * x[0] + fb.x) * m * g4.x + rv[it].x;
-                        x[1] = (fg.y * x[1] + fb.y) * m * g4.y + rv[it].y;
-                        x[2] = (fg.z * x[2] + fb.z) * m * g4.z + rv[it].z;
-                        x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[it].w;
-                        const long o = obase + (long)t * p.N + n;
-                        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
-                        if (p.out_hi) {
-                            bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-                            split_bf16(x[0], h0, l0); split_bf16(x[1], h1, l1); split_bf16(x[2], h2, l2); split_bf16(x[3], h3, l3);
-                            __nv_bfloat162 ha = __halves2bfloat162(h0, h1), hb = __halves2bfloat162(h2, h3);
-                            __nv_bfloat162 la = __halves2bfloat162(l0, l1), lb = __halves2bfloat162(l2, l3);
-                            *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
-                            *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int it = hf * 4 + i;
+                            const int t = t0 + it * 4 + rs;
+                            if (t >= p.T) continue;
+                            float x[4] = {sv[i].x + b4.x, sv[i].y + b4.y, sv[i].z + b4.z, sv[i].w + b4.w};
+                            if (p.flags & EPI_SILU) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
+                            }
+                            const float m = mrow[it];
+                            x[0] = (fg.x * x[0] + fb.x) * m * g4.x + rv[i].x;
+                            x[1] = (fg.y * x[1] + fb.y) * m * g4.y + rv[i].y;
+                            x[2] = (fg.z * x[2] + fb.z) * m * g4.z + rv[i].z;
+                            x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[i].w;
+                            const long o = obase + (long)t * p.N + n;
+                            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
+                            if (p.out_hi) {
+                                uint32_t h01, l01, h23, l23;
+                                split_bf16x2(x[0], x[1], h01, l01); split_bf16x2(x[2], x[3], h23, l23);
+                                *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(h01, h23);
+                                *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(l01, l23);
+                            }
                         }
                     }
                 }
