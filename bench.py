@@ -306,11 +306,16 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), out
 
-    for _ in range(args.warmup):
-        step_device()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                 # started BEFORE warm-up: nvidia-smi start-up stalls the driver for ~100 ms
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    th0 = time.perf_counter()
+    step_device()                       # host-side enqueue time of one step (no sync): launch-bound check
+    host_ms = (time.perf_counter() - th0) * 1e3
+    torch.cuda.synchronize()
     l0 = model.estimator.launch_count()
     ms_dev, out_dev = timed(step_device, args.steps)
     launches = model.estimator.launch_count() - l0
@@ -393,7 +398,7 @@ def main():
                    "samples": clocks["samples"], "power_w_max": clocks.get("power_w_max")},
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 2),
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 split-bf16 conv-GEMM, all launches of one solve)",
                      "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
                      "peak_source": peak_src, "launches": gm["launches"], "kernel_ms_per_step": gm["ms"],

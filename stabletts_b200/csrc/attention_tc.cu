@@ -25,6 +25,9 @@
 #include <math_constants.h>
 #include <mutex>
 #include <string>
+#include <cstring>
+#include <cstdlib>
+#include <cstdio>
 
 namespace st {
 
@@ -448,6 +451,272 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// v2 pipeline: O accumulates in TMEM (PV_j issued with accumulate), S is double-buffered in TMEM and
+// K in shared memory so S_{j+1} (and S_{j+2}) run on the tensor core while the softmax warps work on
+// S_j, and the running max is LAZY (FA4-style): exponentials use a stale max m_used and O / l are only
+// rescaled when some row's block max exceeds m_used by more than 2^8 — then, and only then, the softmax
+// warps wait for PV_{j-1}, read O from TMEM, scale it and store it back (tcgen05.st).  The per-block
+// critical path is max(softmax, MMA) instead of their sum.
+// ----------------------------------------------------------------------------------------------
+constexpr int ATT2_SMEM = 2 * Q_BYTES + 4 * K_BYTES + 2 * K_BYTES + 2 * P_BYTES + 1024;   // 112 KB + barriers/alignment
+constexpr int TMEM_COLS_ATT2 = 256;         // S0 [0,64) S1 [64,128) O [128,192)
+constexpr float LAZY_THRESHOLD = 8.0f;      // log2 domain: p <= 2^8 between rescales
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(A_THREADS, 2)
+attention_tc2_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);          // 16 barriers + tmem slot live in the alignment slack
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 160 + 1023) & ~uintptr_t(1023));
+    uint8_t* sQh = smem;                 uint8_t* sQl = sQh + Q_BYTES;
+    uint8_t* sK = sQl + Q_BYTES;         // [2][hi 8K | lo 8K]
+    uint8_t* sVh = sK + 4 * K_BYTES;     uint8_t* sVl = sVh + K_BYTES;
+    uint8_t* sPh = sVl + K_BYTES;        uint8_t* sPl = sPh + P_BYTES;
+    uint64_t *q_full = bars, *k_full = bars + 1 /*[2]*/, *k_empty = bars + 3 /*[2]*/, *v_full = bars + 5,
+             *pv_done = bars + 6, *s_full = bars + 7 /*[2]*/, *p_full = bars + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    if (sPl + P_BYTES > smem_raw + ATT2_SMEM) __trap();              // dynamic smem base less aligned than assumed
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bb = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
+    const int b = bb % p.B;
+    const int kvlen = p.kvlen[b];
+    const int head = bb * p.n_heads + h;
+
+    if (q0 >= kvlen) {
+        for (int i = threadIdx.x; i < AQ * (DH / 4); i += A_THREADS) {
+            const int r = i / (DH / 4), c4 = (i % (DH / 4)) * 4, t = q0 + r;
+            if (t < p.T) {
+                const long o = ((long)bb * p.T + t) * p.H + h * DH + c4;
+                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.out_hi) { *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(0, 0); *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(0, 0); }
+            }
+        }
+        return;
+    }
+    const int nb = (kvlen + AK - 1) / AK;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 10; ++i) mbar_init(&bars[i], i == 9 ? 4 : 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS_ATT2));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_O = tmem_base + 128;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(q_full, 2 * Q_BYTES);
+            tma_load_3d(&maps.q_hi, q_full, sQh, 0, q0, head);
+            tma_load_3d(&maps.q_lo, q_full, sQl, 0, q0, head);
+            for (int j = 0; j < nb; ++j) {
+                const int slot = j & 1;
+                mbar_wait(&k_empty[slot], ((j >> 1) & 1) ^ 1);
+                mbar_expect_tx(&k_full[slot], 2 * K_BYTES);
+                tma_load_3d(&maps.k_hi, &k_full[slot], sK + slot * 2 * K_BYTES, 0, j * AK, head);
+                tma_load_3d(&maps.k_lo, &k_full[slot], sK + slot * 2 * K_BYTES + K_BYTES, 0, j * AK, head);
+                mbar_wait(pv_done, (j & 1) ^ 1);                 // PV_{j-1} finished reading V (and P)
+                mbar_expect_tx(v_full, 2 * K_BYTES);
+                tma_load_3d(&maps.v_hi, v_full, sVh, j * AK, 0, head);
+                tma_load_3d(&maps.v_lo, v_full, sVl, j * AK, 0, head);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_n(64);
+        const uint64_t dQh = make_sw128_desc(smem_u32(sQh)), dQl = make_sw128_desc(smem_u32(sQl));
+        const uint64_t dVh = make_sw128_desc(smem_u32(sVh)), dVl = make_sw128_desc(smem_u32(sVl));
+        const uint64_t dPh = make_sw128_desc(smem_u32(sPh)), dPl = make_sw128_desc(smem_u32(sPl));
+        auto issue_S = [&](int j) {          // S_j -> TMEM buffer j&1, from K ring slot j&1
+            const int slot = j & 1;
+            const uint64_t dKh = make_sw128_desc(smem_u32(sK + slot * 2 * K_BYTES));
+            const uint64_t dKl = make_sw128_desc(smem_u32(sK + slot * 2 * K_BYTES + K_BYTES));
+            const uint32_t tS = tmem_base + slot * 64;
+#pragma unroll
+            for (int k = 0; k < DH / 16; ++k) {
+                const uint64_t adv = (uint64_t)(k * 2);
+                umma_bf16(tS, dQl + adv, dKh + adv, idesc, k != 0);
+                umma_bf16(tS, dQh + adv, dKl + adv, idesc, 1);
+                umma_bf16(tS, dQh + adv, dKh + adv, idesc, 1);
+            }
+            umma_commit(&k_empty[slot]);
+            umma_commit(&s_full[slot]);
+        };
+        mbar_wait(q_full, 0);
+        for (int j = 0; j < 2 && j < nb; ++j) {
+            mbar_wait(&k_full[j], 0);
+            tc_fence_after();
+            if (elect_one()) issue_S(j);
+            __syncwarp();
+        }
+        for (int j = 0; j < nb; ++j) {
+            mbar_wait(p_full, j & 1);
+            mbar_wait(v_full, j & 1);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < AK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 2);
+                    umma_bf16(tmem_O, dPl + adv, dVh + adv, idesc, (j | k) != 0);
+                    umma_bf16(tmem_O, dPh + adv, dVl + adv, idesc, 1);
+                    umma_bf16(tmem_O, dPh + adv, dVh + adv, idesc, 1);
+                }
+                umma_commit(pv_done);
+            }
+            __syncwarp();
+            if (j + 2 < nb) {                // S buffer j&1 was consumed by softmax_j (implied by p_full_j)
+                mbar_wait(&k_full[j & 1], ((j + 2) >> 1) & 1);
+                tc_fence_after();
+                if (elect_one()) issue_S(j + 2);
+                __syncwarp();
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        const int r = wq * 32 + lane;
+        const int t = q0 + r;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const int prefix = p.prefix[b];
+        const float* mrow = p.mask + (long)b * p.T;
+        float m_used = -CUDART_INF_F, l_run = 0.f;
+        uint8_t* pr_hi = sPh + r * 128;
+        uint8_t* pr_lo = sPl + r * 128;
+        const int sw = r & 7;
+        uint32_t v[32];
+
+        for (int j = 0; j < nb; ++j) {
+            const int k0 = j * AK;
+            const uint32_t tS = tmem_base + (j & 1) * 64 + lane_addr;
+            const bool need_mask = k0 + AK > prefix;
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            float cand = -CUDART_INF_F;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                tmem_ld32(tS + half * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float sv = __uint_as_float(v[i]);
+                    if (need_mask) { const int kk = k0 + half * 32 + i; if (kk >= kvlen || __ldg(mrow + kk) == 0.f) sv = -CUDART_INF_F; }
+                    cand = fmaxf(cand, sv);
+                }
+            }
+            bool waited_pv = (j == 0);
+            if (__any_sync(0xffffffffu, cand > m_used + LAZY_THRESHOLD)) {
+                const float m_new = fmaxf(m_used, cand);
+                const float factor = (m_new == -CUDART_INF_F) ? 1.f : exp2f(m_used - m_new);     // m_used = -inf -> 0
+                l_run *= factor;
+                if (j > 0) {                 // rescale O in TMEM: no PV may be in flight
+                    mbar_wait(pv_done, (j - 1) & 1);
+                    tc_fence_after();
+                    waited_pv = true;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        tmem_ld32(tmem_O + lane_addr + half * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
+                        tmem_st32(tmem_O + lane_addr + half * 32, v);
+                    }
+                    tmem_st_wait();
+                }
+                m_used = m_new;
+            }
+            const float m_eff = (m_used == -CUDART_INF_F) ? 0.f : m_used;
+            if (!waited_pv) { mbar_wait(pv_done, (j - 1) & 1); }     // P buffer free (PV_{j-1} retired)
+            float psum = 0.f;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                tmem_ld32(tS + half * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t hw[4], lw[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float pv2[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = c * 8 + e * 2 + u;
+                            float sv = __uint_as_float(v[i]);
+                            if (need_mask) { const int kk = k0 + half * 32 + i; if (kk >= kvlen || __ldg(mrow + kk) == 0.f) sv = -CUDART_INF_F; }
+                            const float pe = exp2f(sv - m_eff);
+                            psum += pe;
+                            pv2[u] = pe;
+                        }
+                        split_bf16x2(pv2[0], pv2[1], hw[e], lw[e]);
+                    }
+                    const int off = (((half * 4 + c) ^ sw) << 4);
+                    *reinterpret_cast<uint4*>(pr_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(pr_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+            }
+            l_run += psum;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        // O complete after PV_{nb-1}
+        mbar_wait(pv_done, (nb - 1) & 1);
+        tc_fence_after();
+        const bool valid = t < p.T && mrow[min(t, p.T - 1)] != 0.f && l_run > 0.f;
+        const float inv = valid ? 1.0f / l_run : 0.f;
+        const long o = ((long)bb * p.T + t) * p.H + h * DH;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            tmem_ld32(tmem_O + lane_addr + half * 32, v);
+            tmem_ld_wait();
+            if (t < p.T) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c * 8 + e]) * inv;
+                    const long oc = o + half * 32 + c * 8;
+                    if (p.out_f32) {
+                        *reinterpret_cast<float4*>(p.out_f32 + oc) = make_float4(f[0], f[1], f[2], f[3]);
+                        *reinterpret_cast<float4*>(p.out_f32 + oc + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                    }
+                    if (p.out_hi) {
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) split_bf16x2(f[2 * e], f[2 * e + 1], hw[e], lw[e]);
+                        *reinterpret_cast<uint4*>(p.out_hi + oc) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4*>(p.out_lo + oc) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS_ATT2));
+    }
+}
+
 std::mutex g_att_mu;
 bool g_att_attr = false;
 std::string g_att_err;
@@ -488,13 +757,23 @@ cudaError_t launch_attention_tc(const AttnArgs& a, const AttnTcScratch& sc, cuda
     p.BB = a.BB; p.B = a.B; p.T = a.T; p.H = a.H; p.n_heads = a.n_heads;
     p.mask = a.mask; p.kvlen = a.kvlen; p.prefix = a.prefix;
     p.out_f32 = a.out_f32; p.out_hi = a.out_hi; p.out_lo = a.out_lo;
+    static int version = -1;
+    if (version < 0) { const char* e = getenv("STABLETTS_B200_ATT"); version = (e && !strcmp(e, "v1")) ? 1 : 2; }
     if (!g_att_attr) {
         cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-        if (e != cudaSuccess) { g_att_err = "cudaFuncSetAttribute failed for attention_tc_kernel"; return e; }
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM);
+        if (e != cudaSuccess) { g_att_err = "cudaFuncSetAttribute failed for attention_tc kernels"; return e; }
+        if (getenv("STABLETTS_B200_DEBUG")) {
+            int o1 = 0, o2 = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, attention_tc_kernel, A_THREADS, ATT_SMEM);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, attention_tc2_kernel, A_THREADS, ATT2_SMEM);
+            fprintf(stderr, "[stabletts_b200] attention CTAs/SM: v1 %d, v2 %d\n", o1, o2);
+        }
         g_att_attr = true;
     }
     dim3 grid((a.T + AQ - 1) / AQ, a.n_heads, a.BB);
-    attention_tc_kernel<<<grid, A_THREADS, ATT_SMEM, s>>>(maps, p);
+    if (version == 1) attention_tc_kernel<<<grid, A_THREADS, ATT_SMEM, s>>>(maps, p);
+    else attention_tc2_kernel<<<grid, A_THREADS, ATT2_SMEM, s>>>(maps, p);
     return cudaGetLastError();
 }
 
