@@ -212,15 +212,13 @@ void layout_ws(const st_handle* h, Workspace& w, void* base, size_t cap, int B, 
     mk(w.P, bct, d.hidden, true, false);
     for (int i = 0; i < 5; ++i) mk(w.X[i], bbt, d.hidden, true, tc);
     mk(w.U, bbt, d.hidden, !tc, tc);
-    mk(w.QKV, bbt, 3 * d.hidden, true, false);
+    mk(w.QKV, bbt, 3 * d.hidden, !tc, tc);       // tcgen05: RoPE'd split planes straight from the GEMM epilogue
     mk(w.AO, bbt, d.hidden, !tc, tc);
     mk(w.Hid, bbt, d.filter, !tc, tc);
     w.kvlen = bp.take<int>(B);
     w.prefix = bp.take<int>(B);
-    if (tc) {
-        const size_t qk = bbt * d.hidden, vt = attention_tc_scratch_elems(w.BB, T, d.hidden);
-        w.att.q_hi = bp.take<bf16>(qk); w.att.q_lo = bp.take<bf16>(qk);
-        w.att.k_hi = bp.take<bf16>(qk); w.att.k_lo = bp.take<bf16>(qk);
+    if (tc && getenv("STABLETTS_B200_VT")) {
+        const size_t vt = attention_tc_scratch_elems(w.BB, T, d.hidden);
         w.att.vt_hi = bp.take<bf16>(vt); w.att.vt_lo = bp.take<bf16>(vt);
     }
     w.rope_cs = bp.take<float>((size_t)T * 32);
@@ -370,16 +368,18 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
         ln.u_f32 = w.U.f32; ln.u_hi = w.U.hi; ln.u_lo = w.U.lo;
         ST_LAUNCH_P(ST_PROF_LN, 0, (double)w.BB * w.T * H * (4 + (ln.has_film ? 4 : 0) + 4), s, launch_film_ln_mod(ln, s));
         {   // q,k,v projections as one N=3H GEMM (models/diffusion_transformer.py:59-61)
-            GemmArgs g = base(EPI_BIAS);
+            // tcgen05 engine: partial RoPE + softmax scale fused in the epilogue, split-bf16 output
+            GemmArgs g = base(h->engine == ST_ENGINE_TCGEN05 ? (EPI_BIAS | EPI_ROPE) : EPI_BIAS);
+            g.rope_H = H;
             if (run_gemm(h, g, h->qkv[l], &w.U, nullptr, w.QKV, s, ST_PROF_GEMM_QKV)) return 1;
         }
         {
             AttnArgs a;
-            a.qkv = w.QKV.f32; a.rope_cs = w.rope_cs; a.mask = mask; a.kvlen = w.kvlen; a.prefix = w.prefix;
+            a.qkv = w.QKV.f32; a.qkv_hi = w.QKV.hi; a.qkv_lo = w.QKV.lo;
+            a.rope_cs = w.rope_cs; a.mask = mask; a.kvlen = w.kvlen; a.prefix = w.prefix;
             a.out_f32 = w.AO.f32; a.out_hi = w.AO.hi; a.out_lo = w.AO.lo;
             a.BB = w.BB; a.B = w.B; a.T = w.T; a.H = H; a.n_heads = d.n_heads;
             if (h->engine == ST_ENGINE_TCGEN05) {
-                h->launches++;     // prep kernel (the attention kernel is counted by ST_LAUNCH_P)
                 ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_tc(a, w.att, s));
             } else {
                 ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_simt(a, s));
@@ -831,10 +831,11 @@ int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* 
     ST_CUDA(cudaMalloc(&kvlen, sizeof(int) * B)); ST_CUDA(cudaMalloc(&prefix, sizeof(int) * B));
     ST_CUDA(cudaMalloc(&cs, sizeof(float) * T * 32));
     AttnTcScratch sc;
-    const size_t qk = (size_t)B * T * h->d.hidden, vt = attention_tc_scratch_elems(B, T, h->d.hidden);
+    bf16 *qh = nullptr, *ql = nullptr;
+    const size_t nq = (size_t)B * T * 3 * h->d.hidden, vt = attention_tc_scratch_elems(B, T, h->d.hidden);
     if (tc) {
-        ST_CUDA(cudaMalloc(&sc.q_hi, qk * 2)); ST_CUDA(cudaMalloc(&sc.q_lo, qk * 2)); ST_CUDA(cudaMalloc(&sc.k_hi, qk * 2));
-        ST_CUDA(cudaMalloc(&sc.k_lo, qk * 2)); ST_CUDA(cudaMalloc(&sc.vt_hi, vt * 2)); ST_CUDA(cudaMalloc(&sc.vt_lo, vt * 2));
+        ST_CUDA(cudaMalloc(&qh, nq * 2)); ST_CUDA(cudaMalloc(&ql, nq * 2));
+        ST_CUDA(cudaMalloc(&sc.vt_hi, vt * 2)); ST_CUDA(cudaMalloc(&sc.vt_lo, vt * 2));
     }
     int rc = 0;
     do {
@@ -842,8 +843,9 @@ int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* 
             rc = fail(h, "attention prep failed"); break;
         }
         AttnArgs a;
-        a.qkv = qkv; a.rope_cs = cs; a.mask = mask; a.kvlen = kvlen; a.prefix = prefix; a.out_f32 = out;
+        a.qkv = qkv; a.qkv_hi = qh; a.qkv_lo = ql; a.rope_cs = cs; a.mask = mask; a.kvlen = kvlen; a.prefix = prefix; a.out_f32 = out;
         a.BB = B; a.B = B; a.T = T; a.H = h->d.hidden; a.n_heads = h->d.n_heads;
+        if (tc && launch_rope_split(qkv, cs, qh, ql, B, T, h->d.hidden, s) != cudaSuccess) { rc = fail(h, "rope_split failed"); break; }
         cudaError_t e = tc ? launch_attention_tc(a, sc, s) : launch_attention_simt(a, s);
         if (e != cudaSuccess) { rc = fail(h, std::string("attention launch failed: ") + cudaGetErrorString(e) + " / " + attention_tc_last_error()); break; }
     } while (0);
@@ -851,7 +853,7 @@ int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* 
     cudaError_t e = cudaGetLastError();
     if (!rc && e != cudaSuccess) rc = fail(h, std::string("st_test_attention: ") + cudaGetErrorString(e));
     cudaFree(kvlen); cudaFree(prefix); cudaFree(cs);
-    if (tc) { cudaFree(sc.q_hi); cudaFree(sc.q_lo); cudaFree(sc.k_hi); cudaFree(sc.k_lo); cudaFree(sc.vt_hi); cudaFree(sc.vt_lo); }
+    if (tc) { cudaFree(qh); cudaFree(ql); cudaFree(sc.vt_hi); cudaFree(sc.vt_lo); }
     return rc;
 }
 

@@ -1,27 +1,28 @@
-// tcgen05 masked multi-head attention with partial RoPE (models/diffusion_transformer.py:58-79,
-// 107-108, 123-198) — flash-style, split-bf16 operands, fp32 softmax.
+// tcgen05 masked multi-head attention (models/diffusion_transformer.py:58-79,107-108) — flash-style,
+// split-bf16 operands, fp32 softmax in the exp2 domain.
 //
-// Two kernels:
-//  1. qkv_prep_kernel: packed fp32 qkv (BB, T, 3H) -> per-head operand planes
-//        Q, K : [BB*nh][T][64]    split-bf16, RoPE applied, Q pre-scaled by log2(e)/sqrt(64)
-//        V^T  : [BB*nh][64][Tpad] split-bf16 (keys contiguous: the K-major B operand of P·V)
-//  2. attention_tc_kernel: one CTA per (128-query tile, head, batch row); per 64-key block
-//        S  = Q·K^T          tcgen05.mma 128x64x16, 3 split terms x 4 k-steps  -> TMEM (fp32)
-//        softmax             one thread per query row reads its S row from TMEM (tcgen05.ld): no
-//                            cross-thread reductions; online max/sum in the exp2 domain; P written
-//                            to shared memory as split-bf16 in the 128B-swizzled K-major layout
-//        PV = P·V            tcgen05.mma 128x64x16 (A = P from smem, B = V^T tile)  -> TMEM
-//        O  = O*corr + PV    in registers (tcgen05.ld of the PV tile)
-//     warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = softmax/epilogue.
-//     K and V have separate single-stage buffers so K_{j+1} streams in during softmax_j and V_{j+1}
-//     during S_{j+1}; 96 KB smem + 128 TMEM columns per CTA -> two CTAs per SM overlap each other's
-//     MMA and softmax phases.
-//
-// Mask semantics: keys with mask == 0 get probability exactly 0; query rows with mask == 0 are
-// written as 0 (the reference multiplies them by the mask afterwards, :111).
+// Input: the QKV projection's own output planes (BB, T, 3H) as split-bf16 (hi, lo).  RoPE and the
+// softmax scale are already applied by the GEMM epilogue (EPI_ROPE, gemm_epilogue.cuh), so Q, K and V
+// tiles are plain TMA boxes of that tensor — no re-layout pass:
+//     Q tile  [128 queries][64 dims]  channels [64h, 64h+64)        K-major A operand
+//     K tile  [ 64 keys   ][64 dims]  channels [H + 64h, ...)       K-major B operand of S = Q·K^T
+//     V tile  [ 64 keys   ][64 dims]  channels [2H + 64h, ...)      MN-major B operand of O += P·V
+// One CTA per (128-query tile, head, batch row); warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM
+// alloc), warps 2-5 = softmax (thread = query row, reads its S row straight from TMEM).
+//   * S is double-buffered in TMEM and K in shared memory: S_{j+1}, S_{j+2} run on the tensor core
+//     while the softmax warps work on S_j;
+//   * O accumulates in TMEM (PV_j issued with accumulate) and the running max is LAZY: exponentials
+//     use a stale max m_used; O and l are rescaled (tcgen05.ld/st) only when a block max exceeds it
+//     by more than 2^8, which after the first block is rare;
+//   * single softmax pass: p = ex2(s - m_used) is computed optimistically together with the block max
+//     and only redone in the rare rescale case; P goes to shared memory as split-bf16 in the 128B
+//     swizzled K-major layout the P·V MMA reads.
+//   112 KB smem + 256 TMEM columns per CTA -> two CTAs per SM.
+// Mask semantics: keys with mask == 0 get probability exactly 0; query rows with mask == 0 are written
+// as 0 (the reference multiplies them by the mask afterwards, :111).
 #include "common.cuh"
-#include <cuda.h>
-#include <cudaTypedefs.h>
+#include "tc_ptx.cuh"
+#include "gemm_epilogue.cuh"     // kQScale
 #include <math_constants.h>
 #include <mutex>
 #include <string>
@@ -37,6 +38,8 @@ const char* gemm_tc_last_error();
 
 namespace {
 
+using namespace ptx;
+
 constexpr int AQ = 128;          // queries per CTA (TMEM lanes)
 constexpr int AK = 64;           // keys per block
 constexpr int DH = 64;
@@ -44,10 +47,11 @@ constexpr int A_THREADS = 192;
 constexpr int Q_BYTES = AQ * DH * 2;        // 16 KB per plane
 constexpr int K_BYTES = AK * DH * 2;        // 8 KB per plane
 constexpr int P_BYTES = AQ * AK * 2;        // 16 KB per plane
-constexpr int ATT_SMEM = 2 * Q_BYTES + 4 * K_BYTES + 2 * P_BYTES + 1024 + 256;
-constexpr int TMEM_COLS_ATT = 128;          // S: [0,64)  PV: [64,128)
+constexpr int ATT_SMEM = 2 * Q_BYTES + 4 * K_BYTES + 2 * K_BYTES + 2 * P_BYTES + 1024;   // 112 KB + barriers/alignment
+constexpr int TMEM_COLS_ATT = 256;          // S0 [0,64) S1 [64,128) O [128,192)
+constexpr float LAZY_THRESHOLD = 8.0f;      // log2 domain: p <= 2^8 between rescales
 
-struct AttMaps { CUtensorMap q_hi, q_lo, k_hi, k_lo, v_hi, v_lo; };
+struct AttMaps { CUtensorMap q_hi, q_lo, kv_hi, kv_lo, vt_hi, vt_lo; };
 
 struct AttParams {
     int BB, B, T, H, n_heads;
@@ -55,186 +59,102 @@ struct AttParams {
     float* out_f32; bf16* out_hi; bf16* out_lo;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 rx;\n\t"
-        ".reg .pred px;\n\t"
-        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
-        "selp.b32 %0, 1, 0, px;\n\t"
-        "}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-__host__ __device__ constexpr uint32_t make_idesc_n(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
+// kind::f16 instruction descriptor, M=128, N=64, A K-major; B K-major or MN-major (bit 16)
+__host__ __device__ constexpr uint32_t att_idesc(bool b_mn) { return make_idesc_bf16(128, 64) | (b_mn ? (1u << 16) : 0u); }
 
 // ----------------------------------------------------------------------------------------------
-// prep: RoPE + scale + split + per-head re-layout (+ V transpose)
+// fp32 packed qkv (BB, T, 3H) -> RoPE'd, q-scaled split-bf16 planes of the same shape.  Used by the
+// kernel-level test hook and when the QKV projection ran on the SIMT engine; the product path gets
+// this from the QKV GEMM epilogue instead.
 // ----------------------------------------------------------------------------------------------
-constexpr int PREP_T = 32;
-
-__global__ void __launch_bounds__(256) qkv_prep_kernel(const float* __restrict__ qkv, const float* __restrict__ rope_cs,
-                                                       bf16* __restrict__ q_hi, bf16* __restrict__ q_lo,
-                                                       bf16* __restrict__ k_hi, bf16* __restrict__ k_lo,
-                                                       bf16* __restrict__ vt_hi, bf16* __restrict__ vt_lo,
-                                                       int T, int Tpad, int H, int n_heads) {
-    __shared__ float sq[PREP_T][DH + 1], sk[PREP_T][DH + 1], sv[PREP_T][DH + 1];
-    const int bb = blockIdx.z, h = blockIdx.y, t0 = blockIdx.x * PREP_T;
-    const int H3 = 3 * H;
-    for (int i = threadIdx.x; i < PREP_T * (DH / 4); i += 256) {
-        const int r = i / (DH / 4), c4 = (i % (DH / 4)) * 4;
-        const int t = t0 + r;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
-        if (t < T) {
-            const float* base = qkv + ((long)bb * T + t) * H3 + h * DH + c4;
-            a = *reinterpret_cast<const float4*>(base);
-            b = *reinterpret_cast<const float4*>(base + H);
-            c = *reinterpret_cast<const float4*>(base + 2 * H);
+__global__ void rope_split_kernel(const float* __restrict__ qkv, const float* __restrict__ rope_cs, bf16* __restrict__ hi,
+                                  bf16* __restrict__ lo, long rows, int T, int H) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (row, column pair)
+    const int H3 = 3 * H, half = H3 / 2;
+    if (i >= rows * half) return;
+    const long row = i / half;
+    const int c = (int)(i % half) * 2;
+    const int t = (int)(row % T);
+    float x[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int n = c + e, d = n & 63;
+        float v = qkv[row * H3 + n];
+        if (n < 2 * H && d < 32) {
+            const int j = d & 15;
+            const float cs = rope_cs[((long)t * 16 + j) * 2], sn = rope_cs[((long)t * 16 + j) * 2 + 1];
+            const float o = (d < 16) ? -qkv[row * H3 + n + 16] : qkv[row * H3 + n - 16];
+            v = v * cs + o * sn;
         }
-        sq[r][c4] = a.x; sq[r][c4 + 1] = a.y; sq[r][c4 + 2] = a.z; sq[r][c4 + 3] = a.w;
-        sk[r][c4] = b.x; sk[r][c4 + 1] = b.y; sk[r][c4 + 2] = b.z; sk[r][c4 + 3] = b.w;
-        sv[r][c4] = c.x; sv[r][c4 + 1] = c.y; sv[r][c4 + 2] = c.z; sv[r][c4 + 3] = c.w;
+        if (n < H) v *= kQScale;
+        x[e] = v;
+    }
+    uint32_t h2, l2;
+    split_bf16x2(x[0], x[1], h2, l2);
+    *reinterpret_cast<uint32_t*>(hi + row * H3 + c) = h2;
+    *reinterpret_cast<uint32_t*>(lo + row * H3 + c) = l2;
+}
+
+// fallback only (STABLETTS_B200_VT=1): V part of the planes -> [BB*nh][64][Tpad] (keys contiguous)
+__global__ void vt_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, bf16* __restrict__ vt_hi,
+                          bf16* __restrict__ vt_lo, int T, int Tpad, int H, int n_heads) {
+    __shared__ bf16 sh[32][DH + 2], sl[32][DH + 2];
+    const int bb = blockIdx.z, h = blockIdx.y, t0 = blockIdx.x * 32;
+    for (int i = threadIdx.x; i < 32 * DH; i += blockDim.x) {
+        const int r = i / DH, d = i % DH, t = t0 + r;
+        const long src = ((long)bb * T + t) * 3 * H + 2 * H + h * DH + d;
+        sh[r][d] = t < T ? hi[src] : __float2bfloat16(0.f);
+        sl[r][d] = t < T ? lo[src] : __float2bfloat16(0.f);
     }
     __syncthreads();
-    const long head = (long)bb * n_heads + h;
-    const float qscale = 0.125f * 1.4426950408889634f;      // 1/sqrt(64) * log2(e): softmax runs on exp2
-    // q, k: one thread per (token, 8-dim chunk)
-    for (int i = threadIdx.x; i < PREP_T * 8; i += 256) {
-        const int r = i >> 3, ch = i & 7, t = t0 + r;
-        if (t >= T) continue;
-        float qv[8], kv[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int d = ch * 8 + e;
-            float q = sq[r][d], k = sk[r][d];
-            if (d < 32) {                                   // models/diffusion_transformer.py:173-178,196
-                const int j = d & 15;
-                const float c = rope_cs[((long)t * 16 + j) * 2], s = rope_cs[((long)t * 16 + j) * 2 + 1];
-                const float qo = (d < 16) ? -sq[r][d + 16] : sq[r][d - 16];
-                const float ko = (d < 16) ? -sk[r][d + 16] : sk[r][d - 16];
-                q = q * c + qo * s;
-                k = k * c + ko * s;
-            }
-            qv[e] = q * qscale; kv[e] = k;
+    for (int i = threadIdx.x; i < 32 * DH; i += blockDim.x) {
+        const int d = i / 32, r = i % 32, t = t0 + r;
+        if (t < Tpad) {
+            const long dst = (((long)bb * n_heads + h) * DH + d) * Tpad + t;
+            vt_hi[dst] = sh[r][d]; vt_lo[dst] = sl[r][d];
         }
-        uint32_t qh[4], ql[4], kh[4], kl[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            bf16 h0, l0, h1, l1;
-            split_bf16(qv[2 * e], h0, l0); split_bf16(qv[2 * e + 1], h1, l1);
-            __nv_bfloat162 hp = __halves2bfloat162(h0, h1), lp = __halves2bfloat162(l0, l1);
-            qh[e] = *reinterpret_cast<uint32_t*>(&hp); ql[e] = *reinterpret_cast<uint32_t*>(&lp);
-            split_bf16(kv[2 * e], h0, l0); split_bf16(kv[2 * e + 1], h1, l1);
-            hp = __halves2bfloat162(h0, h1); lp = __halves2bfloat162(l0, l1);
-            kh[e] = *reinterpret_cast<uint32_t*>(&hp); kl[e] = *reinterpret_cast<uint32_t*>(&lp);
-        }
-        const long o = (head * T + t) * DH + ch * 8;
-        *reinterpret_cast<uint4*>(q_hi + o) = make_uint4(qh[0], qh[1], qh[2], qh[3]);
-        *reinterpret_cast<uint4*>(q_lo + o) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
-        *reinterpret_cast<uint4*>(k_hi + o) = make_uint4(kh[0], kh[1], kh[2], kh[3]);
-        *reinterpret_cast<uint4*>(k_lo + o) = make_uint4(kl[0], kl[1], kl[2], kl[3]);
-    }
-    // V^T: one thread per (dim d, 8-token chunk); tokens in [T, Tpad) are written as zeros
-    for (int i = threadIdx.x; i < DH * (PREP_T / 8); i += 256) {
-        const int d = i / (PREP_T / 8), tc = (i % (PREP_T / 8)) * 8;
-        if (t0 + tc >= Tpad) continue;
-        uint32_t vh[4], vl[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            bf16 h0, l0, h1, l1;
-            split_bf16(sv[tc + 2 * e][d], h0, l0); split_bf16(sv[tc + 2 * e + 1][d], h1, l1);
-            __nv_bfloat162 hp = __halves2bfloat162(h0, h1), lp = __halves2bfloat162(l0, l1);
-            vh[e] = *reinterpret_cast<uint32_t*>(&hp); vl[e] = *reinterpret_cast<uint32_t*>(&lp);
-        }
-        const long o = (head * DH + d) * Tpad + t0 + tc;
-        *reinterpret_cast<uint4*>(vt_hi + o) = make_uint4(vh[0], vh[1], vh[2], vh[3]);
-        *reinterpret_cast<uint4*>(vt_lo + o) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
     }
 }
 
 // ----------------------------------------------------------------------------------------------
+template <bool V_MN>
 __global__ void __launch_bounds__(A_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQh = smem;              uint8_t* sQl = sQh + Q_BYTES;
-    uint8_t* sKh = sQl + Q_BYTES;     uint8_t* sKl = sKh + K_BYTES;
-    uint8_t* sVh = sKl + K_BYTES;     uint8_t* sVl = sVh + K_BYTES;
-    uint8_t* sPh = sVl + K_BYTES;     uint8_t* sPl = sPh + P_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sPl + P_BYTES);
-    uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
-             *s_full = bars + 5, *p_full = bars + 6, *pv_full = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);          // barriers + TMEM slot live in the alignment slack
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 160 + 1023) & ~uintptr_t(1023));
+    uint8_t* sQh = smem;                 uint8_t* sQl = sQh + Q_BYTES;
+    uint8_t* sK = sQl + Q_BYTES;         // ring of 2: [hi 8K | lo 8K]
+    uint8_t* sVh = sK + 4 * K_BYTES;     uint8_t* sVl = sVh + K_BYTES;
+    uint8_t* sPh = sVl + K_BYTES;        uint8_t* sPl = sPh + P_BYTES;
+    uint64_t *q_full = bars, *k_full = bars + 1 /*[2]*/, *k_empty = bars + 3 /*[2]*/, *v_full = bars + 5,
+             *pv_done = bars + 6, *s_full = bars + 7 /*[2]*/, *p_full = bars + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    if (sPl + P_BYTES > smem_raw + ATT_SMEM) __trap();               // dynamic smem base less aligned than assumed
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bb = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
     const int b = bb % p.B;
     const int kvlen = p.kvlen[b];
-    const int head = bb * p.n_heads + h;
+    const int cq = h * DH, ck = p.H + h * DH, cv = 2 * p.H + h * DH;     // channel offsets of this head
 
     if (q0 >= kvlen) {
         // whole query tile is padding (or the utterance is empty): exact zeros, no pipeline needed
@@ -251,272 +171,10 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
     const int nb = (kvlen + AK - 1) / AK;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < 8; ++i) mbar_init(&bars[i], i == 6 ? 4 : 1);      // p_full: one arrive per softmax warp
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < 10; ++i) mbar_init(&bars[i], i == 9 ? 4 : 1);      // p_full: one arrive per softmax warp
+        mbar_fence_init();
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS_ATT));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_PV = tmem_base + 64;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            mbar_expect_tx(q_full, 2 * Q_BYTES);
-            tma_load_3d(&maps.q_hi, q_full, sQh, 0, q0, head);
-            tma_load_3d(&maps.q_lo, q_full, sQl, 0, q0, head);
-            for (int j = 0; j < nb; ++j) {
-                const uint32_t ph = (j & 1) ^ 1;
-                mbar_wait(k_empty, ph);
-                mbar_expect_tx(k_full, 2 * K_BYTES);
-                tma_load_3d(&maps.k_hi, k_full, sKh, 0, j * AK, head);
-                tma_load_3d(&maps.k_lo, k_full, sKl, 0, j * AK, head);
-                mbar_wait(v_empty, ph);
-                mbar_expect_tx(v_full, 2 * K_BYTES);
-                tma_load_3d(&maps.v_hi, v_full, sVh, j * AK, 0, head);
-                tma_load_3d(&maps.v_lo, v_full, sVl, j * AK, 0, head);
-            }
-        }
-    } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc_n(64);
-        const uint64_t dQh = make_sw128_desc(smem_u32(sQh)), dQl = make_sw128_desc(smem_u32(sQl));
-        const uint64_t dKh = make_sw128_desc(smem_u32(sKh)), dKl = make_sw128_desc(smem_u32(sKl));
-        const uint64_t dVh = make_sw128_desc(smem_u32(sVh)), dVl = make_sw128_desc(smem_u32(sVl));
-        const uint64_t dPh = make_sw128_desc(smem_u32(sPh)), dPl = make_sw128_desc(smem_u32(sPl));
-        auto issue_S = [&]() {
-#pragma unroll
-            for (int k = 0; k < DH / 16; ++k) {
-                const uint64_t adv = (uint64_t)(k * 2);
-                umma_bf16(tmem_S, dQl + adv, dKh + adv, idesc, k != 0);
-                umma_bf16(tmem_S, dQh + adv, dKl + adv, idesc, 1);
-                umma_bf16(tmem_S, dQh + adv, dKh + adv, idesc, 1);
-            }
-        };
-        mbar_wait(q_full, 0);
-        mbar_wait(k_full, 0);
-        tc_fence_after();
-        if (elect_one()) { issue_S(); umma_commit(k_empty); umma_commit(s_full); }
-        __syncwarp();
-        for (int j = 0; j < nb; ++j) {
-            const uint32_t ph = j & 1;
-            mbar_wait(p_full, ph);
-            mbar_wait(v_full, ph);
-            tc_fence_after();
-            if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < AK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 2);
-                    umma_bf16(tmem_PV, dPl + adv, dVh + adv, idesc, k != 0);
-                    umma_bf16(tmem_PV, dPh + adv, dVl + adv, idesc, 1);
-                    umma_bf16(tmem_PV, dPh + adv, dVh + adv, idesc, 1);
-                }
-                umma_commit(v_empty);
-                umma_commit(pv_full);
-            }
-            __syncwarp();
-            if (j + 1 < nb) {
-                mbar_wait(k_full, ph ^ 1);
-                tc_fence_after();
-                if (elect_one()) { issue_S(); umma_commit(k_empty); umma_commit(s_full); }
-                __syncwarp();
-            }
-        }
-    } else {
-        // ================= softmax / epilogue: thread <-> query row =================
-        const int wq = warp & 3;
-        const int r = wq * 32 + lane;
-        const int t = q0 + r;
-        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        const int prefix = p.prefix[b];
-        const float* mrow = p.mask + (long)b * p.T;
-        float O[DH];
-#pragma unroll
-        for (int d = 0; d < DH; ++d) O[d] = 0.f;
-        float m_run = -CUDART_INF_F, l_run = 0.f;
-        uint8_t* pr_hi = sPh + r * 128;
-        uint8_t* pr_lo = sPl + r * 128;
-        const int sw = r & 7;
-
-        for (int j = 0; j < nb; ++j) {
-            const uint32_t ph = j & 1;
-            const int k0 = j * AK;
-            const bool need_mask = k0 + AK > prefix;          // block reaches past the all-ones prefix
-            mbar_wait(s_full, ph);
-            tc_fence_after();
-            uint32_t v[32];
-            float mx = m_run;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld32(tmem_S + lane_addr + half * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float s = __uint_as_float(v[i]);
-                    if (need_mask) { const int kk = k0 + half * 32 + i; if (kk >= kvlen || __ldg(mrow + kk) == 0.f) s = -CUDART_INF_F; }
-                    mx = fmaxf(mx, s);
-                }
-            }
-            // mx is finite: key 0.. of every non-empty utterance is valid (prefix mask) or, for a general
-            // binary mask, kvlen > 0 guarantees a valid key in some block; guard the all-masked-so-far case
-            const float m_new = mx;
-            const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-            const float corr = exp2f(m_run - m_use);           // m_run = -inf -> 0
-            float psum = 0.f;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld32(tmem_S + lane_addr + half * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {               // 4 chunks of 8 keys = 16 B of bf16
-                    uint32_t hw[4], lw[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float pv2[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int i = c * 8 + e * 2 + u;
-                            float s = __uint_as_float(v[i]);
-                            if (need_mask) { const int kk = k0 + half * 32 + i; if (kk >= kvlen || __ldg(mrow + kk) == 0.f) s = -CUDART_INF_F; }
-                            const float pe = exp2f(s - m_use);
-                            psum += pe;
-                            pv2[u] = pe;
-                        }
-                        bf16 h0, l0, h1, l1;
-                        split_bf16(pv2[0], h0, l0); split_bf16(pv2[1], h1, l1);
-                        __nv_bfloat162 hp = __halves2bfloat162(h0, h1), lp = __halves2bfloat162(l0, l1);
-                        hw[e] = *reinterpret_cast<uint32_t*>(&hp); lw[e] = *reinterpret_cast<uint32_t*>(&lp);
-                    }
-                    const int chunk = half * 4 + c;         // 16-byte chunk index inside the 128 B row
-                    const int off = ((chunk ^ sw) << 4);    // 128B swizzle: chunk ^= (row & 7)
-                    *reinterpret_cast<uint4*>(pr_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                    *reinterpret_cast<uint4*>(pr_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                }
-            }
-            l_run = l_run * corr + psum;
-            m_run = m_new;
-            // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
-            // O = O * corr + P·V
-            mbar_wait(pv_full, ph);
-            tc_fence_after();
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld32(tmem_PV + lane_addr + half * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) O[half * 32 + i] = fmaf(O[half * 32 + i], corr, __uint_as_float(v[i]));
-            }
-            tc_fence_before();
-        }
-        if (t < p.T) {
-            const bool valid = mrow[t] != 0.f && l_run > 0.f;
-            const float inv = valid ? 1.0f / l_run : 0.f;
-            const long o = ((long)bb * p.T + t) * p.H + h * DH;
-#pragma unroll
-            for (int c = 0; c < DH / 8; ++c) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = O[c * 8 + e] * inv;
-                if (p.out_f32) {
-                    *reinterpret_cast<float4*>(p.out_f32 + o + c * 8) = make_float4(f[0], f[1], f[2], f[3]);
-                    *reinterpret_cast<float4*>(p.out_f32 + o + c * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                }
-                if (p.out_hi) {
-                    uint32_t hw[4], lw[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        bf16 h0, l0, h1, l1;
-                        split_bf16(f[2 * e], h0, l0); split_bf16(f[2 * e + 1], h1, l1);
-                        __nv_bfloat162 hp = __halves2bfloat162(h0, h1), lp = __halves2bfloat162(l0, l1);
-                        hw[e] = *reinterpret_cast<uint32_t*>(&hp); lw[e] = *reinterpret_cast<uint32_t*>(&lp);
-                    }
-                    *reinterpret_cast<uint4*>(p.out_hi + o + c * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                    *reinterpret_cast<uint4*>(p.out_lo + o + c * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS_ATT));
-    }
-}
-
-// ----------------------------------------------------------------------------------------------
-// v2 pipeline: O accumulates in TMEM (PV_j issued with accumulate), S is double-buffered in TMEM and
-// K in shared memory so S_{j+1} (and S_{j+2}) run on the tensor core while the softmax warps work on
-// S_j, and the running max is LAZY (FA4-style): exponentials use a stale max m_used and O / l are only
-// rescaled when some row's block max exceeds m_used by more than 2^8 — then, and only then, the softmax
-// warps wait for PV_{j-1}, read O from TMEM, scale it and store it back (tcgen05.st).  The per-block
-// critical path is max(softmax, MMA) instead of their sum.
-// ----------------------------------------------------------------------------------------------
-constexpr int ATT2_SMEM = 2 * Q_BYTES + 4 * K_BYTES + 2 * K_BYTES + 2 * P_BYTES + 1024;   // 112 KB + barriers/alignment
-constexpr int TMEM_COLS_ATT2 = 256;         // S0 [0,64) S1 [64,128) O [128,192)
-constexpr float LAZY_THRESHOLD = 8.0f;      // log2 domain: p <= 2^8 between rescales
-
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__global__ void __launch_bounds__(A_THREADS, 2)
-attention_tc2_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);          // 16 barriers + tmem slot live in the alignment slack
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 160 + 1023) & ~uintptr_t(1023));
-    uint8_t* sQh = smem;                 uint8_t* sQl = sQh + Q_BYTES;
-    uint8_t* sK = sQl + Q_BYTES;         // [2][hi 8K | lo 8K]
-    uint8_t* sVh = sK + 4 * K_BYTES;     uint8_t* sVl = sVh + K_BYTES;
-    uint8_t* sPh = sVl + K_BYTES;        uint8_t* sPl = sPh + P_BYTES;
-    uint64_t *q_full = bars, *k_full = bars + 1 /*[2]*/, *k_empty = bars + 3 /*[2]*/, *v_full = bars + 5,
-             *pv_done = bars + 6, *s_full = bars + 7 /*[2]*/, *p_full = bars + 9;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-    if (sPl + P_BYTES > smem_raw + ATT2_SMEM) __trap();              // dynamic smem base less aligned than assumed
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bb = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
-    const int b = bb % p.B;
-    const int kvlen = p.kvlen[b];
-    const int head = bb * p.n_heads + h;
-
-    if (q0 >= kvlen) {
-        for (int i = threadIdx.x; i < AQ * (DH / 4); i += A_THREADS) {
-            const int r = i / (DH / 4), c4 = (i % (DH / 4)) * 4, t = q0 + r;
-            if (t < p.T) {
-                const long o = ((long)bb * p.T + t) * p.H + h * DH + c4;
-                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.out_hi) { *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(0, 0); *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(0, 0); }
-            }
-        }
-        return;
-    }
-    const int nb = (kvlen + AK - 1) / AK;
-
-    if (warp == 0 && lane == 0) {
-        for (int i = 0; i < 10; ++i) mbar_init(&bars[i], i == 9 ? 4 : 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS_ATT2));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
+    if (warp == 1) tmem_alloc_1sm<TMEM_COLS_ATT>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -526,22 +184,29 @@ attention_tc2_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
     if (warp == 0) {
         if (elect_one()) {
             mbar_expect_tx(q_full, 2 * Q_BYTES);
-            tma_load_3d(&maps.q_hi, q_full, sQh, 0, q0, head);
-            tma_load_3d(&maps.q_lo, q_full, sQl, 0, q0, head);
+            tma_load_3d(&maps.q_hi, q_full, sQh, cq, q0, bb);
+            tma_load_3d(&maps.q_lo, q_full, sQl, cq, q0, bb);
             for (int j = 0; j < nb; ++j) {
                 const int slot = j & 1;
                 mbar_wait(&k_empty[slot], ((j >> 1) & 1) ^ 1);
                 mbar_expect_tx(&k_full[slot], 2 * K_BYTES);
-                tma_load_3d(&maps.k_hi, &k_full[slot], sK + slot * 2 * K_BYTES, 0, j * AK, head);
-                tma_load_3d(&maps.k_lo, &k_full[slot], sK + slot * 2 * K_BYTES + K_BYTES, 0, j * AK, head);
+                tma_load_3d(&maps.kv_hi, &k_full[slot], sK + slot * 2 * K_BYTES, ck, j * AK, bb);
+                tma_load_3d(&maps.kv_lo, &k_full[slot], sK + slot * 2 * K_BYTES + K_BYTES, ck, j * AK, bb);
                 mbar_wait(pv_done, (j & 1) ^ 1);                 // PV_{j-1} finished reading V (and P)
                 mbar_expect_tx(v_full, 2 * K_BYTES);
-                tma_load_3d(&maps.v_hi, v_full, sVh, j * AK, 0, head);
-                tma_load_3d(&maps.v_lo, v_full, sVl, j * AK, 0, head);
+                if (V_MN) {
+                    tma_load_3d(&maps.kv_hi, v_full, sVh, cv, j * AK, bb);
+                    tma_load_3d(&maps.kv_lo, v_full, sVl, cv, j * AK, bb);
+                } else {
+                    tma_load_3d(&maps.vt_hi, v_full, sVh, j * AK, 0, bb * p.n_heads + h);
+                    tma_load_3d(&maps.vt_lo, v_full, sVl, j * AK, 0, bb * p.n_heads + h);
+                }
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc_n(64);
+        constexpr uint32_t idesc_s = att_idesc(false), idesc_pv = att_idesc(V_MN);
+        // P·V k-step of 16 keys: K-major V^T tile -> +32 B inside the row; MN-major V tile -> 16 rows = +2048 B
+        constexpr uint64_t v_adv = V_MN ? (uint64_t)((16 * 128) >> 4) : 2;
         const uint64_t dQh = make_sw128_desc(smem_u32(sQh)), dQl = make_sw128_desc(smem_u32(sQl));
         const uint64_t dVh = make_sw128_desc(smem_u32(sVh)), dVl = make_sw128_desc(smem_u32(sVl));
         const uint64_t dPh = make_sw128_desc(smem_u32(sPh)), dPl = make_sw128_desc(smem_u32(sPl));
@@ -553,9 +218,9 @@ attention_tc2_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
 #pragma unroll
             for (int k = 0; k < DH / 16; ++k) {
                 const uint64_t adv = (uint64_t)(k * 2);
-                umma_bf16(tS, dQl + adv, dKh + adv, idesc, k != 0);
-                umma_bf16(tS, dQh + adv, dKl + adv, idesc, 1);
-                umma_bf16(tS, dQh + adv, dKh + adv, idesc, 1);
+                umma_bf16(tS, dQl + adv, dKh + adv, idesc_s, k != 0);
+                umma_bf16(tS, dQh + adv, dKl + adv, idesc_s, 1);
+                umma_bf16(tS, dQh + adv, dKh + adv, idesc_s, 1);
             }
             umma_commit(&k_empty[slot]);
             umma_commit(&s_full[slot]);
@@ -574,10 +239,10 @@ attention_tc2_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
             if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < AK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 2);
-                    umma_bf16(tmem_O, dPl + adv, dVh + adv, idesc, (j | k) != 0);
-                    umma_bf16(tmem_O, dPh + adv, dVl + adv, idesc, 1);
-                    umma_bf16(tmem_O, dPh + adv, dVh + adv, idesc, 1);
+                    const uint64_t pa = (uint64_t)(k * 2), va = (uint64_t)k * v_adv;
+                    umma_bf16(tmem_O, dPl + pa, dVh + va, idesc_pv, (j | k) != 0);
+                    umma_bf16(tmem_O, dPh + pa, dVl + va, idesc_pv, 1);
+                    umma_bf16(tmem_O, dPh + pa, dVh + va, idesc_pv, 1);
                 }
                 umma_commit(pv_done);
             }
@@ -590,6 +255,7 @@ attention_tc2_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
             }
         }
     } else {
+        // ================= softmax / epilogue: thread <-> query row =================
         const int wq = warp & 3;
         const int r = wq * 32 + lane;
         const int t = q0 + r;
@@ -605,25 +271,37 @@ attention_tc2_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
         for (int j = 0; j < nb; ++j) {
             const int k0 = j * AK;
             const uint32_t tS = tmem_base + (j & 1) * 64 + lane_addr;
-            const bool need_mask = k0 + AK > prefix;
+            const bool need_mask = k0 + AK > prefix;          // block reaches past the all-ones prefix
             mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
-            float cand = -CUDART_INF_F;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld32(tS + half * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float sv = __uint_as_float(v[i]);
-                    if (need_mask) { const int kk = k0 + half * 32 + i; if (kk >= kvlen || __ldg(mrow + kk) == 0.f) sv = -CUDART_INF_F; }
-                    cand = fmaxf(cand, sv);
-                }
-            }
+            uint32_t hw[32], lw[32];                          // packed P row: 64 keys x (hi, lo)
+            float cand, psum;
             bool waited_pv = (j == 0);
+            auto softmax_pass = [&](float m_eff) {
+                cand = -CUDART_INF_F; psum = 0.f;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    tmem_ld32(tS + half * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+                        if (need_mask) {
+                            const int kk = k0 + half * 32 + i;
+                            if (kk >= kvlen || __ldg(mrow + kk) == 0.f) s0 = -CUDART_INF_F;
+                            if (kk + 1 >= kvlen || __ldg(mrow + kk + 1) == 0.f) s1 = -CUDART_INF_F;
+                        }
+                        cand = fmaxf(cand, fmaxf(s0, s1));
+                        const float p0 = ex2_approx(s0 - m_eff), p1 = ex2_approx(s1 - m_eff);
+                        psum += p0 + p1;
+                        split_bf16x2(p0, p1, hw[half * 16 + i / 2], lw[half * 16 + i / 2]);
+                    }
+                }
+            };
+            softmax_pass((m_used == -CUDART_INF_F) ? 0.f : m_used);      // optimistic: stale max
             if (__any_sync(0xffffffffu, cand > m_used + LAZY_THRESHOLD)) {
                 const float m_new = fmaxf(m_used, cand);
-                const float factor = (m_new == -CUDART_INF_F) ? 1.f : exp2f(m_used - m_new);     // m_used = -inf -> 0
+                const float factor = (m_new == -CUDART_INF_F) ? 1.f : ex2_approx(m_used - m_new);    // m_used = -inf -> 0
                 l_run *= factor;
                 if (j > 0) {                 // rescale O in TMEM: no PV may be in flight
                     mbar_wait(pv_done, (j - 1) & 1);
@@ -640,37 +318,17 @@ attention_tc2_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
                     tmem_st_wait();
                 }
                 m_used = m_new;
-            }
-            const float m_eff = (m_used == -CUDART_INF_F) ? 0.f : m_used;
-            if (!waited_pv) { mbar_wait(pv_done, (j - 1) & 1); }     // P buffer free (PV_{j-1} retired)
-            float psum = 0.f;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld32(tS + half * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t hw[4], lw[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float pv2[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int i = c * 8 + e * 2 + u;
-                            float sv = __uint_as_float(v[i]);
-                            if (need_mask) { const int kk = k0 + half * 32 + i; if (kk >= kvlen || __ldg(mrow + kk) == 0.f) sv = -CUDART_INF_F; }
-                            const float pe = exp2f(sv - m_eff);
-                            psum += pe;
-                            pv2[u] = pe;
-                        }
-                        split_bf16x2(pv2[0], pv2[1], hw[e], lw[e]);
-                    }
-                    const int off = (((half * 4 + c) ^ sw) << 4);
-                    *reinterpret_cast<uint4*>(pr_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                    *reinterpret_cast<uint4*>(pr_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                }
+                softmax_pass((m_used == -CUDART_INF_F) ? 0.f : m_used);  // redo against the new max
             }
             l_run += psum;
+            if (!waited_pv) mbar_wait(pv_done, (j - 1) & 1);             // P buffer free (PV_{j-1} retired)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {                                 // 8 chunks of 8 keys = 16 B of bf16
+                const int off = ((c ^ sw) << 4);                          // 128B swizzle: chunk ^= (row & 7)
+                *reinterpret_cast<uint4*>(pr_hi + off) = make_uint4(hw[c * 4], hw[c * 4 + 1], hw[c * 4 + 2], hw[c * 4 + 3]);
+                *reinterpret_cast<uint4*>(pr_lo + off) = make_uint4(lw[c * 4], lw[c * 4 + 1], lw[c * 4 + 2], lw[c * 4 + 3]);
+            }
+            // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
             __syncwarp();
@@ -698,11 +356,11 @@ attention_tc2_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
                         *reinterpret_cast<float4*>(p.out_f32 + oc + 4) = make_float4(f[4], f[5], f[6], f[7]);
                     }
                     if (p.out_hi) {
-                        uint32_t hw[4], lw[4];
+                        uint32_t h4[4], l4[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) split_bf16x2(f[2 * e], f[2 * e + 1], hw[e], lw[e]);
-                        *reinterpret_cast<uint4*>(p.out_hi + oc) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                        *reinterpret_cast<uint4*>(p.out_lo + oc) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        for (int e = 0; e < 4; ++e) split_bf16x2(f[2 * e], f[2 * e + 1], h4[e], l4[e]);
+                        *reinterpret_cast<uint4*>(p.out_hi + oc) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                        *reinterpret_cast<uint4*>(p.out_lo + oc) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
                     }
                 }
             }
@@ -713,7 +371,7 @@ attention_tc2_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS_ATT2));
+        tmem_dealloc_1sm<TMEM_COLS_ATT>(tmem_base);
     }
 }
 
@@ -726,54 +384,61 @@ std::string g_att_err;
 const char* attention_tc_last_error() { return g_att_err.c_str(); }
 
 size_t attention_tc_scratch_elems(int BB, int T, int H) {
-    // Q, K planes: BB*T*H each; V^T planes: BB*H*Tpad
     const int Tpad = (T + 7) & ~7;
-    return (size_t)BB * H * Tpad;
+    return (size_t)BB * H * Tpad;             // V^T fallback planes
 }
 
+cudaError_t launch_rope_split(const float* qkv, const float* rope_cs, bf16* hi, bf16* lo, int BB, int T, int H, cudaStream_t s) {
+    const long rows = (long)BB * T, n = rows * (3 * H / 2);
+    if (n == 0) return cudaSuccess;
+    rope_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(qkv, rope_cs, hi, lo, rows, T, H);
+    return cudaGetLastError();
+}
+
+// a.qkv_hi / a.qkv_lo: RoPE'd, q-scaled split planes (BB, T, 3H)
 cudaError_t launch_attention_tc(const AttnArgs& a, const AttnTcScratch& sc, cudaStream_t s) {
     std::lock_guard<std::mutex> lk(g_att_mu);
     if (a.H != a.n_heads * DH) return cudaErrorInvalidValue;
     if (a.BB == 0 || a.T == 0) return cudaSuccess;
+    if (!a.qkv_hi || !a.qkv_lo) { g_att_err = "split qkv planes missing"; return cudaErrorInvalidValue; }
+    static int use_vt = -1;
+    if (use_vt < 0) { const char* e = getenv("STABLETTS_B200_VT"); use_vt = (e && !strcmp(e, "1")) ? 1 : 0; }
     const int Tpad = (a.T + 7) & ~7;
-    {
-        dim3 grid((Tpad + PREP_T - 1) / PREP_T, a.n_heads, a.BB);
-        qkv_prep_kernel<<<grid, 256, 0, s>>>(a.qkv, a.rope_cs, sc.q_hi, sc.q_lo, sc.k_hi, sc.k_lo, sc.vt_hi, sc.vt_lo, a.T, Tpad,
-                                             a.H, a.n_heads);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
     AttMaps maps;
-    const uint64_t heads = (uint64_t)a.BB * a.n_heads;
+    const uint64_t C3 = 3 * (uint64_t)a.H;
     bool ok = true;
-    ok = ok && tmap_encode_bf16(sc.q_hi, 3, DH, (uint64_t)a.T, heads, DH, AQ, &maps.q_hi);
-    ok = ok && tmap_encode_bf16(sc.q_lo, 3, DH, (uint64_t)a.T, heads, DH, AQ, &maps.q_lo);
-    ok = ok && tmap_encode_bf16(sc.k_hi, 3, DH, (uint64_t)a.T, heads, DH, AK, &maps.k_hi);
-    ok = ok && tmap_encode_bf16(sc.k_lo, 3, DH, (uint64_t)a.T, heads, DH, AK, &maps.k_lo);
-    ok = ok && tmap_encode_bf16(sc.vt_hi, 3, (uint64_t)Tpad, DH, heads, AK, DH, &maps.v_hi);
-    ok = ok && tmap_encode_bf16(sc.vt_lo, 3, (uint64_t)Tpad, DH, heads, AK, DH, &maps.v_lo);
+    ok = ok && tmap_encode_bf16(a.qkv_hi, 3, C3, (uint64_t)a.T, (uint64_t)a.BB, DH, AQ, &maps.q_hi);
+    ok = ok && tmap_encode_bf16(a.qkv_lo, 3, C3, (uint64_t)a.T, (uint64_t)a.BB, DH, AQ, &maps.q_lo);
+    ok = ok && tmap_encode_bf16(a.qkv_hi, 3, C3, (uint64_t)a.T, (uint64_t)a.BB, DH, AK, &maps.kv_hi);
+    ok = ok && tmap_encode_bf16(a.qkv_lo, 3, C3, (uint64_t)a.T, (uint64_t)a.BB, DH, AK, &maps.kv_lo);
+    if (ok) { maps.vt_hi = maps.kv_hi; maps.vt_lo = maps.kv_lo; }
+    if (ok && use_vt) {
+        if (!sc.vt_hi || !sc.vt_lo) { g_att_err = "V^T scratch missing"; return cudaErrorInvalidValue; }
+        dim3 grid((Tpad + 31) / 32, a.n_heads, a.BB);
+        vt_kernel<<<grid, 256, 0, s>>>(a.qkv_hi, a.qkv_lo, sc.vt_hi, sc.vt_lo, a.T, Tpad, a.H, a.n_heads);
+        const uint64_t heads = (uint64_t)a.BB * a.n_heads;
+        ok = ok && tmap_encode_bf16(sc.vt_hi, 3, (uint64_t)Tpad, DH, heads, AK, DH, &maps.vt_hi);
+        ok = ok && tmap_encode_bf16(sc.vt_lo, 3, (uint64_t)Tpad, DH, heads, AK, DH, &maps.vt_lo);
+    }
     if (!ok) { g_att_err = gemm_tc_last_error(); return cudaErrorInvalidValue; }
     AttParams p;
     p.BB = a.BB; p.B = a.B; p.T = a.T; p.H = a.H; p.n_heads = a.n_heads;
     p.mask = a.mask; p.kvlen = a.kvlen; p.prefix = a.prefix;
     p.out_f32 = a.out_f32; p.out_hi = a.out_hi; p.out_lo = a.out_lo;
-    static int version = -1;
-    if (version < 0) { const char* e = getenv("STABLETTS_B200_ATT"); version = (e && !strcmp(e, "v1")) ? 1 : 2; }
     if (!g_att_attr) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM);
-        if (e != cudaSuccess) { g_att_err = "cudaFuncSetAttribute failed for attention_tc kernels"; return e; }
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+        if (e != cudaSuccess) { g_att_err = "cudaFuncSetAttribute failed for attention_tc_kernel"; return e; }
         if (getenv("STABLETTS_B200_DEBUG")) {
-            int o1 = 0, o2 = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, attention_tc_kernel, A_THREADS, ATT_SMEM);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, attention_tc2_kernel, A_THREADS, ATT2_SMEM);
-            fprintf(stderr, "[stabletts_b200] attention CTAs/SM: v1 %d, v2 %d\n", o1, o2);
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attention_tc_kernel<true>, A_THREADS, ATT_SMEM);
+            fprintf(stderr, "[stabletts_b200] attention CTAs/SM: %d (V %s)\n", occ, use_vt ? "transposed" : "MN-major");
         }
         g_att_attr = true;
     }
     dim3 grid((a.T + AQ - 1) / AQ, a.n_heads, a.BB);
-    if (version == 1) attention_tc_kernel<<<grid, A_THREADS, ATT_SMEM, s>>>(maps, p);
-    else attention_tc2_kernel<<<grid, A_THREADS, ATT2_SMEM, s>>>(maps, p);
+    if (use_vt) attention_tc_kernel<false><<<grid, A_THREADS, ATT_SMEM, s>>>(maps, p);
+    else attention_tc_kernel<true><<<grid, A_THREADS, ATT_SMEM, s>>>(maps, p);
     return cudaGetLastError();
 }
 

@@ -54,7 +54,7 @@ struct GemmArgs {
     const float* film = nullptr; long film_bstride = 0; int film_H = 0;   // gamma[n], beta[film_H + n]
     const float* gate = nullptr; long gate_bstride = 0; int c_clamp = 0;
     const float* resid = nullptr; int resid_clamp = 0;
-    const float* rope_cs = nullptr;               // (T, 16, 2) cos/sin table (EPI_ROPE)
+    const float* rope_cs = nullptr; int rope_H = 0; // (T, 16, 2) cos/sin table; columns [0,2*rope_H) are q|k (EPI_ROPE)
     float* out_f32 = nullptr;
     bf16*  out_hi = nullptr;
     bf16*  out_lo = nullptr;
@@ -109,7 +109,9 @@ cudaError_t launch_split(const float* in, bf16* hi, bf16* lo, long numel, cudaSt
 // attention (attention.cu): qkv (BB, T, 3H) fp32 -> out (BB, T, H); partial RoPE fused on load.
 // ----------------------------------------------------------------------------------------------
 struct AttnArgs {
-    const float* qkv = nullptr;
+    const float* qkv = nullptr;       // SIMT engine: raw fp32 projections (RoPE applied on load)
+    const bf16* qkv_hi = nullptr;     // tcgen05 engine: RoPE'd, q-scaled split planes (BB, T, 3H)
+    const bf16* qkv_lo = nullptr;
     const float* rope_cs = nullptr;   // (T, 16, 2)
     const float* mask = nullptr;      // (B, T)
     const int* kvlen = nullptr;       // (B) 1 + last index with mask != 0
@@ -119,13 +121,14 @@ struct AttnArgs {
 };
 cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t s);
 
-// tcgen05 engine (attention_tc.cu): per-head split-bf16 operand planes produced by its prep kernel
+// tcgen05 engine (attention_tc.cu)
 struct AttnTcScratch {
-    bf16 *q_hi = nullptr, *q_lo = nullptr, *k_hi = nullptr, *k_lo = nullptr;   // [BB*nh][T][64]
-    bf16 *vt_hi = nullptr, *vt_lo = nullptr;                                    // [BB*nh][64][Tpad]
+    bf16 *vt_hi = nullptr, *vt_lo = nullptr;     // [BB*nh][64][Tpad], only for the STABLETTS_B200_VT=1 fallback
 };
-size_t attention_tc_scratch_elems(int BB, int T, int H);    // elements per plane (covers Tpad)
+size_t attention_tc_scratch_elems(int BB, int T, int H);    // elements per V^T plane
 cudaError_t launch_attention_tc(const AttnArgs& a, const AttnTcScratch& sc, cudaStream_t s);
+// fp32 packed qkv -> RoPE'd, q-scaled split planes (what the QKV GEMM epilogue emits on the product path)
+cudaError_t launch_rope_split(const float* qkv, const float* rope_cs, bf16* hi, bf16* lo, int BB, int T, int H, cudaStream_t s);
 const char* attention_tc_last_error();
 
 // ----------------------------------------------------------------------------------------------

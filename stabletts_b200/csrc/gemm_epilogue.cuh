@@ -1,0 +1,137 @@
+// Fused conv-GEMM epilogue shared by the 1-CTA (gemm_tc.cu) and 2-CTA (gemm_tc2.cu) tcgen05 kernels.
+//
+// One call drains this warp's share of a finished accumulator tile (its TMEM lane quarter = 32 frames,
+// every second 32-column chunk):
+//   Phase A: tcgen05.ld (thread = frame, 32 columns) -> XOR-swizzled shared-memory staging, no math.
+//   Phase B: lane = (4 frames x 8 float4 column groups): every global access is a coalesced 128-byte
+//            row segment (residual read, fp32 / split-bf16 writes); per-column vectors (bias, gate,
+//            FiLM) sit in registers for the whole chunk, the per-frame mask for the whole tile.
+//   v = acc + bias; [SiLU]; [partial RoPE on q/k head chunks, q pre-scaled for the exp2 softmax];
+//   v = (gamma*v + beta) * mask * gate + resid  -> fp32 and/or split-bf16 planes.
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace st {
+
+struct TcParams {
+    int n_src, Cs0, Cs1, taps, N, a_bmod, BB, T;
+    int m_tiles_per_b, n_tiles, total_tiles;
+    int flags, B, film_H, c_clamp, resid_clamp, rope_H;
+    long film_bstride, gate_bstride;
+    const float *bias, *mask, *film, *gate, *resid, *rope_cs;
+    float* out_f32; bf16* out_hi; bf16* out_lo;
+};
+
+inline void fill_tc_params(TcParams& p, const GemmArgs& g) {
+    p.n_src = g.n_src; p.Cs0 = g.Cs[0]; p.Cs1 = g.Cs[1]; p.taps = g.taps; p.N = g.N; p.a_bmod = g.a_bmod; p.BB = g.BB; p.T = g.T;
+    p.flags = g.flags; p.B = g.B; p.film_H = g.film_H; p.c_clamp = g.c_clamp; p.resid_clamp = g.resid_clamp; p.rope_H = g.rope_H;
+    p.film_bstride = g.film_bstride; p.gate_bstride = g.gate_bstride;
+    p.bias = g.bias; p.mask = g.mask; p.film = g.film; p.gate = g.gate; p.resid = g.resid; p.rope_cs = g.rope_cs;
+    p.out_f32 = g.out_f32; p.out_hi = g.out_hi; p.out_lo = g.out_lo;
+}
+
+// softmax scale folded into q: 1/sqrt(64) * log2(e) (attention runs in the exp2 domain)
+constexpr float kQScale = 0.125f * 1.4426950408889634f;
+
+// bb: batch row, t0: first frame of this warp's 32-frame slab, n0: first column of the tile,
+// tmem_acc: TMEM address of (lane quarter, accumulator column 0), stg: this warp's 4 KB staging.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, int bb, int t0, int n0, uint32_t tmem_acc, float4* stg,
+                                              int eh, int lane) {
+    using namespace ptx;
+    const int rs = lane >> 3, c4 = lane & 7;
+    const int mb = bb % p.B;
+    float mrow[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int t = t0 + it * 4 + rs;
+        mrow[it] = ((p.flags & EPI_MASK) && t < p.T) ? __ldg(p.mask + (long)mb * p.T + t) : 1.f;
+    }
+    const float* film = p.film + (long)mb * p.film_bstride;
+    const float* gate = p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride;
+    const float* resid = p.resid + (long)min(bb, p.resid_clamp) * p.T * p.N;
+    const long obase = (long)bb * p.T * p.N;
+
+#pragma unroll 1
+    for (int c0 = eh * 32; c0 < BN; c0 += 64) {
+        if (n0 + c0 >= p.N) break;             // warp-uniform
+        {
+            uint32_t v[32];
+            tmem_ld32(tmem_acc + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                stg[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                                               __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+        }
+        __syncwarp();
+        const int nb = n0 + c0;                // chunk base column (multiple of 32), warp-uniform
+        const int n = nb + c4 * 4;
+        // RoPE applies to the first 32 dims of every 64-wide head of q and k (columns [0, 2H));
+        // pairs (j, j+16) live in lanes c4 and c4^4 of the same frame (models/diffusion_transformer.py:173-198)
+        const bool rope = (p.flags & EPI_ROPE) && nb < 2 * p.rope_H && (nb & 63) == 0;
+        const float post = ((p.flags & EPI_ROPE) && nb < p.rope_H) ? kQScale : 1.0f;
+        const bool col_ok = n < p.N;           // N % 4 == 0: a float4 column group is all-in or all-out
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = b4;
+        if (col_ok) {
+            if (p.flags & EPI_BIAS) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            if (p.flags & EPI_GATE) g4 = __ldg(reinterpret_cast<const float4*>(gate + n));
+            if (p.flags & EPI_FILM) {
+                fg = __ldg(reinterpret_cast<const float4*>(film + n));
+                fb = __ldg(reinterpret_cast<const float4*>(film + p.film_H + n));
+            }
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            float4 sv[4], rv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rl = (hf * 4 + i) * 4 + rs;
+                sv[i] = stg[rl * 8 + (c4 ^ (rl & 7))];
+                rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((p.flags & EPI_RESID) && col_ok && t0 + rl < p.T)
+                    rv[i] = __ldg(reinterpret_cast<const float4*>(resid + (long)(t0 + rl) * p.N + n));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int it = hf * 4 + i;
+                const int t = t0 + it * 4 + rs;
+                float x[4] = {sv[i].x + b4.x, sv[i].y + b4.y, sv[i].z + b4.z, sv[i].w + b4.w};
+                if (p.flags & EPI_SILU) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
+                }
+                if (rope) {                    // warp-uniform branch; shuffles executed by all 32 lanes
+                    const int tc = min(t, p.T - 1);
+                    const float4 cs0 = __ldg(reinterpret_cast<const float4*>(p.rope_cs + ((long)tc * 16 + (c4 & 3) * 4) * 2));
+                    const float4 cs1 = __ldg(reinterpret_cast<const float4*>(p.rope_cs + ((long)tc * 16 + (c4 & 3) * 4) * 2 + 4));
+                    const float sgn = (c4 < 4) ? -1.f : 1.f;      // r_j = -x_{j+16} (j<16), +x_{j-16} (j>=16)
+                    const float p0 = __shfl_xor_sync(0xffffffffu, x[0], 4), p1 = __shfl_xor_sync(0xffffffffu, x[1], 4);
+                    const float p2 = __shfl_xor_sync(0xffffffffu, x[2], 4), p3 = __shfl_xor_sync(0xffffffffu, x[3], 4);
+                    x[0] = x[0] * cs0.x + sgn * p0 * cs0.y;
+                    x[1] = x[1] * cs0.z + sgn * p1 * cs0.w;
+                    x[2] = x[2] * cs1.x + sgn * p2 * cs1.y;
+                    x[3] = x[3] * cs1.z + sgn * p3 * cs1.w;
+                }
+                if (t >= p.T || !col_ok) continue;
+                const float m = mrow[it];
+                x[0] = (fg.x * x[0] * post + fb.x) * m * g4.x + rv[i].x;
+                x[1] = (fg.y * x[1] * post + fb.y) * m * g4.y + rv[i].y;
+                x[2] = (fg.z * x[2] * post + fb.z) * m * g4.z + rv[i].z;
+                x[3] = (fg.w * x[3] * post + fb.w) * m * g4.w + rv[i].w;
+                const long o = obase + (long)t * p.N + n;
+                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
+                if (p.out_hi) {
+                    uint32_t h01, l01, h23, l23;
+                    split_bf16x2(x[0], x[1], h01, l01); split_bf16x2(x[2], x[3], h23, l23);
+                    *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(h01, h23);
+                    *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(l01, l23);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace st

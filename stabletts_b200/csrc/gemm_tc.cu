@@ -16,6 +16,7 @@
 //   fused bias/SiLU/FiLM/mask/gate/residual -> fp32 and/or split-bf16 global stores).  Two TMEM
 //   accumulator stages let tile i's epilogue overlap tile i+1's MMAs.
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -36,15 +37,6 @@ constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KB
 
 struct TcMaps {
     CUtensorMap a_hi[2], a_lo[2], w_hi, w_lo;
-};
-
-struct TcParams {
-    int n_src, Cs0, Cs1, taps, N, a_bmod, BB, T;
-    int m_tiles_per_b, n_tiles, total_tiles;
-    int flags, B, film_H, c_clamp, resid_clamp;
-    long film_bstride, gate_bstride;
-    const float *bias, *mask, *film, *gate, *resid;
-    float* out_f32; bf16* out_hi; bf16* out_lo;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -247,95 +239,17 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
-        // ================= epilogue (4 warps = 128 TMEM lanes = 128 frames) =================
-        // Phase A: tcgen05.ld (thread = row, 32 columns) -> swizzled smem staging, no math.
-        // Phase B: lane = (4 rows x 8 float4 columns): every global access is a coalesced 128-byte row
-        //          segment (residual read, fp32 / split-bf16 writes); per-column vectors (bias, gate,
-        //          FiLM) live in registers for the whole chunk, per-row mask for the whole tile.
+        // ================= epilogue (8 warps: 4 TMEM lane quarters x 2 column halves) =================
         const int wq = warp & 3;                       // TMEM lane quarter this warp may access
-        float4* stg = reinterpret_cast<float4*>(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 4) * 256;   // 4 KB per warp
         const int eh = (warp - 4) >> 2;                // two warps share a lane quarter: even / odd 32-column chunks
-        const int rs = lane >> 3, c4 = lane & 7;
+        float4* stg = reinterpret_cast<float4*>(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 4) * 256;   // 4 KB per warp
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
             const int bb = m_tile / p.m_tiles_per_b, t0 = (m_tile % p.m_tiles_per_b) * BLOCK_M + wq * 32;
-            const int n0 = n_tile * BN;
-            const int mb = bb % p.B;
-            float mrow[8];
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int t = t0 + it * 4 + rs;
-                mrow[it] = ((p.flags & EPI_MASK) && t < p.T) ? __ldg(p.mask + (long)mb * p.T + t) : 1.f;
-            }
-            const float* film = p.film + (long)mb * p.film_bstride;
-            const float* gate = p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride;
-            const float* resid = p.resid + (long)min(bb, p.resid_clamp) * p.T * p.N;
-            const long obase = (long)bb * p.T * p.N;
-
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = eh * 32; c0 < BN; c0 += 64) {
-                if (n0 + c0 >= p.N) break;             // warp-uniform
-                {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        stg[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
-                                                                       __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
-                }
-                __syncwarp();
-                const int n = n0 + c0 + c4 * 4;
-                if (n < p.N) {                         // N % 4 == 0: a float4 column group is all-in or all-out
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = b4;
-                    if (p.flags & EPI_BIAS) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                    if (p.flags & EPI_GATE) g4 = __ldg(reinterpret_cast<const float4*>(gate + n));
-                    if (p.flags & EPI_FILM) {
-                        fg = __ldg(reinterpret_cast<const float4*>(film + n));
-                        fb = __ldg(reinterpret_cast<const float4*>(film + p.film_H + n));
-                    }
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        float4 sv[4], rv[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int rl = (hf * 4 + i) * 4 + rs;
-                            sv[i] = stg[rl * 8 + (c4 ^ (rl & 7))];
-                            rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if ((p.flags & EPI_RESID) && t0 + rl < p.T)
-                                rv[i] = __ldg(reinterpret_cast<const float4*>(resid + (long)(t0 + rl) * p.N + n));
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int it = hf * 4 + i;
-                            const int t = t0 + it * 4 + rs;
-                            if (t >= p.T) continue;
-                            float x[4] = {sv[i].x + b4.x, sv[i].y + b4.y, sv[i].z + b4.z, sv[i].w + b4.w};
-                            if (p.flags & EPI_SILU) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
-                            }
-                            const float m = mrow[it];
-                            x[0] = (fg.x * x[0] + fb.x) * m * g4.x + rv[i].x;
-                            x[1] = (fg.y * x[1] + fb.y) * m * g4.y + rv[i].y;
-                            x[2] = (fg.z * x[2] + fb.z) * m * g4.z + rv[i].z;
-                            x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[i].w;
-                            const long o = obase + (long)t * p.N + n;
-                            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
-                            if (p.out_hi) {
-                                uint32_t h01, l01, h23, l23;
-                                split_bf16x2(x[0], x[1], h01, l01); split_bf16x2(x[2], x[3], h23, l23);
-                                *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(h01, h23);
-                                *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(l01, l23);
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
+            epilogue_tile<BN>(p, bb, t0, n_tile * BN, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN), stg, eh, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -424,14 +338,10 @@ cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t s) {
     if (!get_map(g.W_hi, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BLOCK_K, BN, &maps.w_hi)) return cudaErrorInvalidValue;
     if (!get_map(g.W_lo, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BLOCK_K, BN, &maps.w_lo)) return cudaErrorInvalidValue;
     TcParams p;
-    p.n_src = g.n_src; p.Cs0 = g.Cs[0]; p.Cs1 = g.Cs[1]; p.taps = g.taps; p.N = g.N; p.a_bmod = g.a_bmod; p.BB = g.BB; p.T = g.T;
+    fill_tc_params(p, g);
     p.m_tiles_per_b = (g.T + BLOCK_M - 1) / BLOCK_M;
     p.n_tiles = (g.N + BN - 1) / BN;
     p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
-    p.flags = g.flags; p.B = g.B; p.film_H = g.film_H; p.c_clamp = g.c_clamp; p.resid_clamp = g.resid_clamp;
-    p.film_bstride = g.film_bstride; p.gate_bstride = g.gate_bstride;
-    p.bias = g.bias; p.mask = g.mask; p.film = g.film; p.gate = g.gate; p.resid = g.resid;
-    p.out_f32 = g.out_f32; p.out_hi = g.out_hi; p.out_lo = g.out_lo;
     constexpr int idx = BN == 256 ? 1 : 0;
     if (!g_attr_set[idx]) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);

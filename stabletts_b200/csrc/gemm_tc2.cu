@@ -13,6 +13,7 @@
 //   tmem_empty[a]  leader only   count 16: 8 epilogue warps of each CTA (the peer arrives remotely, mapa)
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "gemm_epilogue.cuh"
 #include <string>
 
 namespace st {
@@ -38,14 +39,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 4096;
 
 struct Maps2 { CUtensorMap a_hi[2], a_lo[2], w_hi, w_lo; };
 
-struct Params2 {
-    int n_src, Cs0, Cs1, taps, N, a_bmod, BB, T;
-    int m_tiles_per_b, n_tiles, total_tiles;
-    int flags, B, film_H, c_clamp, resid_clamp;
-    long film_bstride, gate_bstride;
-    const float *bias, *mask, *film, *gate, *resid;
-    float* out_f32; bf16* out_hi; bf16* out_lo;
-};
+typedef TcParams Params2;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
@@ -141,92 +135,18 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
             }
         }
     } else if (warp >= 4) {
-        // ================= epilogue (both CTAs, own 128 rows) =================
+        // ================= epilogue (both CTAs, own 128 rows; 8 warps) =================
         const int wq = warp & 3;
+        const int eh = (warp - 4) >> 2;
         float4* stg = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 4) * 256;
-        const int eh = (warp - 4) >> 2;                // two warps share a lane quarter: even / odd 32-column chunks
-        const int rs = lane >> 3, c4 = lane & 7;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
             const int bb = m_tile / p.m_tiles_per_b;
             const int t0 = (m_tile % p.m_tiles_per_b) * (2 * BM) + (int)rank * BM + wq * 32;
-            const int n0 = n_tile * BN2;
-            const int mb = bb % p.B;
-            float mrow[8];
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int t = t0 + it * 4 + rs;
-                mrow[it] = ((p.flags & EPI_MASK) && t < p.T) ? __ldg(p.mask + (long)mb * p.T + t) : 1.f;
-            }
-            const float* film = p.film + (long)mb * p.film_bstride;
-            const float* gate = p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride;
-            const float* resid = p.resid + (long)min(bb, p.resid_clamp) * p.T * p.N;
-            const long obase = (long)bb * p.T * p.N;
-
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = eh * 32; c0 < BN2; c0 += 64) {
-                if (n0 + c0 >= p.N) break;
-                {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN2 + c0), v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        stg[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
-                                                                       __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
-                }
-                __syncwarp();
-                const int n = n0 + c0 + c4 * 4;
-                if (n < p.N) {                         // N % 4 == 0: a float4 column group is all-in or all-out
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = b4;
-                    if (p.flags & EPI_BIAS) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                    if (p.flags & EPI_GATE) g4 = __ldg(reinterpret_cast<const float4*>(gate + n));
-                    if (p.flags & EPI_FILM) {
-                        fg = __ldg(reinterpret_cast<const float4*>(film + n));
-                        fb = __ldg(reinterpret_cast<const float4*>(film + p.film_H + n));
-                    }
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        float4 sv[4], rv[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int rl = (hf * 4 + i) * 4 + rs;
-                            sv[i] = stg[rl * 8 + (c4 ^ (rl & 7))];
-                            rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if ((p.flags & EPI_RESID) && t0 + rl < p.T)
-                                rv[i] = __ldg(reinterpret_cast<const float4*>(resid + (long)(t0 + rl) * p.N + n));
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int it = hf * 4 + i;
-                            const int t = t0 + it * 4 + rs;
-                            if (t >= p.T) continue;
-                            float x[4] = {sv[i].x + b4.x, sv[i].y + b4.y, sv[i].z + b4.z, sv[i].w + b4.w};
-                            if (p.flags & EPI_SILU) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
-                            }
-                            const float m = mrow[it];
-                            x[0] = (fg.x * x[0] + fb.x) * m * g4.x + rv[i].x;
-                            x[1] = (fg.y * x[1] + fb.y) * m * g4.y + rv[i].y;
-                            x[2] = (fg.z * x[2] + fb.z) * m * g4.z + rv[i].z;
-                            x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[i].w;
-                            const long o = obase + (long)t * p.N + n;
-                            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
-                            if (p.out_hi) {
-                                uint32_t h01, l01, h23, l23;
-                                split_bf16x2(x[0], x[1], h01, l01); split_bf16x2(x[2], x[3], h23, l23);
-                                *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(h01, h23);
-                                *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(l01, l23);
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
+            epilogue_tile<BN2>(p, bb, t0, n_tile * BN2, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN2), stg, eh, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);      // the LEADER's barrier gates the next MMA
@@ -270,14 +190,10 @@ cudaError_t launch_gemm_tc2(const GemmArgs& g, int num_sms, cudaStream_t s) {
         g_err2 = gemm_tc_last_error(); return cudaErrorInvalidValue;
     }
     Params2 p;
-    p.n_src = g.n_src; p.Cs0 = g.Cs[0]; p.Cs1 = g.Cs[1]; p.taps = g.taps; p.N = g.N; p.a_bmod = g.a_bmod; p.BB = g.BB; p.T = g.T;
+    fill_tc_params(p, g);
     p.m_tiles_per_b = (g.T + 2 * BM - 1) / (2 * BM);
     p.n_tiles = (g.N + BN2 - 1) / BN2;
     p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
-    p.flags = g.flags; p.B = g.B; p.film_H = g.film_H; p.c_clamp = g.c_clamp; p.resid_clamp = g.resid_clamp;
-    p.film_bstride = g.film_bstride; p.gate_bstride = g.gate_bstride;
-    p.bias = g.bias; p.mask = g.mask; p.film = g.film; p.gate = g.gate; p.resid = g.resid;
-    p.out_f32 = g.out_f32; p.out_hi = g.out_hi; p.out_lo = g.out_lo;
     if (!g_attr2) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) { g_err2 = "cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc2_kernel"; return e; }
