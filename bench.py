@@ -259,8 +259,14 @@ def main():
             inp["fs"], inp["fc"] = fs_d.cpu(), fc_d.cpu()
         kw = dict(fake_speaker=fs_d, fake_content=fc_d, cfg_strength=cfgd["cfg"])
 
-    def solve(mu, mask, c, z):
+    def solve_one(mu, mask, c, z):
         return model(mu, mask, cfgd["n_steps"], 1.0, c, cfgd["method"], kw, z=z)
+
+    def solve(mu, mask, c, z):
+        if cfgd["lengths"] is None:
+            return solve_one(mu, mask, c, z)
+        lens_local = mask.sum(dim=(1, 2)).long().tolist()       # host-visible lengths (bucketing is host logic)
+        return shard.bucketed_solve(solve_one, mu, mask, c, z, lens_local, n_buckets=4)
 
     # device-resident global inputs on rank 0
     if rank == 0:

@@ -41,6 +41,40 @@ def partition_by_cost(lengths: Sequence[int], world: int) -> List[List[int]]:
     return [sorted(s, key=lambda i: lengths[i]) for s in shards]
 
 
+def length_buckets(lengths: Sequence[int], n_buckets: int) -> List[List[int]]:
+    """Bucket utterance indices by length (the idea of the reference's DistributedBucketSampler,
+    datas/sampler.py:4-132, applied to inference): sort by length, cut into ``n_buckets`` contiguous
+    groups of near-equal COST so each group pads only to its own maximum."""
+    order = sorted(range(len(lengths)), key=lambda i: lengths[i])
+    total = sum(utterance_cost(int(lengths[i])) for i in order)
+    buckets: List[List[int]] = [[]]
+    acc = 0.0
+    for i in order:
+        c = utterance_cost(int(lengths[i]))
+        if buckets[-1] and acc + c / 2 > total * len(buckets) / n_buckets and len(buckets) < n_buckets:
+            buckets.append([])
+        buckets[-1].append(i)
+        acc += c
+    return [b for b in buckets if b]
+
+
+def bucketed_solve(solve: Callable[..., torch.Tensor], mu, mask, c, z, lengths: Sequence[int], n_buckets: int = 4,
+                   min_pad: int = 3) -> torch.Tensor:
+    """Run ``solve`` per length bucket with each bucket cropped to (its max length + ``min_pad``) frames
+    (capped at T), and scatter the results back into a (B, M, T) tensor.  Padded frames stay zero
+    (the estimator's output is exactly 0 there).  ``min_pad`` >= 3 keeps the reference's padded-edge
+    behaviour: an utterance followed by >= 3 pad frames is insensitive to further padding
+    (SURVEY.md fact 4)."""
+    B, M, T = mu.shape
+    out = torch.zeros_like(z)
+    for idx in length_buckets(lengths, n_buckets):
+        Tb = min(T, max(int(lengths[i]) for i in idx) + min_pad)
+        sel = torch.as_tensor(idx, device=mu.device)
+        o = solve(mu[sel, :, :Tb].contiguous(), mask[sel, :, :Tb].contiguous(), c[sel].contiguous(), z[sel, :, :Tb].contiguous())
+        out[sel, :, :Tb] = o
+    return out
+
+
 def scatter_batch(tensors: Optional[Sequence[torch.Tensor]], counts: Sequence[int], src: int = 0,
                   group=None, device=None, meta: Optional[Sequence[tuple]] = None) -> List[torch.Tensor]:
     """Scatter each tensor's dim-0 slices (sizes ``counts``) from ``src`` with batched point-to-point

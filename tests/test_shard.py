@@ -79,3 +79,22 @@ def test_split_counts_and_cost_partition():
     assert max(loads) / min(loads) < 1.05
     for p in parts:
         assert [lens[i] for i in p] == sorted(lens[i] for i in p)
+
+
+def test_length_buckets_and_bucketed_solve():
+    g = torch.Generator().manual_seed(5)
+    lens = torch.randint(200, 2001, (128,), generator=g).tolist()
+    bk = shard.length_buckets(lens, 4)
+    assert sorted(i for b in bk for i in b) == list(range(128)) and len(bk) == 4
+    mx = [max(lens[i] for i in b) for b in bk]
+    assert mx == sorted(mx)
+    padded = sum(len(b) * m for b, m in zip(bk, mx))
+    assert padded < 0.75 * 128 * max(lens)                 # bucketing removes most of the padding waste
+    # plumbing with a per-utterance stand-in solve
+    B, M, T = 10, 4, 50
+    ls = [50, 7, 33, 20, 45, 12, 50, 9, 27, 41]
+    mask = (torch.arange(T)[None] < torch.tensor(ls)[:, None]).float().unsqueeze(1)
+    mu, z, c = torch.randn(B, M, T) * mask, torch.randn(B, M, T), torch.randn(B, 6)
+    f = lambda mu_, mask_, c_, z_: (z_ + 2 * mu_) * mask_ + c_.mean(1)[:, None, None] * mask_
+    out = shard.bucketed_solve(f, mu, mask, c, z, ls, n_buckets=3)
+    assert torch.allclose(out, f(mu, mask, c, z))
