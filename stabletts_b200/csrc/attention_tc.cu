@@ -271,35 +271,45 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
         for (int j = 0; j < nb; ++j) {
             const int k0 = j * AK;
             const uint32_t tS = tmem_base + (j & 1) * 64 + lane_addr;
-            const bool need_mask = k0 + AK > prefix;          // block reaches past the all-ones prefix
             mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
+            // key validity of this block as two warp-uniform 32-bit words (only blocks reaching past the
+            // all-ones prefix of the mask need it; interior blocks skip the test entirely)
+            const bool need_mask = k0 + AK > prefix;
+            uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu;
+            if (need_mask) {
+                const int ka = k0 + lane, kb = k0 + 32 + lane;
+                mb0 = __ballot_sync(0xffffffffu, ka < kvlen && __ldg(mrow + min(ka, p.T - 1)) != 0.f);
+                mb1 = __ballot_sync(0xffffffffu, kb < kvlen && __ldg(mrow + min(kb, p.T - 1)) != 0.f);
+            }
             uint32_t hw[32], lw[32];                          // packed P row: 64 keys x (hi, lo)
-            float cand, psum;
+            float cand = -CUDART_INF_F, psum = 0.f;
             bool waited_pv = (j == 0);
-            auto softmax_pass = [&](float m_eff) {
+            // single optimistic pass against the stale max; repeated once in the rare rescale case.
+            // (one code instance on purpose: the kernel must stay inside the instruction cache)
+#pragma unroll 1
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                const float m_eff = (m_used == -CUDART_INF_F) ? 0.f : m_used;
                 cand = -CUDART_INF_F; psum = 0.f;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     tmem_ld32(tS + half * 32, v);
                     tmem_ld_wait();
+                    if (need_mask) {
+                        const uint32_t bits = half ? mb1 : mb0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (!((bits >> i) & 1u)) v[i] = 0xff800000u;     // -inf
+                    }
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-                        if (need_mask) {
-                            const int kk = k0 + half * 32 + i;
-                            if (kk >= kvlen || __ldg(mrow + kk) == 0.f) s0 = -CUDART_INF_F;
-                            if (kk + 1 >= kvlen || __ldg(mrow + kk + 1) == 0.f) s1 = -CUDART_INF_F;
-                        }
+                        const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
                         cand = fmaxf(cand, fmaxf(s0, s1));
                         const float p0 = ex2_approx(s0 - m_eff), p1 = ex2_approx(s1 - m_eff);
                         psum += p0 + p1;
                         split_bf16x2(p0, p1, hw[half * 16 + i / 2], lw[half * 16 + i / 2]);
                     }
                 }
-            };
-            softmax_pass((m_used == -CUDART_INF_F) ? 0.f : m_used);      // optimistic: stale max
-            if (__any_sync(0xffffffffu, cand > m_used + LAZY_THRESHOLD)) {
+                if (attempt == 1 || !__any_sync(0xffffffffu, cand > m_used + LAZY_THRESHOLD)) break;
                 const float m_new = fmaxf(m_used, cand);
                 const float factor = (m_new == -CUDART_INF_F) ? 1.f : ex2_approx(m_used - m_new);    // m_used = -inf -> 0
                 l_run *= factor;
@@ -307,7 +317,7 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
                     mbar_wait(pv_done, (j - 1) & 1);
                     tc_fence_after();
                     waited_pv = true;
-#pragma unroll
+#pragma unroll 1
                     for (int half = 0; half < 2; ++half) {
                         tmem_ld32(tmem_O + lane_addr + half * 32, v);
                         tmem_ld_wait();
@@ -318,7 +328,6 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
                     tmem_st_wait();
                 }
                 m_used = m_new;
-                softmax_pass((m_used == -CUDART_INF_F) ? 0.f : m_used);  // redo against the new max
             }
             l_run += psum;
             if (!waited_pv) mbar_wait(pv_done, (j - 1) & 1);             // P buffer free (PV_{j-1} retired)
