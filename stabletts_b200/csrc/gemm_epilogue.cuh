@@ -73,17 +73,18 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, int bb, int t0,
         const bool rope = (p.flags & EPI_ROPE) && nb < 2 * p.rope_H && (nb & 63) == 0;
         const float post = ((p.flags & EPI_ROPE) && nb < p.rope_H) ? kQScale : 1.0f;
         const bool col_ok = n < p.N;           // N % 4 == 0: a float4 column group is all-in or all-out
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = b4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = b4, bp4 = b4;
         if (col_ok) {
             if (p.flags & EPI_BIAS) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            if (rope && (p.flags & EPI_BIAS)) bp4 = __ldg(reinterpret_cast<const float4*>(p.bias + (n ^ 16)));   // RoPE partner column
             if (p.flags & EPI_GATE) g4 = __ldg(reinterpret_cast<const float4*>(gate + n));
             if (p.flags & EPI_FILM) {
                 fg = __ldg(reinterpret_cast<const float4*>(film + n));
                 fb = __ldg(reinterpret_cast<const float4*>(film + p.film_H + n));
             }
         }
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {                 // not unrolled: keeps the epilogue inside the instruction cache
             float4 sv[4], rv[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -102,20 +103,19 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, int bb, int t0,
 #pragma unroll
                     for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
                 }
-                if (rope) {                    // warp-uniform branch; shuffles executed by all 32 lanes
-                    const int tc = min(t, p.T - 1);
+                if (rope) {                    // warp-uniform branch
+                    const int tc = min(t, p.T - 1), rl = it * 4 + rs;
                     const float4 cs0 = __ldg(reinterpret_cast<const float4*>(p.rope_cs + ((long)tc * 16 + (c4 & 3) * 4) * 2));
                     const float4 cs1 = __ldg(reinterpret_cast<const float4*>(p.rope_cs + ((long)tc * 16 + (c4 & 3) * 4) * 2 + 4));
+                    const float4 pv = stg[rl * 8 + ((c4 ^ 4) ^ (rl & 7))];      // partner dims (j +- 16) of the same frame
                     const float sgn = (c4 < 4) ? -1.f : 1.f;      // r_j = -x_{j+16} (j<16), +x_{j-16} (j>=16)
-                    const float p0 = __shfl_xor_sync(0xffffffffu, x[0], 4), p1 = __shfl_xor_sync(0xffffffffu, x[1], 4);
-                    const float p2 = __shfl_xor_sync(0xffffffffu, x[2], 4), p3 = __shfl_xor_sync(0xffffffffu, x[3], 4);
-                    x[0] = x[0] * cs0.x + sgn * p0 * cs0.y;
-                    x[1] = x[1] * cs0.z + sgn * p1 * cs0.w;
-                    x[2] = x[2] * cs1.x + sgn * p2 * cs1.y;
-                    x[3] = x[3] * cs1.z + sgn * p3 * cs1.w;
+                    x[0] = x[0] * cs0.x + sgn * (pv.x + bp4.x) * cs0.y;
+                    x[1] = x[1] * cs0.z + sgn * (pv.y + bp4.y) * cs0.w;
+                    x[2] = x[2] * cs1.x + sgn * (pv.z + bp4.z) * cs1.y;
+                    x[3] = x[3] * cs1.z + sgn * (pv.w + bp4.w) * cs1.w;
                 }
                 if (t >= p.T || !col_ok) continue;
-                const float m = mrow[it];
+                const float m = hf ? mrow[4 + i] : mrow[i];      // static indices: mrow stays in registers
                 x[0] = (fg.x * x[0] * post + fb.x) * m * g4.x + rv[i].x;
                 x[1] = (fg.y * x[1] * post + fb.y) * m * g4.y + rv[i].y;
                 x[2] = (fg.z * x[2] * post + fb.z) * m * g4.z + rv[i].z;

@@ -97,3 +97,31 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout only in the authoring container")
+def test_drop_in_inside_reference_stabletts(built):
+    """swapping the class in the reference's own StableTTS keeps its module tree and
+    checkpoint keys intact (the synthesise call itself needs a GPU and is covered by the -m gpu tests)."""
+    import sys
+    import types
+    sys.path.insert(0, "/root/reference")
+    if "torchdiffeq" not in sys.modules:
+        stub = types.ModuleType("torchdiffeq")
+        stub.odeint = lambda *a, **k: None
+        sys.modules["torchdiffeq"] = stub
+    import models.flow_matching as ref_fm
+    import models.model as ref_model
+    import stabletts_b200
+    ref = ref_model.StableTTS(401, 80, 256, 1024, 4, 3, 6, 3, 0.1, 256)
+    keys_ref = list(ref.state_dict().keys())
+    orig = ref_model.CFMDecoder
+    try:
+        ref_model.CFMDecoder = stabletts_b200.CFMDecoder          # the one-line swap of INTEGRATION.md
+        ours = ref_model.StableTTS(401, 80, 256, 1024, 4, 3, 6, 3, 0.1, 256)
+    finally:
+        ref_model.CFMDecoder = orig
+    assert isinstance(ours.decoder, stabletts_b200.CFMDecoder)
+    assert list(ours.state_dict().keys()) == keys_ref
+    ours.load_state_dict(ref.state_dict(), strict=True)          # a reference checkpoint loads unchanged
+    assert ref_fm.CFMDecoder is not stabletts_b200.CFMDecoder
