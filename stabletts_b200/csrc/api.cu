@@ -72,6 +72,12 @@ struct st_handle {
     std::vector<void*> owned;
     void* ws_ptr = nullptr; size_t ws_bytes = 0; bool ws_owned = false;
     int64_t launches = 0;
+    // CUDA-graph cache for launch-bound (small) solves: key -> instantiated graph + its launch count
+    struct GraphEntry { std::string key; cudaGraphExec_t exec; int64_t launches; };
+    std::vector<GraphEntry> graphs;
+    std::vector<std::string> graph_seen;   // keys enqueued directly once (kernels loaded, attributes set) before capture
+    int graph_mode = -1;               // -1: read STABLETTS_B200_GRAPH on first use; 0 off; 1 always; 2 auto (small problems)
+    void drop_graphs() { for (auto& g : graphs) cudaGraphExecDestroy(g.exec); graphs.clear(); }
     // optional per-launch CUDA-event profiling (bench.py roofline): category, flops, bytes, event pair
     bool prof_on = false;
     struct ProfRec { int cat; double flops, bytes; cudaEvent_t e0, e1; };
@@ -243,6 +249,7 @@ int ensure_ws(st_handle* h, Workspace& w, int B, int T, int cfg) {
     if (h->ws_ptr == nullptr || h->ws_bytes < probe.bytes) {
         if (h->ws_ptr && !h->ws_owned)
             return fail(h, "attached workspace too small: need " + std::to_string(probe.bytes) + " bytes");
+        h->drop_graphs();
         if (h->ws_ptr) { cudaFree(h->ws_ptr); h->ws_ptr = nullptr; }
         ST_CUDA(cudaMalloc(&h->ws_ptr, probe.bytes));
         h->ws_bytes = probe.bytes; h->ws_owned = true;
@@ -484,6 +491,7 @@ int st_destroy(st_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    h->drop_graphs();
     for (auto& kv : h->raw) cudaFree(kv.second.first);
     for (void* p : h->owned) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -494,6 +502,7 @@ int st_destroy(st_handle* h) {
 
 int st_set_engine(st_handle* h, int engine) {
     if (!h) return 1;
+    h->drop_graphs();
     if (engine != ST_ENGINE_TCGEN05 && engine != ST_ENGINE_SIMT) return fail(h, "unknown engine");
     h->engine = engine;
     return 0;
@@ -546,6 +555,7 @@ int st_finalize_weights(st_handle* h, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const st_dims& d = h->d;
     const int H = d.hidden, F = d.filter, M = d.n_mel, k = d.kernel, L = d.n_layers;
+    h->drop_graphs();                  // cached graphs hold pointers into the old packed weights
     for (void* p : h->owned) cudaFree(p);
     h->owned.clear();
     h->qkv.assign(L, GemmW()); h->wo.assign(L, GemmW()); h->c1.assign(L, GemmW()); h->c2.assign(L, GemmW());
@@ -589,6 +599,7 @@ size_t st_workspace_bytes(const st_handle* h, int B, int T, int cfg) {
 int st_attach_workspace(st_handle* h, void* dev_ptr, size_t bytes) {
     if (!h) return 1;
     if (h->ws_ptr && h->ws_owned) { cudaSetDevice(h->device); cudaFree(h->ws_ptr); }
+    h->drop_graphs();                  // cached graphs hold pointers into the old workspace
     h->ws_ptr = dev_ptr; h->ws_bytes = dev_ptr ? bytes : 0; h->ws_owned = false;
     return 0;
 }
@@ -612,18 +623,10 @@ int st_estimator_forward(st_handle* h, const float* t, int t_count, const float*
     return 0;
 }
 
-int st_solve(st_handle* h, float* z_inout, const float* mu, const float* mask, const float* c, const float* fake_content,
-             const float* fake_speaker, float cfg_strength, const float* t_span_host, int n_steps, int method, int B, int T,
-             void* stream) {
-    if (check_common(h, B, T)) return 1;
-    if (!z_inout || !mu || !mask || !c || !t_span_host) return fail(h, "st_solve: null pointer");
-    if (n_steps <= 0) return fail(h, "n_timesteps must be positive");
-    if (method < ST_EULER || method > ST_DOPRI5_FIXED) return fail(h, "unknown ODE method");
-    const int cfg = (fake_content && fake_speaker) ? 1 : 0;
-    if (!cfg && (fake_content || fake_speaker)) return fail(h, "CFG needs both fake_content and fake_speaker");
-    cudaStream_t s = (cudaStream_t)stream;
-    Workspace w;
-    if (ensure_ws(h, w, B, T, cfg)) return 1;
+// enqueues one complete solve on `s` (no host synchronisation, capturable into a CUDA graph)
+static int solve_impl(st_handle* h, Workspace& w, float* z_inout, const float* mu, const float* mask, const float* c,
+                      const float* fake_content, const float* fake_speaker, float cfg_strength, const float* t_span_host,
+                      int n_steps, int method, int B, int T, int cfg, cudaStream_t s) {
     const st_dims& d = h->d;
     const Tableau tb = tableau_for(method);
     const long numel = (long)B * T * d.n_mel;
@@ -675,6 +678,82 @@ int st_solve(st_handle* h, float* z_inout, const float* mu, const float* mask, c
         }
     }
     ST_LAUNCH(launch_btc_to_bct(w.xt.f32, z_inout, B, d.n_mel, T, s));
+    return 0;
+}
+
+int st_solve(st_handle* h, float* z_inout, const float* mu, const float* mask, const float* c, const float* fake_content,
+             const float* fake_speaker, float cfg_strength, const float* t_span_host, int n_steps, int method, int B, int T,
+             void* stream) {
+    if (check_common(h, B, T)) return 1;
+    if (!z_inout || !mu || !mask || !c || !t_span_host) return fail(h, "st_solve: null pointer");
+    if (n_steps <= 0) return fail(h, "n_timesteps must be positive");
+    if (method < ST_EULER || method > ST_DOPRI5_FIXED) return fail(h, "unknown ODE method");
+    const int cfg = (fake_content && fake_speaker) ? 1 : 0;
+    if (!cfg && (fake_content || fake_speaker)) return fail(h, "CFG needs both fake_content and fake_speaker");
+    cudaStream_t s = (cudaStream_t)stream;
+    Workspace w;
+    if (ensure_ws(h, w, B, T, cfg)) return 1;
+    const st_dims& d = h->d;
+    if (h->graph_mode < 0) {
+        const char* e = getenv("STABLETTS_B200_GRAPH");
+        h->graph_mode = !e ? 2 : (!strcmp(e, "0") ? 0 : (!strcmp(e, "1") ? 1 : 2));
+    }
+    // Small problems are launch-bound (~90 kernels per evaluation, a few microseconds each): replay the whole
+    // solve as one CUDA graph.  Inputs are staged into workspace-owned buffers so the graph's pointers are stable.
+    const long rows = (long)(cfg ? 2 * B : B) * T;
+    const bool use_graph = !h->prof_on && (h->graph_mode == 1 || (h->graph_mode == 2 && rows <= 24576));
+    if (!use_graph)
+        return solve_impl(h, w, z_inout, mu, mask, c, fake_content, fake_speaker, cfg_strength, t_span_host, n_steps, method, B, T, cfg, s);
+
+    const size_t n = (size_t)B * T * d.n_mel;
+    if (z_inout != w.h_z) ST_CUDA(cudaMemcpyAsync(w.h_z, z_inout, n * 4, cudaMemcpyDeviceToDevice, s));
+    if (mu != w.h_mu) ST_CUDA(cudaMemcpyAsync(w.h_mu, mu, n * 4, cudaMemcpyDeviceToDevice, s));
+    if (mask != w.h_mask) ST_CUDA(cudaMemcpyAsync(w.h_mask, mask, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, s));
+    if (c != w.h_c) ST_CUDA(cudaMemcpyAsync(w.h_c, c, (size_t)B * d.gin * 4, cudaMemcpyDeviceToDevice, s));
+    if (cfg) {
+        if (fake_content != w.h_fc) ST_CUDA(cudaMemcpyAsync(w.h_fc, fake_content, (size_t)d.n_mel * 4, cudaMemcpyDeviceToDevice, s));
+        if (fake_speaker != w.h_fs) ST_CUDA(cudaMemcpyAsync(w.h_fs, fake_speaker, (size_t)d.gin * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    std::string key((const char*)t_span_host, sizeof(float) * (n_steps + 1));
+    char meta[160];
+    snprintf(meta, sizeof meta, "|%d,%d,%d,%d,%d,%d,%08x,%p", B, T, cfg, method, n_steps, h->engine, *(const unsigned*)&cfg_strength, h->ws_ptr);
+    key += meta;
+    st_handle::GraphEntry* ge = nullptr;
+    for (auto& g : h->graphs) if (g.key == key) { ge = &g; break; }
+    if (!ge) {
+        bool seen = false;
+        for (auto& k : h->graph_seen) if (k == key) { seen = true; break; }
+        if (!seen) {                   // first occurrence: plain enqueue (module loading / attribute calls stay out of capture)
+            if (h->graph_seen.size() >= 32) h->graph_seen.clear();
+            h->graph_seen.push_back(key);
+            return solve_impl(h, w, z_inout, mu, mask, c, fake_content, fake_speaker, cfg_strength, t_span_host, n_steps, method, B, T, cfg, s);
+        }
+        const int64_t l0 = h->launches;
+        cudaGraph_t graph = nullptr;
+        ST_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = solve_impl(h, w, w.h_z, w.h_mu, w.h_mask, w.h_c, cfg ? w.h_fc : nullptr, cfg ? w.h_fs : nullptr, cfg_strength,
+                            t_span_host, n_steps, method, B, T, cfg, s);
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        const int64_t captured = h->launches - l0;
+        h->launches = l0;
+        if (rc || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            h->graph_mode = 0;                         // do not retry: fall back to direct enqueue for this handle
+            if (rc) return 1;
+            return solve_impl(h, w, z_inout, mu, mask, c, fake_content, fake_speaker, cfg_strength, t_span_host, n_steps, method, B, T, cfg, s);
+        }
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { cudaGetLastError(); h->graph_mode = 0; return fail(h, std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ie)); }
+        if (h->graphs.size() >= 8) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+        h->graphs.push_back({key, exec, captured});
+        ge = &h->graphs.back();
+    }
+    ST_CUDA(cudaGraphLaunch(ge->exec, s));
+    h->launches += ge->launches;
+    if (z_inout != w.h_z) ST_CUDA(cudaMemcpyAsync(z_inout, w.h_z, n * 4, cudaMemcpyDeviceToDevice, s));
     return 0;
 }
 

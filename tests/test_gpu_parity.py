@@ -154,3 +154,32 @@ def test_properties_at_benchmark_shape(dev):
     o643 = m.estimator(one["t"].to(dev), x0[:, :, :643].contiguous().to(dev), one["mask"][:, :, :643].contiguous().to(dev),
                        one["mu"][:, :, :643].contiguous().to(dev), one["c"].to(dev))
     assert rel_errs(o643[:, :, :640], o700[:, :, :640])[0] < 1e-4
+
+
+def test_graph_replay_and_host_entry(dev, golden_dir):
+    """Small solves are replayed as a CUDA graph from the 2nd identical call on: the 1st (direct), 2nd
+    (capture + launch) and 3rd (replay) results must be bit-identical; st_solve_host (host buffers,
+    copies inside the call) must agree too."""
+    import ctypes as C
+    from stabletts_b200 import _lib
+    cs = cases.SOLVE_CASES["solve_euler10_cfg"]
+    m = model_for(cs["n_mel"], "tcgen05", dev)
+    inp = weights.make_inputs(cs["seed"], cs["lengths"], cs["T"], cs["n_mel"])
+    fs, fc = weights.make_cfg_params(cases.CFG_SEED, cs["n_mel"])
+    kw = dict(fake_speaker=fs.to(dev), fake_content=fc.to(dev), cfg_strength=cs["cfg"])
+    torch.manual_seed(cs["seed"] + 1000)
+    z = torch.randn_like(inp["mu"])
+    outs = [m(inp["mu"].to(dev), inp["mask"].to(dev), cs["steps"], 1.0, inp["c"].to(dev), "euler", kw, z=z.to(dev)).cpu() for _ in range(3)]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    g = np.load(os.path.join(golden_dir, "solve_euler10_cfg.npz"))
+    assert rel_errs(outs[2], torch.from_numpy(g["out"]))[0] < 1e-3
+    # host-buffer entry point of the C ABI
+    lib, h = _lib.load_library(), m.estimator._handle
+    B, M, T = z.shape
+    zh = z.clone().contiguous(); muh = inp["mu"].contiguous(); mk = inp["mask"].reshape(B, T).contiguous(); ch = inp["c"].contiguous()
+    fch, fsh = fc.reshape(-1).contiguous(), fs.reshape(-1).contiguous()
+    tspan = (C.c_float * (cs["steps"] + 1))(*torch.linspace(0, 1, cs["steps"] + 1).tolist())
+    rc = lib.st_solve_host(h, zh.data_ptr(), muh.data_ptr(), mk.data_ptr(), ch.data_ptr(), fch.data_ptr(), fsh.data_ptr(),
+                           C.c_float(cs["cfg"]), tspan, cs["steps"], _lib.ST_EULER, B, T, torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib, h, rc, "st_solve_host")
+    assert rel_errs(zh, outs[0])[0] < 1e-6
