@@ -34,6 +34,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
+    "cfg0": dict(B=1, T=300, n_steps=10, method="euler", cfg=3.0, lengths=None,
+                 desc="batch=1, ~300-frame mel (64 phonemes), 10-step Euler + CFG — the reference's CPU-runnable plumbing case"),
     # name: per-GPU batch, T, steps, method, cfg, description (BASELINE.json configs[1..4])
     "cfg1": dict(B=32, T=1000, n_steps=10, method="euler", cfg=3.0, lengths=None,
                  desc="batch=32/GPU, n_mel=80, T=1000, 10-step Euler + CFG"),
@@ -362,6 +364,11 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))["dram_bytes_per_launch_avg"]
+    except Exception:
+        pass
     gm = prof["gemm"]
     ach_tf = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
     nfe = cfgd["n_steps"] * NFE_PER_STEP[cfgd["method"]] * (2 if cfgd["cfg"] is not None else 1)
@@ -406,7 +413,9 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 2),
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 split-bf16 conv-GEMM, all launches of one solve)",
-                     "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
+                     "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
+                     "traffic_note": "dram__bytes_read+write per launch, mean over the ncu --set full capture in profiles/gemm_traffic.json",
+                     "achieved_per_launch_gflop": gm["flops"] / max(gm["launches"], 1) / 1e9,
                      "peak_source": peak_src, "launches": gm["launches"], "kernel_ms_per_step": gm["ms"],
                      "note": "algorithmic FLOPs (2*rows*N*K*taps); the bf16x3 split issues 3 MMAs per algorithmic MAC"},
         "breakdown_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
