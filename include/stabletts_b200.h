@@ -103,6 +103,17 @@ int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const
                   float cfg_strength, const float* t_span_host, int n_steps, int method, int B, int T,
                   void* stream);
 
+/* ---- caller-side glue: StableTTS.synthesise's duration -> alignment -> mu_y ----
+ * Replaces models/model.py:83-85 + the cumsum of generate_path (:19):
+ *   logw, x_mask: (B, Tx) device fp32 (the reference's (B,1,Tx));  cum out (B, Tx) fp32 cumulative
+ *   ceil-durations;  y_lengths out (B) int64 = clamp_min(sum(ceil(exp(logw)*mask)*length_scale), 1). */
+int st_align_lengths(const float* logw, const float* x_mask, float length_scale, int B, int Tx, float* cum,
+                     int64_t* y_lengths, void* stream);
+/* Replaces models/model.py:89-95 (sequence_mask, generate_path :17-27, attn^T·mu_x as a gather):
+ *   mu_x (B, M, Tx) -> mu_y (B, M, Ty), y_mask (B, Ty); attn (B, Tx, Ty) dense path or NULL. */
+int st_align_expand(const float* mu_x, const float* x_mask, const float* cum, const int64_t* y_lengths, int B, int M,
+                    int Tx, int Ty, float* mu_y, float* y_mask, float* attn, void* stream);
+
 /* Number of kernels this library launched since the handle was created (bench.py gpu_launches). */
 int64_t st_launch_count(const st_handle* h);
 

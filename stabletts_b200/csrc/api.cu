@@ -76,6 +76,7 @@ struct st_handle {
     struct GraphEntry { std::string key; cudaGraphExec_t exec; int64_t launches; };
     std::vector<GraphEntry> graphs;
     std::vector<std::string> graph_seen;   // keys enqueued directly once (kernels loaded, attributes set) before capture
+    cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the caller's may be the legacy stream)
     int graph_mode = -1;               // -1: read STABLETTS_B200_GRAPH on first use; 0 off; 1 always; 2 auto (small problems)
     void drop_graphs() { for (auto& g : graphs) cudaGraphExecDestroy(g.exec); graphs.clear(); }
     // optional per-launch CUDA-event profiling (bench.py roofline): category, flops, bytes, event pair
@@ -123,6 +124,7 @@ int fail(st_handle* h, const std::string& msg) {
 // in: (Nsrc, Csrc, k) reference Conv1d / Linear layout -> out[tap][n_off + n][c] for c in [c_off, c_off+Cc)
 __global__ void pack_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int Nsrc, int Csrc, int k,
                                  int Ntot, int n_off, int c_off, int Cc) {
+    pdl_trigger(); pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     long total = (long)k * Nsrc * Cc;
     if (i >= total) return;
@@ -135,6 +137,7 @@ __global__ void pack_conv_kernel(const float* __restrict__ in, float* __restrict
 
 struct TArr { float v[256]; };
 __global__ void time_embed_val_kernel(TArr t, int n_t, int H, float* __restrict__ out) {
+    pdl_trigger(); pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int half = H / 2;
     if (i >= n_t * half) return;
@@ -492,6 +495,7 @@ int st_destroy(st_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     h->drop_graphs();
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     for (auto& kv : h->raw) cudaFree(kv.second.first);
     for (void* p : h->owned) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -730,17 +734,20 @@ int st_solve(st_handle* h, float* z_inout, const float* mu, const float* mask, c
         }
         const int64_t l0 = h->launches;
         cudaGraph_t graph = nullptr;
-        ST_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        if (!h->cap_stream) ST_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+        ST_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
         int rc = solve_impl(h, w, w.h_z, w.h_mu, w.h_mask, w.h_c, cfg ? w.h_fc : nullptr, cfg ? w.h_fs : nullptr, cfg_strength,
-                            t_span_host, n_steps, method, B, T, cfg, s);
-        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+                            t_span_host, n_steps, method, B, T, cfg, h->cap_stream);
+        cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
         const int64_t captured = h->launches - l0;
         h->launches = l0;
         if (rc || ce != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
             h->graph_mode = 0;                         // do not retry: fall back to direct enqueue for this handle
-            if (rc) return 1;
+            if (getenv("STABLETTS_B200_DEBUG"))
+                fprintf(stderr, "[stabletts_b200] graph capture failed (%s / %s); falling back to direct enqueue\n",
+                        cudaGetErrorString(ce), h->err.c_str());
             return solve_impl(h, w, z_inout, mu, mask, c, fake_content, fake_speaker, cfg_strength, t_span_host, n_steps, method, B, T, cfg, s);
         }
         cudaGraphExec_t exec = nullptr;
@@ -781,6 +788,24 @@ int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const
         return 1;
     ST_CUDA(cudaMemcpyAsync(z_inout_host, w.h_z, n * 4, cudaMemcpyDeviceToHost, s));
     ST_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ---- caller-side glue of the path; stateless: errors go to st_last_error(NULL) ----
+int st_align_lengths(const float* logw, const float* x_mask, float length_scale, int B, int Tx, float* cum, int64_t* y_lengths,
+                     void* stream) {
+    st_handle* h = nullptr;
+    if (!logw || !x_mask || !cum || !y_lengths || B < 0 || Tx <= 0) return fail(h, "st_align_lengths: bad argument");
+    ST_CUDA(launch_align_lengths(logw, x_mask, length_scale, B, Tx, cum, (long long*)y_lengths, (cudaStream_t)stream));
+    return 0;
+}
+
+int st_align_expand(const float* mu_x, const float* x_mask, const float* cum, const int64_t* y_lengths, int B, int M, int Tx,
+                    int Ty, float* mu_y, float* y_mask, float* attn, void* stream) {
+    st_handle* h = nullptr;
+    if (!mu_x || !x_mask || !cum || !y_lengths || !mu_y || !y_mask || B < 0 || M <= 0 || Tx <= 0 || Ty < 0)
+        return fail(h, "st_align_expand: bad argument");
+    ST_CUDA(launch_align_expand(mu_x, x_mask, cum, (const long long*)y_lengths, B, M, Tx, Ty, mu_y, y_mask, attn, (cudaStream_t)stream));
     return 0;
 }
 

@@ -20,6 +20,7 @@ constexpr int DH = 64;       // head dim
 constexpr int DROT = 32;     // rotated dims
 
 __global__ void __launch_bounds__(AT_Q) attention_simt_kernel(AttnArgs a) {
+    pdl_trigger(); pdl_wait();
     __shared__ __align__(16) float Ks[AT_K][DH];
     __shared__ __align__(16) float Vs[AT_K][DH];
     __shared__ float Mk[AT_K];

@@ -149,6 +149,7 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
              *pv_done = bars + 6, *s_full = bars + 7 /*[2]*/, *p_full = bars + 9;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
     if (sPl + P_BYTES > smem_raw + ATT_SMEM) __trap();               // dynamic smem base less aligned than assumed
+    pdl_trigger(); pdl_wait();         // (this kernel's prologue is tiny: wait up front, before the kvlen read)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bb = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
@@ -446,9 +447,8 @@ cudaError_t launch_attention_tc(const AttnArgs& a, const AttnTcScratch& sc, cuda
         g_att_attr = true;
     }
     dim3 grid((a.T + AQ - 1) / AQ, a.n_heads, a.BB);
-    if (use_vt) attention_tc_kernel<false><<<grid, A_THREADS, ATT_SMEM, s>>>(maps, p);
-    else attention_tc_kernel<true><<<grid, A_THREADS, ATT_SMEM, s>>>(maps, p);
-    return cudaGetLastError();
+    if (use_vt) return launch_k(attention_tc_kernel<false>, grid, dim3(A_THREADS), (size_t)ATT_SMEM, s, maps, p);
+    return launch_k(attention_tc_kernel<true>, grid, dim3(A_THREADS), (size_t)ATT_SMEM, s, maps, p);
 }
 
 }  // namespace st

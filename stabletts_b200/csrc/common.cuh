@@ -105,6 +105,12 @@ cudaError_t launch_lincomb(float* dst, const float* y, const float* const* K, co
 // fp32 -> split bf16 planes
 cudaError_t launch_split(const float* in, bf16* hi, bf16* lo, long numel, cudaStream_t s);
 
+// duration -> alignment -> mu_y expansion (align.cu; models/model.py:81-95)
+cudaError_t launch_align_lengths(const float* logw, const float* x_mask, float length_scale, int B, int Tx, float* cum,
+                                 long long* ylen, cudaStream_t s);
+cudaError_t launch_align_expand(const float* mu_x, const float* x_mask, const float* cum, const long long* ylen, int B, int M,
+                                int Tx, int Ty, float* mu_y, float* y_mask, float* attn, cudaStream_t s);
+
 // ----------------------------------------------------------------------------------------------
 // attention (attention.cu): qkv (BB, T, 3H) fp32 -> out (BB, T, H); partial RoPE fused on load.
 // ----------------------------------------------------------------------------------------------
@@ -132,6 +138,26 @@ cudaError_t launch_rope_split(const float* qkv, const float* rope_cs, bf16* hi, 
 const char* attention_tc_last_error();
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the path (1) lets its successor start launching
+// immediately and (2) waits for ALL its predecessors to complete before its first global access, so
+// launch latency, smem carve-up, barrier init, TMEM allocation and tensor-map prefetch of kernel N+1
+// overlap the tail of kernel N.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();     // elementwise.cu: STABLETTS_B200_PDL != "0"
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 // two floats -> packed (hi0,hi1) and (lo0,lo1) bf16x2 words: one cvt.rn.bf16x2 per plane

@@ -2,14 +2,23 @@
 // LayerNorm → adaLN-modulate (one pass, warp-shuffle reductions), tiny GEMVs for the
 // t-/c-conditioning vectors, CFG combine and Runge–Kutta linear combinations.
 #include "common.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace st {
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("STABLETTS_B200_PDL"); v = (e && !strcmp(e, "0")) ? 0 : 1; }
+    return v == 1;
+}
 
 // ---------------------------------------------------------------------------------------------
 // (B, C, T) <-> (B, T, C) tiled transposes (32x32 smem tile, +1 padding: conflict-free)
 // ---------------------------------------------------------------------------------------------
 __global__ void bct_to_btc_kernel(const float* __restrict__ in, float* __restrict__ out_f32, bf16* __restrict__ out_hi,
                                   bf16* __restrict__ out_lo, int B, int C, int T, const float* __restrict__ bcast) {
+    pdl_trigger(); pdl_wait();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -35,11 +44,11 @@ __global__ void bct_to_btc_kernel(const float* __restrict__ in, float* __restric
 cudaError_t launch_bct_to_btc(const float* in, float* out_f32, bf16* out_hi, bf16* out_lo, int B, int C, int T,
                               const float* bcast, cudaStream_t s) {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B + (bcast ? 1 : 0)), block(32, 8);
-    bct_to_btc_kernel<<<grid, block, 0, s>>>(in, out_f32, out_hi, out_lo, B, C, T, bcast);
-    return cudaGetLastError();
+    return launch_k(bct_to_btc_kernel, grid, block, 0, s, in, out_f32, out_hi, out_lo, B, C, T, bcast);
 }
 
 __global__ void btc_to_bct_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int T) {
+    pdl_trigger(); pdl_wait();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -56,8 +65,7 @@ __global__ void btc_to_bct_kernel(const float* __restrict__ in, float* __restric
 
 cudaError_t launch_btc_to_bct(const float* in, float* out, int B, int C, int T, cudaStream_t s) {
     dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    btc_to_bct_kernel<<<grid, block, 0, s>>>(in, out, B, C, T);
-    return cudaGetLastError();
+    return launch_k(btc_to_bct_kernel, grid, block, 0, s, in, out, B, C, T);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -68,6 +76,7 @@ cudaError_t launch_btc_to_bct(const float* in, float* out, int B, int C, int T, 
 // ---------------------------------------------------------------------------------------------
 template <int H>
 __global__ void __launch_bounds__(256) film_ln_mod_kernel(LnArgs a) {
+    pdl_trigger(); pdl_wait();
     constexpr int V = H / 32;          // channels per lane
     static_assert(V % 4 == 0, "H must be a multiple of 128");
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -147,8 +156,7 @@ cudaError_t launch_film_ln_mod(const LnArgs& a, cudaStream_t s) {
     long rows = (long)a.BB * a.T;
     if (rows == 0) return cudaSuccess;
     int blocks = (int)((rows * 32 + 255) / 256);
-    film_ln_mod_kernel<256><<<blocks, 256, 0, s>>>(a);
-    return cudaGetLastError();
+    return launch_k(film_ln_mod_kernel<256>, dim3(blocks), dim3(256), 0, s, a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -156,6 +164,7 @@ cudaError_t launch_film_ln_mod(const LnArgs& a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 __global__ void gemv_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                             float* __restrict__ y, long y_rstride, int R, int K, int N, int silu_in, int silu_out) {
+    pdl_trigger(); pdl_wait();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (gw >= R * N) return;
@@ -182,12 +191,12 @@ cudaError_t launch_gemv(const float* x, const float* W, const float* bias, float
     long warps = (long)R * N;
     if (warps == 0) return cudaSuccess;
     int blocks = (int)((warps * 32 + 255) / 256);
-    gemv_kernel<<<blocks, 256, 0, s>>>(x, W, bias, y, y_rstride, R, K, N, silu_in, silu_out);
-    return cudaGetLastError();
+    return launch_k(gemv_kernel, dim3(blocks), dim3(256), 0, s, x, W, bias, y, y_rstride, R, K, N, silu_in, silu_out);
 }
 
 // models/estimator.py:41-49: emb = 1000 * t * exp(-i * ln(1e4)/(half-1)); cat(sin, cos)
 __global__ void time_embed_kernel(const float* __restrict__ t, int n_t, int H, float* __restrict__ out) {
+    pdl_trigger(); pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int half = H / 2;
     if (i >= n_t * half) return;
@@ -201,12 +210,12 @@ __global__ void time_embed_kernel(const float* __restrict__ t, int n_t, int H, f
 
 cudaError_t launch_time_embed(const float* t, int n_t, int H, float* out, cudaStream_t s) {
     int n = n_t * (H / 2);
-    time_embed_kernel<<<(n + 127) / 128, 128, 0, s>>>(t, n_t, H, out);
-    return cudaGetLastError();
+    return launch_k(time_embed_kernel, dim3((n + 127) / 128), dim3(128), 0, s, t, n_t, H, out);
 }
 
 // models/diffusion_transformer.py:157-171: theta_i = 1/base^(2i/d); angle = pos * theta_i
 __global__ void rope_table_kernel(float* __restrict__ cs, int T, int d_rot) {
+    pdl_trigger(); pdl_wait();
     int half = d_rot / 2;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T * half) return;
@@ -220,11 +229,11 @@ __global__ void rope_table_kernel(float* __restrict__ cs, int T, int d_rot) {
 cudaError_t launch_rope_table(float* cs, int T, int d_rot, cudaStream_t s) {
     int n = T * (d_rot / 2);
     if (n == 0) return cudaSuccess;
-    rope_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(cs, T, d_rot);
-    return cudaGetLastError();
+    return launch_k(rope_table_kernel, dim3((n + 127) / 128), dim3(128), 0, s, cs, T, d_rot);
 }
 
 __global__ void mask_lengths_kernel(const float* __restrict__ mask, int* __restrict__ kvlen, int* __restrict__ prefix, int B, int T) {
+    pdl_trigger(); pdl_wait();
     int b = blockIdx.x;
     int best = 0, first0 = T;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -252,11 +261,11 @@ __global__ void mask_lengths_kernel(const float* __restrict__ mask, int* __restr
 }
 
 cudaError_t launch_mask_lengths(const float* mask, int* kvlen, int* prefix, int B, int T, cudaStream_t s) {
-    mask_lengths_kernel<<<B, 256, 0, s>>>(mask, kvlen, prefix, B, T);
-    return cudaGetLastError();
+    return launch_k(mask_lengths_kernel, dim3(B), dim3(256), 0, s, mask, kvlen, prefix, B, T);
 }
 
 __global__ void cfg_combine_kernel(const float* __restrict__ V, float* __restrict__ K, long n, int cfg, float s_cfg) {
+    pdl_trigger(); pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float c = V[i];
@@ -267,13 +276,13 @@ __global__ void cfg_combine_kernel(const float* __restrict__ V, float* __restric
 cudaError_t launch_cfg_combine(const float* V, float* K_out, int B, long per_batch, int cfg, float s_cfg, cudaStream_t s) {
     long n = (long)B * per_batch;
     if (n == 0) return cudaSuccess;
-    cfg_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(V, K_out, n, cfg, s_cfg);
-    return cudaGetLastError();
+    return launch_k(cfg_combine_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, V, K_out, n, cfg, s_cfg);
 }
 
 struct LinArgs { const float* K[6]; float coef[6]; int n; };
 
 __global__ void lincomb_kernel(float* __restrict__ dst, const float* __restrict__ y, LinArgs a, long numel) {
+    pdl_trigger(); pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= numel) return;
     float acc = 0.f;
@@ -289,11 +298,11 @@ cudaError_t launch_lincomb(float* dst, const float* y, const float* const* K, co
     LinArgs a;
     for (int j = 0; j < 6; ++j) { a.K[j] = j < n ? K[j] : nullptr; a.coef[j] = j < n ? coef[j] : 0.f; }
     a.n = n;
-    lincomb_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, s>>>(dst, y, a, numel);
-    return cudaGetLastError();
+    return launch_k(lincomb_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, s, dst, y, a, numel);
 }
 
 __global__ void split_kernel(const float* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo, long n) {
+    pdl_trigger(); pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     bf16 h, l;
@@ -303,8 +312,7 @@ __global__ void split_kernel(const float* __restrict__ in, bf16* __restrict__ hi
 
 cudaError_t launch_split(const float* in, bf16* hi, bf16* lo, long numel, cudaStream_t s) {
     if (numel == 0) return cudaSuccess;
-    split_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, s>>>(in, hi, lo, numel);
-    return cudaGetLastError();
+    return launch_k(split_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, s, in, hi, lo, numel);
 }
 
 }  // namespace st

@@ -10,6 +10,7 @@ namespace st {
 constexpr int SM_BM = 64, SM_BN = 64, SM_BK = 16;
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
+    pdl_trigger(); pdl_wait();
     __shared__ __align__(16) float As[SM_BK][SM_BM + 4];
     __shared__ __align__(16) float Ws[SM_BK][SM_BN + 4];
     const int bb = blockIdx.z;

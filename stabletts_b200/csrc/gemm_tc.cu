@@ -155,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+    pdl_trigger();                     // successor may start its prologue now; it waits for us before touching memory
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb0 = (p.Cs0 + BLOCK_K - 1) / BLOCK_K;
     const int kb1 = p.n_src > 1 ? (p.Cs1 + BLOCK_K - 1) / BLOCK_K : 0;
@@ -179,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                        // predecessors complete: operands / residuals are valid from here on
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -349,8 +351,7 @@ cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t s) {
         g_attr_set[idx] = true;
     }
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-    gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(maps, p);
-    return cudaGetLastError();
+    return launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, s, maps, p);
 }
 
 }  // namespace

@@ -51,6 +51,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
@@ -75,6 +76,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
     cluster_sync();                    // peer barriers initialised, both TMEM allocations done
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
@@ -201,8 +203,7 @@ cudaError_t launch_gemm_tc2(const GemmArgs& g, int num_sms, cudaStream_t s) {
     }
     const int pairs = num_sms / 2;
     const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
-    gemm_tc2_kernel<<<2 * clusters, THREADS, SMEM_BYTES, s>>>(maps, p);
-    return cudaGetLastError();
+    return launch_k(gemm_tc2_kernel, dim3(2 * clusters), dim3(THREADS), (size_t)SMEM_BYTES, s, maps, p);
 }
 
 }  // namespace st
