@@ -114,6 +114,16 @@ int st_align_lengths(const float* logw, const float* x_mask, float length_scale,
 int st_align_expand(const float* mu_x, const float* x_mask, const float* cum, const int64_t* y_lengths, int B, int M,
                     int Tx, int Ty, float* mu_y, float* y_mask, float* attn, void* stream);
 
+/* ---- TextEncoder (models/text_encoder.py:8-44) on the same kernels ---------------
+ * dims: n_mel = out_channels, n_layers = n_enc_layers (3).  Weights are loaded with st_load_weight under the
+ * reference keys relative to `encoder.`: "emb.weight", "encoder.{i}.attn.conv_{q,k,v,o}.{weight,bias}",
+ * "encoder.{i}.mlp.conv_{1,2}.*", "encoder.{i}.adaLN_modulation.2.*", "proj.*"; then st_finalize_weights. */
+int st_create_text_encoder(const st_dims* dims, int n_vocab, int device, st_handle** out);
+/* Replaces TextEncoder.forward(x, c, x_lengths) (:34-44): ids (B,T) int64, c (B,gin), x_lengths (B) int64 ->
+ * x_out (B, hidden, T), mu_out (B, n_mel, T), mask_out (B, T). */
+int st_text_encoder_forward(st_handle* h, const int64_t* ids, const float* c, const int64_t* x_lengths, float* x_out,
+                            float* mu_out, float* mask_out, int B, int T, void* stream);
+
 /* Number of kernels this library launched since the handle was created (bench.py gpu_launches). */
 int64_t st_launch_count(const st_handle* h);
 

@@ -61,6 +61,8 @@ struct Workspace {
 
 struct st_handle {
     st_dims d;
+    int kind = 0;                      // 0 = CFM estimator (Decoder), 1 = TextEncoder
+    int n_vocab = 0; float* emb = nullptr;
     int device = 0, engine = ST_ENGINE_TCGEN05, num_sms = 148;
     std::string err;
     std::map<std::string, std::pair<float*, int64_t>> raw;   // name -> (device copy, numel)
@@ -332,6 +334,64 @@ int precompute_film(st_handle* h, Workspace& w, int n_t, cudaStream_t s) {
     return 0;
 }
 
+// One adaLN-Zero DiT block on the residual stream X[xb] (models/diffusion_transformer.py:98-117) after the
+// caller prepared `ln` for the first LayerNorm (plain, or FiLM·mask fused): LN1+modulate -> QKV (+RoPE)
+// -> masked attention -> O·gate + residual -> LN2+modulate·mask -> conv_1+SiLU·mask -> conv_2·mask·gate + residual.
+int dit_block_core(st_handle* h, Workspace& w, int l, LnArgs ln, const float* ada_l, long ada_bs, int xb, const float* mask,
+                   cudaStream_t s) {
+    const st_dims& d = h->d;
+    const int H = d.hidden;
+    auto base = [&](int flags) {
+        GemmArgs g;
+        g.BB = w.BB; g.T = w.T; g.a_bmod = w.BB; g.B = w.B; g.mask = mask; g.flags = flags;
+        g.c_clamp = w.B; g.resid_clamp = w.BB - 1; g.film_H = H; g.rope_cs = w.rope_cs;
+        return g;
+    };
+    ln.shift = ada_l; ln.scale = ada_l + H;
+    ln.u_f32 = w.U.f32; ln.u_hi = w.U.hi; ln.u_lo = w.U.lo;
+    ST_LAUNCH_P(ST_PROF_LN, 0, (double)w.BB * w.T * H * (4 + (ln.has_film ? 4 : 0) + 4), s, launch_film_ln_mod(ln, s));
+    {   // q,k,v projections as one N=3H GEMM (models/diffusion_transformer.py:59-61)
+        // tcgen05 engine: partial RoPE + softmax scale fused in the epilogue, split-bf16 output
+        GemmArgs g = base(h->engine == ST_ENGINE_TCGEN05 ? (EPI_BIAS | EPI_ROPE) : EPI_BIAS);
+        g.rope_H = H;
+        if (run_gemm(h, g, h->qkv[l], &w.U, nullptr, w.QKV, s, ST_PROF_GEMM_QKV)) return 1;
+    }
+    {
+        AttnArgs a;
+        a.qkv = w.QKV.f32; a.qkv_hi = w.QKV.hi; a.qkv_lo = w.QKV.lo;
+        a.rope_cs = w.rope_cs; a.mask = mask; a.kvlen = w.kvlen; a.prefix = w.prefix;
+        a.out_f32 = w.AO.f32; a.out_hi = w.AO.hi; a.out_lo = w.AO.lo;
+        a.BB = w.BB; a.B = w.B; a.T = w.T; a.H = H; a.n_heads = d.n_heads;
+        if (h->engine == ST_ENGINE_TCGEN05) {
+            ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_tc(a, w.att, s));
+        } else {
+            ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_simt(a, s));
+        }
+    }
+    {   // x += gate_msa * conv_o(attn) * mask   (:65, :111)
+        GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
+        g.gate = ada_l + 2 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
+        Act out = w.X[xb]; out.hi = nullptr; out.lo = nullptr;
+        if (run_gemm(h, g, h->wo[l], &w.AO, nullptr, out, s, ST_PROF_GEMM_O)) return 1;
+    }
+    {   // LN2 + modulate, FFN input mask (:112, :26)
+        LnArgs l2 = ln;
+        l2.xin = w.X[xb].f32; l2.xout = nullptr; l2.has_film = 0; l2.mask_out = 1;
+        l2.shift = ada_l + 3 * H; l2.scale = ada_l + 4 * H;
+        ST_LAUNCH_P(ST_PROF_LN, 0, (double)w.BB * w.T * H * 8, s, launch_film_ln_mod(l2, s));
+    }
+    {   // conv_1 + SiLU, (h * mask) feeds conv_2 (:26-29)
+        GemmArgs g = base(EPI_BIAS | EPI_SILU | EPI_MASK);
+        if (run_gemm(h, g, h->c1[l], &w.U, nullptr, w.Hid, s, ST_PROF_GEMM_C1)) return 1;
+    }
+    {   // x += gate_mlp * (conv_2(h) * mask)   (:29-30, :112)
+        GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
+        g.gate = ada_l + 5 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
+        if (run_gemm(h, g, h->c2[l], &w.Hid, nullptr, w.X[xb], s, ST_PROF_GEMM_C2)) return 1;
+    }
+    return 0;
+}
+
 // ----- one estimator evaluation (models/estimator.py:120-137) ------------------------------------------
 // xin: (B, T, M) stage input (fp32 [+ split planes for the tensor engine]); writes w.V (BB, T, M).
 // film: table row for this eval, (L, 2H); film_bstride != 0 when t is per-sample.
@@ -374,48 +434,7 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
             if (run_gemm(h, g, h->lsc[l - n_lsc], &w.X[cur], &w.X[sk], out, s, ST_PROF_GEMM_LSC)) return 1;
             ln.xin = w.X[xb].f32; ln.has_film = 0;
         }
-        ln.shift = ada_l; ln.scale = ada_l + H;
-        ln.u_f32 = w.U.f32; ln.u_hi = w.U.hi; ln.u_lo = w.U.lo;
-        ST_LAUNCH_P(ST_PROF_LN, 0, (double)w.BB * w.T * H * (4 + (ln.has_film ? 4 : 0) + 4), s, launch_film_ln_mod(ln, s));
-        {   // q,k,v projections as one N=3H GEMM (models/diffusion_transformer.py:59-61)
-            // tcgen05 engine: partial RoPE + softmax scale fused in the epilogue, split-bf16 output
-            GemmArgs g = base(h->engine == ST_ENGINE_TCGEN05 ? (EPI_BIAS | EPI_ROPE) : EPI_BIAS);
-            g.rope_H = H;
-            if (run_gemm(h, g, h->qkv[l], &w.U, nullptr, w.QKV, s, ST_PROF_GEMM_QKV)) return 1;
-        }
-        {
-            AttnArgs a;
-            a.qkv = w.QKV.f32; a.qkv_hi = w.QKV.hi; a.qkv_lo = w.QKV.lo;
-            a.rope_cs = w.rope_cs; a.mask = mask; a.kvlen = w.kvlen; a.prefix = w.prefix;
-            a.out_f32 = w.AO.f32; a.out_hi = w.AO.hi; a.out_lo = w.AO.lo;
-            a.BB = w.BB; a.B = w.B; a.T = w.T; a.H = H; a.n_heads = d.n_heads;
-            if (h->engine == ST_ENGINE_TCGEN05) {
-                ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_tc(a, w.att, s));
-            } else {
-                ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_simt(a, s));
-            }
-        }
-        {   // x += gate_msa * conv_o(attn) * mask   (:65, :111)
-            GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
-            g.gate = ada_l + 2 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
-            Act out = w.X[xb]; out.hi = nullptr; out.lo = nullptr;
-            if (run_gemm(h, g, h->wo[l], &w.AO, nullptr, out, s, ST_PROF_GEMM_O)) return 1;
-        }
-        {   // LN2 + modulate, FFN input mask (:112, :26)
-            LnArgs l2 = ln;
-            l2.xin = w.X[xb].f32; l2.xout = nullptr; l2.has_film = 0; l2.mask_out = 1;
-            l2.shift = ada_l + 3 * H; l2.scale = ada_l + 4 * H;
-            ST_LAUNCH_P(ST_PROF_LN, 0, (double)w.BB * w.T * H * 8, s, launch_film_ln_mod(l2, s));
-        }
-        {   // conv_1 + SiLU, (h * mask) feeds conv_2 (:26-29)
-            GemmArgs g = base(EPI_BIAS | EPI_SILU | EPI_MASK);
-            if (run_gemm(h, g, h->c1[l], &w.U, nullptr, w.Hid, s, ST_PROF_GEMM_C1)) return 1;
-        }
-        {   // x += gate_mlp * (conv_2(h) * mask)   (:29-30, :112)
-            GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
-            g.gate = ada_l + 5 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
-            if (run_gemm(h, g, h->c2[l], &w.Hid, nullptr, w.X[xb], s, ST_PROF_GEMM_C2)) return 1;
-        }
+        if (dit_block_core(h, w, l, ln, ada_l, ada_bs, xb, mask, s)) return 1;
         cur = xb;
     }
     {   // final_proj(x * mask) * mask (:136-137); x is already masked at this point
@@ -487,6 +506,18 @@ int st_create(const st_dims* dims, int device, st_handle** out) {
     h = new st_handle();
     h->d = *dims; h->device = device; h->num_sms = p.multiProcessorCount;
     *out = h;
+    return 0;
+}
+
+int st_create_text_encoder(const st_dims* dims, int n_vocab, int device, st_handle** out) {
+    if (!dims || n_vocab <= 0) return fail(nullptr, "st_create_text_encoder: bad argument");
+    st_dims d = *dims;
+    const int layers = d.n_layers;
+    d.n_layers = (layers % 2) ? layers + 1 : layers;       // reuse the estimator's validation (even, <= 6)
+    if (layers <= 0 || layers > 6) return fail(nullptr, "n_layers must be in [1, 6]");
+    int rc = st_create(&d, device, out);
+    if (rc) return rc;
+    (*out)->kind = 1; (*out)->n_vocab = n_vocab; (*out)->d.n_layers = layers;
     return 0;
 }
 
@@ -565,6 +596,21 @@ int st_finalize_weights(st_handle* h, void* stream) {
     h->qkv.assign(L, GemmW()); h->wo.assign(L, GemmW()); h->c1.assign(L, GemmW()); h->c2.assign(L, GemmW());
     h->lsc.assign(L / 2, GemmW());
     h->film_w.assign(L, nullptr); h->film_b.assign(L, nullptr); h->ada_w.assign(L, nullptr); h->ada_b.assign(L, nullptr);
+    if (h->kind == 1) {                // TextEncoder (models/text_encoder.py:22-26): emb, n_layers DiTConVBlocks, proj
+        for (int l = 0; l < L; ++l) {
+            std::string p = "encoder." + std::to_string(l) + ".";
+            if (pack_gemm(h, &h->qkv[l], {p + "attn.conv_q", p + "attn.conv_k", p + "attn.conv_v"}, H, H, 1, 0, H, true, s)) return 1;
+            if (pack_gemm(h, &h->wo[l], {p + "attn.conv_o"}, H, H, 1, 0, H, true, s)) return 1;
+            if (pack_gemm(h, &h->c1[l], {p + "mlp.conv_1"}, F, H, k, 0, H, true, s)) return 1;
+            if (pack_gemm(h, &h->c2[l], {p + "mlp.conv_2"}, H, F, k, 0, F, true, s)) return 1;
+            if (get_raw(h, p + "adaLN_modulation.2.weight", (int64_t)6 * H * H, &h->ada_w[l])) return 1;
+            if (get_raw(h, p + "adaLN_modulation.2.bias", 6 * H, &h->ada_b[l])) return 1;
+        }
+        if (pack_gemm(h, &h->fin, {"proj"}, M, H, 1, 0, H, true, s)) return 1;
+        if (get_raw(h, "emb.weight", (int64_t)h->n_vocab * H, &h->emb)) return 1;
+        h->finalized = true;
+        return 0;
+    }
     if (pack_gemm(h, &h->cond0, {"cond_proj.0"}, F, M, k, 0, M, true, s)) return 1;
     if (pack_gemm(h, &h->cond2, {"cond_proj.2"}, F, F, k, 0, F, true, s)) return 1;
     if (pack_gemm(h, &h->cond4, {"cond_proj.4"}, H, F, k, 0, F, true, s)) return 1;
@@ -611,6 +657,7 @@ int st_attach_workspace(st_handle* h, void* dev_ptr, size_t bytes) {
 int st_estimator_forward(st_handle* h, const float* t, int t_count, const float* x, const float* mask, const float* mu,
                          const float* c, float* out, int B, int T, void* stream) {
     if (check_common(h, B, T)) return 1;
+    if (h->kind != 0) return fail(h, "handle is not a CFM estimator");
     if (!t || !x || !mask || !mu || !c || !out) return fail(h, "st_estimator_forward: null pointer");
     if (t_count != 1 && t_count != B) return fail(h, "t must have 1 or B elements (models/estimator.py:107)");
     cudaStream_t s = (cudaStream_t)stream;
@@ -685,10 +732,46 @@ static int solve_impl(st_handle* h, Workspace& w, float* z_inout, const float* m
     return 0;
 }
 
+// models/text_encoder.py:34-44: emb(x)*sqrt(H) -> n_layers DiTConVBlocks(x, c, x_mask) -> proj(x)*x_mask
+int st_text_encoder_forward(st_handle* h, const int64_t* ids, const float* c, const int64_t* x_lengths, float* x_out,
+                            float* mu_out, float* mask_out, int B, int T, void* stream) {
+    if (check_common(h, B, T)) return 1;
+    if (h->kind != 1) return fail(h, "handle is not a text encoder");
+    if (!ids || !c || !x_lengths || !x_out || !mu_out || !mask_out) return fail(h, "st_text_encoder_forward: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    Workspace w;
+    if (ensure_ws(h, w, B, T, 0)) return 1;
+    const st_dims& d = h->d;
+    const int H = d.hidden, L = d.n_layers;
+    const long ada_bs = (long)L * 6 * H;
+    // x_mask = sequence_mask(x_lengths) (:37) and the masked, scaled embedding (:35; DiTConVBlock masks its input, :106)
+    ST_LAUNCH(launch_embed(ids, x_lengths, h->emb, h->n_vocab, B, T, H, sqrtf((float)H), w.X[0].f32, mask_out, s));
+    ST_LAUNCH(launch_mask_lengths(mask_out, w.kvlen, w.prefix, B, T, s));
+    ST_LAUNCH(launch_rope_table(w.rope_cs, T, 32, s));
+    for (int l = 0; l < L; ++l)        // adaLN(c) for every layer: (B, L, 6H)
+        ST_LAUNCH(launch_gemv(c, h->ada_w[l], h->ada_b[l], w.ada + (size_t)l * 6 * H, ada_bs, B, d.gin, 6 * H, 1, 0, s));
+    for (int l = 0; l < L; ++l) {
+        LnArgs ln;
+        ln.BB = w.BB; ln.T = w.T; ln.H = H; ln.mask = mask_out; ln.B = w.B; ln.c_clamp = w.B; ln.ada_bstride = ada_bs;
+        ln.xin = w.X[0].f32; ln.has_film = 0;
+        if (dit_block_core(h, w, l, ln, w.ada + (size_t)l * 6 * H, ada_bs, 0, mask_out, s)) return 1;
+    }
+    {   // mu_x = proj(x) * x_mask (:42)
+        GemmArgs g;
+        g.BB = w.BB; g.T = w.T; g.a_bmod = w.BB; g.B = w.B; g.mask = mask_out; g.flags = EPI_BIAS | EPI_MASK;
+        g.c_clamp = w.B; g.resid_clamp = w.BB - 1;
+        if (run_gemm(h, g, h->fin, &w.X[0], nullptr, w.V, s)) return 1;
+    }
+    ST_LAUNCH(launch_btc_to_bct(w.X[0].f32, x_out, B, H, T, s));
+    ST_LAUNCH(launch_btc_to_bct(w.V.f32, mu_out, B, d.n_mel, T, s));
+    return 0;
+}
+
 int st_solve(st_handle* h, float* z_inout, const float* mu, const float* mask, const float* c, const float* fake_content,
              const float* fake_speaker, float cfg_strength, const float* t_span_host, int n_steps, int method, int B, int T,
              void* stream) {
     if (check_common(h, B, T)) return 1;
+    if (h->kind != 0) return fail(h, "handle is not a CFM estimator");
     if (!z_inout || !mu || !mask || !c || !t_span_host) return fail(h, "st_solve: null pointer");
     if (n_steps <= 0) return fail(h, "n_timesteps must be positive");
     if (method < ST_EULER || method > ST_DOPRI5_FIXED) return fail(h, "unknown ODE method");

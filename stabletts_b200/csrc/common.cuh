@@ -102,6 +102,9 @@ cudaError_t launch_cfg_combine(const float* V, float* K_out, int B, long per_bat
 // dst = y + sum_i coef[i] * K[i]   (n <= 6)
 cudaError_t launch_lincomb(float* dst, const float* y, const float* const* K, const float* coef, int n, long numel,
                            cudaStream_t s);
+// TextEncoder front end: x (B,T,H) = emb[ids] * scale * mask, mask (B,T) = t < lens[b]
+cudaError_t launch_embed(const int64_t* ids, const int64_t* lens, const float* emb, int n_vocab, int B, int T, int H, float scale,
+                         float* x, float* mask, cudaStream_t s);
 // fp32 -> split bf16 planes
 cudaError_t launch_split(const float* in, bf16* hi, bf16* lo, long numel, cudaStream_t s);
 

@@ -264,6 +264,25 @@ cudaError_t launch_mask_lengths(const float* mask, int* kvlen, int* prefix, int 
     return launch_k(mask_lengths_kernel, dim3(B), dim3(256), 0, s, mask, kvlen, prefix, B, T);
 }
 
+// TextEncoder front end (models/text_encoder.py:35-37): x = emb[id] * sqrt(H) * mask, mask = t < x_lengths[b]
+__global__ void embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ lens, const float* __restrict__ emb,
+                             int n_vocab, int B, int T, int H, float scale, float* __restrict__ x, float* __restrict__ mask) {
+    pdl_trigger(); pdl_wait();
+    const long row = blockIdx.x;                 // (b, t)
+    const int b = (int)(row / T), t = (int)(row % T);
+    const float m = t < lens[b] ? 1.f : 0.f;
+    long id = ids[row];
+    id = id < 0 ? 0 : (id >= n_vocab ? n_vocab - 1 : id);
+    for (int c = threadIdx.x; c < H; c += blockDim.x) x[row * H + c] = emb[id * H + c] * scale * m;
+    if (threadIdx.x == 0) mask[row] = m;
+}
+
+cudaError_t launch_embed(const int64_t* ids, const int64_t* lens, const float* emb, int n_vocab, int B, int T, int H, float scale,
+                         float* x, float* mask, cudaStream_t s) {
+    if ((long)B * T == 0) return cudaSuccess;
+    return launch_k(embed_kernel, dim3((unsigned)((long)B * T)), dim3(64), 0, s, ids, lens, emb, n_vocab, B, T, H, scale, x, mask);
+}
+
 __global__ void cfg_combine_kernel(const float* __restrict__ V, float* __restrict__ K, long n, int cfg, float s_cfg) {
     pdl_trigger(); pdl_wait();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

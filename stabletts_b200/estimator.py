@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from ._native import NativeModule
 
 
 def _param_shapes(n_mel, hidden, filt, n_layers, kernel, gin) -> "OrderedDict[str, Tuple[int, ...]]":
@@ -52,11 +53,7 @@ def _param_shapes(n_mel, hidden, filt, n_layers, kernel, gin) -> "OrderedDict[st
     return s
 
 
-class _Node(nn.Module):
-    """Anonymous container: exists only so parameter paths equal the reference's module tree."""
-
-
-class Decoder(nn.Module):
+class Decoder(NativeModule):
     def __init__(self, noise_channels, cond_channels, hidden_channels, out_channels, filter_channels, dropout=0.1,
                  n_layers=1, n_heads=4, kernel_size=3, gin_channels=0, use_lsc=True):
         super().__init__()
@@ -78,30 +75,15 @@ class Decoder(nn.Module):
         for name, shape in self._shapes.items():
             self._register(name, nn.Parameter(torch.empty(shape)))
         self.initialize_weights()
-        # library state (not part of the module state)
-        self._handle = None
-        self._handle_device = None
-        self._synced: Dict[str, Tuple[int, int]] = {}
-        self._workspace = None
-        # debugging switch between the two CUDA GEMM engines (not a backend dispatch; both are this library)
-        self._engine = _lib.ST_ENGINE_SIMT if os.environ.get("STABLETTS_B200_ENGINE") == "simt" else _lib.ST_ENGINE_TCGEN05
+        self._init_native()                # library state (not part of the module state)
 
-    # -- module tree ------------------------------------------------------------------------------
-    def _register(self, dotted: str, p: nn.Parameter) -> None:
-        mod = self
-        parts = dotted.split(".")
-        for part in parts[:-1]:
-            if part not in mod._modules:
-                mod.add_module(part, _Node())
-            mod = mod._modules[part]
-        mod.register_parameter(parts[-1], p)
+    def _create_handle(self, lib, index):
+        dims = _lib.StDims(self.noise_channels, self.hidden_channels, self.filter_channels, self.n_heads,
+                           self.n_layers, self.kernel_size, self.gin_channels)
+        h = C.c_void_p()
+        _lib.check(lib, None, lib.st_create(C.byref(dims), index, C.byref(h)), "st_create")
+        return h
 
-    def _param(self, dotted: str) -> nn.Parameter:
-        mod = self
-        parts = dotted.split(".")
-        for part in parts[:-1]:
-            mod = mod._modules[part]
-        return mod._parameters[parts[-1]]
 
     def initialize_weights(self):
         """PyTorch default Conv1d/Linear init (U(±1/sqrt(fan_in)) for weight and bias), xavier on the
@@ -122,86 +104,6 @@ class Decoder(nn.Module):
                     bound = 1.0 / math.sqrt(fan_in)
                     p.uniform_(-bound, bound)
 
-    # -- library plumbing -------------------------------------------------------------------------
-    def set_engine(self, name: str) -> None:
-        """'tcgen05' (default product path) or 'simt' (fp32 cross-check engine) — both CUDA."""
-        self._engine = {"tcgen05": _lib.ST_ENGINE_TCGEN05, "simt": _lib.ST_ENGINE_SIMT}[name]
-        if self._handle is not None:
-            lib = _lib.load_library()
-            _lib.check(lib, self._handle, lib.st_set_engine(self._handle, self._engine), "st_set_engine")
-
-    def _ensure_handle(self, device: torch.device):
-        lib = _lib.load_library()
-        if device.type != "cuda":
-            raise RuntimeError("stabletts_b200 runs on CUDA (B200) only: there is no CPU fallback")
-        index = device.index if device.index is not None else torch.cuda.current_device()
-        if self._handle is not None and self._handle_device != index:
-            self.release()
-        if self._handle is None:
-            dims = _lib.StDims(self.noise_channels, self.hidden_channels, self.filter_channels, self.n_heads,
-                               self.n_layers, self.kernel_size, self.gin_channels)
-            h = C.c_void_p()
-            rc = lib.st_create(C.byref(dims), index, C.byref(h))
-            _lib.check(lib, None, rc, "st_create")
-            self._handle, self._handle_device = h, index
-            self._synced.clear()
-            _lib.check(lib, h, lib.st_set_engine(h, self._engine), "st_set_engine")
-        return lib, self._handle
-
-    def _sync_weights(self, lib, h, stream: int) -> None:
-        dirty = False
-        for name in self._shapes:
-            p = self._param(name)
-            if p.device.type != "cuda" or p.dtype != torch.float32:
-                raise RuntimeError(f"parameter {name} must be CUDA fp32 (got {p.device}, {p.dtype}); call .to('cuda')")
-            tag = (p.data_ptr(), p._version)
-            if self._synced.get(name) != tag:
-                pc = p.detach().contiguous()
-                _lib.check(lib, h, lib.st_load_weight(h, name.encode(), pc.data_ptr(), pc.numel(), stream),
-                           f"st_load_weight({name})")
-                self._synced[name] = tag
-                dirty = True
-        if dirty:
-            _lib.check(lib, h, lib.st_finalize_weights(h, stream), "st_finalize_weights")
-
-    def _ensure_workspace(self, lib, h, B: int, T: int, cfg: int, device) -> None:
-        need = lib.st_workspace_bytes(h, B, T, cfg)
-        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != device:
-            self._workspace = None
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
-            _lib.check(lib, h, lib.st_attach_workspace(h, self._workspace.data_ptr(), self._workspace.numel()),
-                       "st_attach_workspace")
-
-    def _prepare(self, ref: torch.Tensor, B: int, T: int, cfg: int):
-        lib, h = self._ensure_handle(ref.device)
-        stream = torch.cuda.current_stream(ref.device).cuda_stream
-        self._sync_weights(lib, h, stream)
-        self._ensure_workspace(lib, h, B, T, cfg, ref.device)
-        return lib, h, stream
-
-    def release(self) -> None:
-        if self._handle is not None:
-            _lib.load_library().st_destroy(self._handle)
-        self._handle = None
-        self._workspace = None
-        self._synced.clear()
-
-    def __del__(self):
-        try:
-            self.release()
-        except Exception:
-            pass
-
-    def launch_count(self) -> int:
-        return 0 if self._handle is None else int(_lib.load_library().st_launch_count(self._handle))
-
-    @staticmethod
-    def _f32c(name: str, t: torch.Tensor, shape) -> torch.Tensor:
-        if not isinstance(t, torch.Tensor) or t.device.type != "cuda":
-            raise RuntimeError(f"{name} must be a CUDA tensor (no CPU fallback)")
-        if tuple(t.shape) != tuple(shape):
-            raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
-        return t.detach().to(torch.float32).contiguous()
 
     # -- the reference's forward ------------------------------------------------------------------
     @torch.no_grad()
