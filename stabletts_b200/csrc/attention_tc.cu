@@ -291,7 +291,7 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
 #pragma unroll 1
             for (int attempt = 0; attempt < 2; ++attempt) {
                 const float m_eff = (m_used == -CUDART_INF_F) ? 0.f : m_used;
-                cand = -CUDART_INF_F; psum = 0.f;
+                float c0 = -CUDART_INF_F, c1 = -CUDART_INF_F, ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;   // short dependency chains
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     tmem_ld32(tS + half * 32, v);
@@ -302,14 +302,18 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
                         for (int i = 0; i < 32; ++i) if (!((bits >> i) & 1u)) v[i] = 0xff800000u;     // -inf
                     }
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
+                    for (int i = 0; i < 32; i += 4) {
                         const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-                        cand = fmaxf(cand, fmaxf(s0, s1));
+                        const float s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
+                        c0 = fmaxf(c0, fmaxf(s0, s1)); c1 = fmaxf(c1, fmaxf(s2, s3));
                         const float p0 = ex2_approx(s0 - m_eff), p1 = ex2_approx(s1 - m_eff);
-                        psum += p0 + p1;
+                        const float p2 = ex2_approx(s2 - m_eff), p3 = ex2_approx(s3 - m_eff);
+                        ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
                         split_bf16x2(p0, p1, hw[half * 16 + i / 2], lw[half * 16 + i / 2]);
+                        split_bf16x2(p2, p3, hw[half * 16 + i / 2 + 1], lw[half * 16 + i / 2 + 1]);
                     }
                 }
+                cand = fmaxf(c0, c1); psum = (ps0 + ps1) + (ps2 + ps3);
                 if (attempt == 1 || !__any_sync(0xffffffffu, cand > m_used + LAZY_THRESHOLD)) break;
                 const float m_new = fmaxf(m_used, cand);
                 const float factor = (m_new == -CUDART_INF_F) ? 1.f : ex2_approx(m_used - m_new);    // m_used = -inf -> 0

@@ -52,6 +52,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, int bb, int t0,
     const float* gate = p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride;
     const float* resid = p.resid + (long)min(bb, p.resid_clamp) * p.T * p.N;
     const long obase = (long)bb * p.T * p.N;
+    const bool plain = (p.flags & (EPI_FILM | EPI_MASK | EPI_GATE | EPI_RESID)) == 0;
 
 #pragma unroll 1
     for (int c0 = eh * 32; c0 < BN; c0 += 64) {
@@ -115,11 +116,15 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, int bb, int t0,
                     x[3] = x[3] * cs1.z + sgn * (pv.w + bp4.w) * cs1.w;
                 }
                 if (t >= p.T || !col_ok) continue;
-                const float m = hf ? mrow[4 + i] : mrow[i];      // static indices: mrow stays in registers
-                x[0] = (fg.x * x[0] * post + fb.x) * m * g4.x + rv[i].x;
-                x[1] = (fg.y * x[1] * post + fb.y) * m * g4.y + rv[i].y;
-                x[2] = (fg.z * x[2] * post + fb.z) * m * g4.z + rv[i].z;
-                x[3] = (fg.w * x[3] * post + fb.w) * m * g4.w + rv[i].w;
+                if (plain) {                   // bias / SiLU / RoPE only (QKV, cond_proj): skip the neutral FiLM·mask·gate+resid chain
+                    x[0] *= post; x[1] *= post; x[2] *= post; x[3] *= post;
+                } else {
+                    const float m = hf ? mrow[4 + i] : mrow[i];      // static indices: mrow stays in registers
+                    x[0] = (fg.x * x[0] + fb.x) * m * g4.x + rv[i].x;
+                    x[1] = (fg.y * x[1] + fb.y) * m * g4.y + rv[i].y;
+                    x[2] = (fg.z * x[2] + fb.z) * m * g4.z + rv[i].z;
+                    x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[i].w;
+                }
                 const long o = obase + (long)t * p.N + n;
                 if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
                 if (p.out_hi) {
