@@ -183,3 +183,36 @@ def test_graph_replay_and_host_entry(dev, golden_dir):
                            C.c_float(cs["cfg"]), tspan, cs["steps"], _lib.ST_EULER, B, T, torch.cuda.current_stream().cuda_stream)
     _lib.check(lib, h, rc, "st_solve_host")
     assert rel_errs(zh, outs[0])[0] < 1e-6
+
+
+def test_general_binary_mask_and_weight_update(dev):
+    """(a) a NON-prefix 0/1 mask (holes inside the utterance): keys with mask 0 are excluded, rows with mask 0
+    are exact zeros — the reference supports it through its mask products and so must the kernels;
+    (b) an in-place parameter update is picked up (the packed copy is refreshed from the version counter)."""
+    st = weights.make_state(cases.WEIGHT_SEED, 80)
+    m = model_for(80, "tcgen05", dev)
+    inp = weights.make_inputs(123, [200, 150], 200)
+    mask = inp["mask"].clone()
+    mask[0, 0, 37:49] = 0.0
+    mask[0, 0, 130] = 0.0
+    mask[1, 0, 0:5] = 0.0                                   # hole at the very start: key 0 is NOT valid
+    mu = inp["mu"] * mask
+    with torch.inference_mode():
+        ref = R.estimator_forward(st, inp["t"], inp["x"], mask, mu, inp["c"])
+    out = m.estimator(inp["t"].to(dev), inp["x"].to(dev), mask.to(dev), mu.to(dev), inp["c"].to(dev))
+    e = rel_errs(out, ref)
+    assert max(e) < 1e-3, e
+    assert float((out.cpu() * (1 - mask)).abs().max()) == 0.0
+    # (b) weight update
+    from stabletts_b200 import CFMDecoder
+    m2 = CFMDecoder(80, 80, 256, 80, 1024, 4, 6, 3, 0.1, 256).eval()
+    m2.estimator.load_state_dict(st, strict=True)
+    m2 = m2.to(dev)
+    small = weights.make_inputs(5, [40], 40)
+    args = [small[k].to(dev) for k in ("t", "x", "mask", "mu", "c")]
+    a = m2.estimator(*args)
+    with torch.no_grad():
+        m2.estimator.final_proj.weight.mul_(2.0)
+        m2.estimator.final_proj.bias.mul_(2.0)
+    b = m2.estimator(*args)
+    assert rel_errs(b, 2.0 * a)[0] < 1e-5
