@@ -96,6 +96,14 @@ int st_solve(st_handle* h, float* z_inout, const float* mu, const float* mask, c
              const float* fake_content, const float* fake_speaker, float cfg_strength,
              const float* t_span_host, int n_steps, int method, int B, int T, void* stream);
 
+/* Replaces the reference's DEFAULT solver: `odeint(..., method=None)` = torchdiffeq's adaptive dopri5 with
+ * rtol = atol = 1e-5 (models/flow_matching.py:54).  torchdiffeq is absent/unpinned: this follows its published
+ * algorithm (see oracle/adaptive_ref.py; parity unpinned).  One 8-byte host read per step (accept/reject), as
+ * torchdiffeq itself does on a GPU.  stats (host, may be NULL): [accepted steps, rejected steps, NFE]. */
+int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float* mask, const float* c,
+                      const float* fake_content, const float* fake_speaker, float cfg_strength, double t_start,
+                      double t_end, double rtol, double atol, int max_steps, int B, int T, void* stream, int64_t* stats);
+
 /* Same as st_solve with HOST buffers: copies inputs host->device and the sample device->host on
  * `stream` and synchronises it before returning (the end-to-end form bench.py's `e2e` times). */
 int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const float* mask_host,

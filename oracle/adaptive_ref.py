@@ -1,0 +1,101 @@
+"""CPU oracle for the ADAPTIVE Dormand–Prince 5(4) solver (TEST INFRASTRUCTURE ONLY).
+
+The reference's default ``solver=None`` means ``torchdiffeq.odeint(..., method='dopri5', rtol=1e-5,
+atol=1e-5)`` (models/flow_matching.py:54).  torchdiffeq is a third-party package, unpinned in the
+reference's requirements.txt:14 and ABSENT here, so this file restates its published algorithm
+(Dormand & Prince 1980 tableau with Shampine's embedded 4th-order weights and dense-output midpoint
+coefficients; Hairer's initial-step heuristic; I-controller with safety 0.9, ifactor 10, dfactor 0.2;
+RMS mixed error norm over ALL elements; evaluation at the requested times by a 4th-order interpolant).
+PARITY UNPINNED: nothing in the reference pins these semantics; the CUDA driver is tested against THIS
+restatement only.
+"""
+from __future__ import annotations
+
+import torch
+
+# Butcher tableau (7 stages, FSAL)
+ALPHA = [1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0]
+BETA = [
+    [1 / 5],
+    [3 / 40, 9 / 40],
+    [44 / 45, -56 / 15, 32 / 9],
+    [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+    [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+    [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
+]
+C_SOL = [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0]
+C_ERROR = [35 / 384 - 1951 / 21600, 0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+           -2187 / 6784 - -12231 / 42400, 11 / 84 - 649 / 6300, -1. / 60.]
+C_MID = [6025192743 / 30085553152 / 2, 0, 51252292925 / 65400821598 / 2, -2691868925 / 45128329728 / 2,
+         187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2]
+SAFETY, IFACTOR, DFACTOR, ORDER = 0.9, 10.0, 0.2, 5
+
+
+def rms_norm(x: torch.Tensor) -> float:
+    return float(x.double().pow(2).mean().sqrt())
+
+
+def select_initial_step(f, t0: float, y0, f0, rtol, atol) -> float:
+    scale = atol + y0.abs() * rtol
+    d0, d1 = rms_norm(y0 / scale), rms_norm(f0 / scale)
+    h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    y1 = y0 + h0 * f0
+    f1 = f(torch.tensor(t0 + h0, dtype=torch.float32), y1)
+    d2 = rms_norm((f1 - f0) / scale) / h0
+    if d1 <= 1e-15 and d2 <= 1e-15:
+        h1 = max(1e-6, h0 * 1e-3)
+    else:
+        h1 = (0.01 / max(d1, d2)) ** (1.0 / ORDER)
+    return min(100 * h0, h1)
+
+
+def odeint_dopri5(f, y0: torch.Tensor, t_end: float = 1.0, rtol: float = 1e-5, atol: float = 1e-5, max_steps: int = 1000):
+    """Integrates dy/dt = f(t, y) from 0 and returns (y(t_end), stats).  Time is carried in float64 (as
+    torchdiffeq does), the state in float32; f receives t as a 0-dim float32 tensor."""
+    t0 = 0.0
+    f0 = f(torch.tensor(t0, dtype=torch.float32), y0)
+    dt = select_initial_step(f, t0, y0, f0, rtol, atol)
+    n_acc = n_rej = 0
+    y = y0
+    interp = None
+    while True:
+        if n_acc + n_rej >= max_steps:
+            raise RuntimeError("max_steps exceeded")
+        t1 = t0 + dt
+        k = [f0]
+        for i in range(6):
+            yi = y
+            for j, b in enumerate(BETA[i]):
+                if b != 0:
+                    yi = yi + (dt * b) * k[j]
+            ti = t1 if ALPHA[i] == 1.0 else t0 + ALPHA[i] * dt
+            k.append(f(torch.tensor(ti, dtype=torch.float32), yi))
+            if i == 5:
+                y1 = yi                                       # last stage input is the 5th-order solution (FSAL)
+        err = sum((dt * c) * kk for c, kk in zip(C_ERROR, k) if c != 0)
+        tol = atol + rtol * torch.max(y.abs(), y1.abs())
+        ratio = rms_norm(err / tol)
+        accept = ratio <= 1.0
+        if ratio == 0:
+            factor = IFACTOR
+        else:
+            dfac = 1.0 if ratio < 1 else DFACTOR
+            factor = min(IFACTOR, max(SAFETY / ratio ** (1.0 / ORDER), dfac))
+        if accept:
+            n_acc += 1
+            y_mid = y + sum((dt * c) * kk for c, kk in zip(C_MID, k) if c != 0)
+            interp = (y, y1, y_mid, k[0], k[6], dt, t0, t1)
+            y, f0, t0 = y1, k[6], t1
+        else:
+            n_rej += 1
+        dt = dt * factor
+        if accept and t0 >= t_end:
+            break
+    ya, yb, ym, fa, fb, h, ta, tb = interp
+    a = 2 * h * (fb - fa) - 8 * (yb + ya) + 16 * ym
+    b = h * (5 * fa - 3 * fb) + 18 * ya + 14 * yb - 32 * ym
+    c = h * (fb - 4 * fa) - 11 * ya - 5 * yb + 16 * ym
+    d = h * fa
+    x = (t_end - ta) / (tb - ta)
+    out = ya + x * (d + x * (c + x * (b + x * a)))
+    return out, dict(accepted=n_acc, rejected=n_rej, nfe=2 + 6 * (n_acc + n_rej))

@@ -47,7 +47,8 @@ constexpr int MAX_EVAL_TABLE = 1024;
 struct Workspace {
     int B = 0, T = 0, cfg = 0, BB = 0, Bc = 0, NT = 0;
     Act xt, ytmp, xs, V, mut, C1, C2, C3, P, X[5], U, QKV, AO, Hid;
-    float* Kst[6] = {};
+    float* Kst[10] = {};               // RK stage derivatives (+ spare state buffers for the adaptive solver)
+    double* dscal = nullptr;           // device scalar for norm reductions
     int* kvlen = nullptr; int* prefix = nullptr;
     AttnTcScratch att;
     float *rope_cs = nullptr, *temb = nullptr, *tmid = nullptr, *tvec = nullptr, *film = nullptr, *ada = nullptr;
@@ -78,6 +79,7 @@ struct st_handle {
     struct GraphEntry { std::string key; cudaGraphExec_t exec; int64_t launches; };
     std::vector<GraphEntry> graphs;
     std::vector<std::string> graph_seen;   // keys enqueued directly once (kernels loaded, attributes set) before capture
+    double* pinned = nullptr;          // 16 B of pinned host memory: norm read-back of the adaptive controller
     cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the caller's may be the legacy stream)
     int graph_mode = -1;               // -1: read STABLETTS_B200_GRAPH on first use; 0 off; 1 always; 2 auto (small problems)
     void drop_graphs() { for (auto& g : graphs) cudaGraphExecDestroy(g.exec); graphs.clear(); }
@@ -215,7 +217,8 @@ void layout_ws(const st_handle* h, Workspace& w, void* base, size_t cap, int B, 
     mk(w.ytmp, bt, d.n_mel, true, false);
     mk(w.xs, bt, d.n_mel, false, tc);
     mk(w.V, bbt, d.n_mel, true, false);
-    for (int i = 0; i < 6; ++i) w.Kst[i] = bp.take<float>(bt * d.n_mel);
+    for (int i = 0; i < 10; ++i) w.Kst[i] = bp.take<float>(bt * d.n_mel);
+    w.dscal = bp.take<double>(2);
     mk(w.mut, bct, d.n_mel, !tc, tc);
     mk(w.C1, bct, d.filter, !tc, tc);
     mk(w.C2, bct, d.filter, !tc, tc);
@@ -527,6 +530,7 @@ int st_destroy(st_handle* h) {
     cudaDeviceSynchronize();
     h->drop_graphs();
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->pinned) cudaFreeHost(h->pinned);
     for (auto& kv : h->raw) cudaFree(kv.second.first);
     for (void* p : h->owned) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -844,6 +848,146 @@ int st_solve(st_handle* h, float* z_inout, const float* mu, const float* mask, c
     ST_CUDA(cudaGraphLaunch(ge->exec, s));
     h->launches += ge->launches;
     if (z_inout != w.h_z) ST_CUDA(cudaMemcpyAsync(z_inout, w.h_z, n * 4, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// ---- adaptive Dormand–Prince 5(4): the reference's default solver (`solver=None` -> torchdiffeq dopri5,
+// models/flow_matching.py:54).  torchdiffeq is absent and unpinned, so this follows its PUBLISHED algorithm
+// (oracle/adaptive_ref.py restates the same and is what the tests compare against): FSAL 7-stage tableau,
+// Shampine's embedded error weights, RMS mixed error norm over all elements, I-controller (safety 0.9,
+// factor in [0.2, 10]), Hairer's initial step, evaluation at t_end through the 4th-order dense output.
+// Like torchdiffeq on a GPU, accept/reject needs ONE host-visible scalar per step (8 bytes, pinned).
+int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float* mask, const float* c,
+                      const float* fake_content, const float* fake_speaker, float cfg_strength, double t_start, double t_end,
+                      double rtol, double atol, int max_steps, int B, int T, void* stream, int64_t* stats) {
+    if (check_common(h, B, T)) return 1;
+    if (h->kind != 0) return fail(h, "handle is not a CFM estimator");
+    if (!z_inout || !mu || !mask || !c) return fail(h, "st_solve_adaptive: null pointer");
+    if (!(t_end > t_start) || rtol <= 0 || atol <= 0 || max_steps <= 0) return fail(h, "st_solve_adaptive: bad tolerances / interval");
+    const int cfg = (fake_content && fake_speaker) ? 1 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    Workspace w;
+    if (ensure_ws(h, w, B, T, cfg)) return 1;
+    if (!h->pinned) ST_CUDA(cudaMallocHost((void**)&h->pinned, 16));
+    const st_dims& d = h->d;
+    const long numel = (long)B * T * d.n_mel;
+    const long film_row = (long)d.n_layers * 2 * d.hidden;
+    static const double ALPHA[6] = {1. / 5, 3. / 10, 4. / 5, 8. / 9, 1.0, 1.0};
+    static const double BETA[6][6] = {{1. / 5}, {3. / 40, 9. / 40}, {44. / 45, -56. / 15, 32. / 9},
+                                      {19372. / 6561, -25360. / 2187, 64448. / 6561, -212. / 729},
+                                      {9017. / 3168, -355. / 33, 46732. / 5247, 49. / 176, -5103. / 18656},
+                                      {35. / 384, 0, 500. / 1113, 125. / 192, -2187. / 6784, 11. / 84}};
+    static const double CERR[7] = {35. / 384 - 1951. / 21600, 0, 500. / 1113 - 22642. / 50085, 125. / 192 - 451. / 720,
+                                   -2187. / 6784 + 12231. / 42400, 11. / 84 - 649. / 6300, -1. / 60};
+    static const double CMID[7] = {6025192743. / 30085553152. / 2, 0, 51252292925. / 65400821598. / 2, -2691868925. / 45128329728. / 2,
+                                   187940372067. / 1594534317056. / 2, -1776094331. / 19743644256. / 2, 11237099. / 235043384. / 2};
+    int64_t nfe = 0, n_acc = 0, n_rej = 0;
+
+    if (precompute_cond(h, w, mu, mask, c, fake_content, fake_speaker, s)) return 1;
+    // state buffers (token-major): y, y1 and 7 stage derivatives rotate through Kst[]
+    float* y = w.xt.f32; float* y1 = w.Kst[7]; float* ymid = w.Kst[8]; float* ysave = w.Kst[9];
+    float* k[7]; for (int i = 0; i < 7; ++i) k[i] = w.Kst[i];
+    ST_LAUNCH(launch_bct_to_btc(z_inout, y, nullptr, nullptr, B, d.n_mel, T, nullptr, s));
+
+    auto feval = [&](double t, const float* yin, float* kout) -> int {        // kout = f(t, yin) (CFG-combined)
+        TArr ta; ta.v[0] = (float)t;
+        h->launches++;
+        time_embed_val_kernel<<<(d.hidden / 2 + 127) / 128, 128, 0, s>>>(ta, 1, d.hidden, w.temb);
+        if (cudaGetLastError() != cudaSuccess) return fail(h, "time embedding launch failed");
+        if (precompute_film(h, w, 1, s)) return 1;
+        Act xin = w.xt; xin.f32 = const_cast<float*>(yin);
+        if (h->engine == ST_ENGINE_TCGEN05) {
+            if (launch_split(yin, w.xs.hi, w.xs.lo, numel, s) != cudaSuccess) return fail(h, "split failed");
+            h->launches++;
+            xin.hi = w.xs.hi; xin.lo = w.xs.lo;
+        }
+        if (estimator_eval(h, w, xin, mask, w.film, 0, s)) return 1;
+        if (launch_cfg_combine(w.V.f32, kout, B, (long)T * d.n_mel, cfg, cfg_strength, s) != cudaSuccess) return fail(h, "cfg combine failed");
+        h->launches++; ++nfe;
+        (void)film_row;
+        return 0;
+    };
+    auto norm = [&](const float* const* K, const float* coef, int n, const float* u, const float* v, double* out) -> int {
+        if (launch_scaled_sumsq(K, coef, n, u, v, (float)atol, (float)rtol, numel, w.dscal, s) != cudaSuccess) return fail(h, "norm launch failed");
+        h->launches++;
+        if (cudaMemcpyAsync(h->pinned, w.dscal, sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess) return fail(h, "norm read-back failed");
+        *out = std::sqrt(h->pinned[0] / (double)numel);
+        return 0;
+    };
+
+    double t0 = t_start;
+    if (feval(t0, y, k[0])) return 1;
+    double dt;
+    {   // Hairer's initial step (order 5 -> exponent 1/5)
+        double d0, d1, d2;
+        const float one = 1.f; const float* Ky[1] = {y}; const float* Kf[1] = {k[0]};
+        if (norm(Ky, &one, 1, y, y, &d0) || norm(Kf, &one, 1, y, y, &d1)) return 1;
+        const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        const float c1 = (float)h0; const float* K1[1] = {k[0]};
+        ST_LAUNCH(launch_lincomb(y1, y, K1, &c1, 1, numel, s));
+        if (feval(t0 + h0, y1, k[1])) return 1;
+        const float pm[2] = {1.f, -1.f}; const float* Kd[2] = {k[1], k[0]};
+        if (norm(Kd, pm, 2, y, y, &d2)) return 1;
+        d2 /= h0;
+        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? std::max(1e-6, h0 * 1e-3) : std::pow(0.01 / std::max(d1, d2), 1.0 / 5.0);
+        dt = std::min(100 * h0, h1);
+    }
+    double ia_t0 = t0, ia_t1 = t0, ia_dt = 0;      // interval of the last accepted step (dense output)
+    while (true) {
+        if (n_acc + n_rej >= max_steps) return fail(h, "st_solve_adaptive: max_steps exceeded");
+        const double t1 = t0 + dt;
+        for (int i = 0; i < 6; ++i) {
+            float coef[6]; const float* Ks[6]; int n = 0;
+            for (int j = 0; j <= i; ++j) if (BETA[i][j] != 0.0) { coef[n] = (float)(dt * BETA[i][j]); Ks[n] = k[j]; ++n; }
+            float* dst = (i == 5) ? y1 : w.ytmp.f32;          // the last stage input IS the 5th-order solution (FSAL)
+            ST_LAUNCH(launch_lincomb(dst, y, Ks, coef, n, numel, s));
+            if (feval(ALPHA[i] == 1.0 ? t1 : t0 + ALPHA[i] * dt, dst, k[i + 1])) return 1;
+        }
+        double ratio;
+        {
+            float coef[7]; const float* Ks[7]; int n = 0;
+            for (int j = 0; j < 7; ++j) if (CERR[j] != 0.0) { coef[n] = (float)(dt * CERR[j]); Ks[n] = k[j]; ++n; }
+            if (norm(Ks, coef, n, y, y1, &ratio)) return 1;
+        }
+        const bool accept = ratio <= 1.0;
+        double factor;
+        if (ratio == 0.0) factor = 10.0;
+        else factor = std::min(10.0, std::max(0.9 / std::pow(ratio, 1.0 / 5.0), ratio < 1.0 ? 1.0 : 0.2));
+        if (accept) {
+            ++n_acc;
+            {   // y_mid for the dense output
+                float coef[6]; const float* Ks[6]; int n = 0;
+                for (int j = 0; j < 7; ++j) if (CMID[j] != 0.0) { coef[n] = (float)(dt * CMID[j]); Ks[n] = k[j]; ++n; }
+                ST_LAUNCH(launch_lincomb(ymid, y, Ks, coef, n, numel, s));
+            }
+            // keep (y_a = y, y_b = y1, f_a = k0, f_b = k6) alive for the interpolant; advance by pointer rotation
+            ia_t0 = t0; ia_t1 = t1; ia_dt = dt;
+            std::swap(y, ysave);        // ysave now holds y_a ... (y pointer will be replaced below)
+            std::swap(y, y1);           // y = y_b (new state); y1 = old ysave buffer (free)
+            std::swap(k[0], k[6]);      // f0 <- f(t1, y1) (FSAL); k[6] now holds f_a
+            t0 = t1;
+        } else {
+            ++n_rej;
+        }
+        dt *= factor;
+        if (accept && t0 >= t_end) break;
+    }
+    {   // 4th-order dense output at t_end on the last accepted interval (y_a = ysave, y_b = y, f_a = k[6], f_b = k[0])
+        const double hh = ia_dt, x = (t_end - ia_t0) / (ia_t1 - ia_t0);
+        const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+        // out = ya + x d + x^2 c + x^3 b + x^4 a with a,b,c,d linear in (ya, yb, ym, fa, fb)
+        const double cya = 1.0 - 11 * x2 + 18 * x3 - 8 * x4;
+        const double cyb = -5 * x2 + 14 * x3 - 8 * x4;
+        const double cym = 16 * x2 - 32 * x3 + 16 * x4;
+        const double cfa = hh * (x - 4 * x2 + 5 * x3 - 2 * x4);
+        const double cfb = hh * (x2 - 3 * x3 + 2 * x4);
+        float coef[5] = {(float)(cya - 1.0), (float)cyb, (float)cym, (float)cfa, (float)cfb};
+        const float* Ks[5] = {ysave, y, ymid, k[6], k[0]};
+        ST_LAUNCH(launch_lincomb(w.ytmp.f32, ysave, Ks, coef, 5, numel, s));
+    }
+    ST_LAUNCH(launch_btc_to_bct(w.ytmp.f32, z_inout, B, d.n_mel, T, s));
+    if (stats) { stats[0] = n_acc; stats[1] = n_rej; stats[2] = nfe; }
     return 0;
 }
 

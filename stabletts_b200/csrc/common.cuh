@@ -105,6 +105,9 @@ cudaError_t launch_lincomb(float* dst, const float* y, const float* const* K, co
 // TextEncoder front end: x (B,T,H) = emb[ids] * scale * mask, mask (B,T) = t < lens[b]
 cudaError_t launch_embed(const int64_t* ids, const int64_t* lens, const float* emb, int n_vocab, int B, int T, int H, float scale,
                          float* x, float* mask, cudaStream_t s);
+// *out = sum_e ((sum_i coef_i K_i[e]) / (atol + rtol max(|u[e]|,|v[e]|)))^2   (n <= 7; out is zeroed first)
+cudaError_t launch_scaled_sumsq(const float* const* K, const float* coef, int n, const float* u, const float* v, float atol,
+                                float rtol, long numel, double* out, cudaStream_t s);
 // fp32 -> split bf16 planes
 cudaError_t launch_split(const float* in, bf16* hi, bf16* lo, long numel, cudaStream_t s);
 

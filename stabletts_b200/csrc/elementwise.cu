@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 namespace st {
 
@@ -318,6 +319,46 @@ cudaError_t launch_lincomb(float* dst, const float* y, const float* const* K, co
     for (int j = 0; j < 6; ++j) { a.K[j] = j < n ? K[j] : nullptr; a.coef[j] = j < n ? coef[j] : 0.f; }
     a.n = n;
     return launch_k(lincomb_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, s, dst, y, a, numel);
+}
+
+// sum over all elements of ( (sum_i coef_i * K_i[e]) / (atol + rtol * max(|u[e]|, |v[e]|)) )^2  -> *out (double, atomic)
+// (the RMS mixed error norm of the adaptive Dormand–Prince controller; also Hairer's initial-step norms)
+struct NormArgs { const float* K[7]; float coef[7]; int n; };
+
+__global__ void scaled_sumsq_kernel(NormArgs a, const float* __restrict__ u, const float* __restrict__ v, float atol, float rtol,
+                                    long numel, double* __restrict__ out) {
+    pdl_trigger(); pdl_wait();
+    double acc = 0.0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (long)gridDim.x * blockDim.x) {
+        float num = 0.f;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) if (j < a.n) num = fmaf(a.coef[j], a.K[j][i], num);
+        const float tol = atol + rtol * fmaxf(fabsf(u[i]), fabsf(v[i]));
+        const float r = num / tol;
+        acc += (double)r * (double)r;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        atomicAdd(out, t);
+    }
+}
+
+cudaError_t launch_scaled_sumsq(const float* const* K, const float* coef, int n, const float* u, const float* v, float atol,
+                                float rtol, long numel, double* out, cudaStream_t s) {
+    if (n > 7) return cudaErrorInvalidValue;
+    NormArgs a;
+    for (int j = 0; j < 7; ++j) { a.K[j] = j < n ? K[j] : nullptr; a.coef[j] = j < n ? coef[j] : 0.f; }
+    a.n = n;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    const int blocks = (int)std::min<long>((numel + 255) / 256, 592);
+    return launch_k(scaled_sumsq_kernel, dim3(blocks > 0 ? blocks : 1), dim3(256), 0, s, a, u, v, atol, rtol, numel, out);
 }
 
 __global__ void split_kernel(const float* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo, long n) {

@@ -1,0 +1,53 @@
+"""Adaptive Dormand–Prince (the reference's default solver).  torchdiffeq is absent: the oracle restates its
+published algorithm and is itself sanity-checked on an ODE with a closed-form solution (CPU); the CUDA driver
+is compared against the oracle on the estimator's vector field (GPU).  Parity with torchdiffeq: UNPINNED."""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_errs
+from oracle import adaptive_ref as AD
+from oracle import estimator_ref as R
+from oracle import cases, weights
+
+
+def test_oracle_on_closed_form_ode():
+    f = lambda t, y: -y + torch.sin(3 * t)
+    out, stats = AD.odeint_dopri5(f, torch.ones(3), 1.0, 1e-7, 1e-7)
+    exact = math.exp(-1) * 1.3 + (math.sin(3) - 3 * math.cos(3)) / 10
+    assert abs(float(out[0]) - exact) < 5e-6
+    assert stats["accepted"] >= 3 and stats["nfe"] == 2 + 6 * (stats["accepted"] + stats["rejected"])
+
+
+@pytest.mark.gpu
+def test_cuda_adaptive_vs_oracle():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as ge
+    ge.build()
+    from stabletts_b200 import CFMDecoder
+    dev = torch.device("cuda:0")
+    n_mel = 80
+    st = weights.make_state(cases.WEIGHT_SEED, n_mel)
+    # damp the (random-weight) vector field so the solve needs tens, not hundreds, of steps
+    for k in list(st):
+        if k.startswith("final_proj"):
+            st[k] = st[k] * 0.05
+    m = CFMDecoder(n_mel, n_mel, 256, n_mel, 1024, 4, 6, 3, 0.1, 256).eval()
+    m.estimator.load_state_dict(st, strict=True)
+    m = m.to(dev)
+    inp = weights.make_inputs(61, [48, 31], 48, n_mel)
+    fs, fc = weights.make_cfg_params(cases.CFG_SEED, n_mel)
+    z = inp["x"]
+    g = lambda t, y: R.cfg_estimator(st, t, y, inp["mask"], inp["mu"], inp["c"], fs, fc, 2.0)
+    with torch.inference_mode():
+        ref, stats = AD.odeint_dopri5(g, z, 1.0)
+    kw = dict(fake_speaker=fs.to(dev), fake_content=fc.to(dev), cfg_strength=2.0)
+    out = m(inp["mu"].to(dev), inp["mask"].to(dev), 10, 1.0, inp["c"].to(dev), None, kw, z=z.to(dev))
+    got = m.last_solver_stats
+    e = rel_errs(out, ref)
+    # both sides solve the same ODE to rtol = atol = 1e-5; step sequences may differ by a borderline accept
+    assert max(e) < 1e-3, (e, stats, got)
+    assert abs(got["accepted"] - stats["accepted"]) <= max(2, stats["accepted"] // 10), (stats, got)
+    assert got["nfe"] == 2 + 6 * (got["accepted"] + got["rejected"])

@@ -80,12 +80,11 @@ def test_no_cpu_fallback(built):
 
 
 def test_solver_names():
-    from stabletts_b200.flow_matching import _method_id
+    from stabletts_b200.flow_matching import _method_id, ST_ADAPTIVE
     from stabletts_b200 import _lib
     assert _method_id("euler") == _lib.ST_EULER and _method_id("midpoint") == _lib.ST_MIDPOINT
-    assert _method_id("rk4") == _lib.ST_RK4
-    with pytest.warns(UserWarning):
-        assert _method_id(None) == _lib.ST_DOPRI5_FIXED
+    assert _method_id("rk4") == _lib.ST_RK4 and _method_id("dopri5_fixed") == _lib.ST_DOPRI5_FIXED
+    assert _method_id(None) == ST_ADAPTIVE and _method_id("dopri5") == ST_ADAPTIVE     # the reference's default
     with pytest.raises(ValueError):
         _method_id("bosh3")
 
