@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--config", default="cfg1", choices=list(CONFIGS))
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-mode", action="store_true",
+                    help="for `ncu` launch lists only: honours --warmup < 3, skips e2e / instrumented / CPU legs (numbers printed under a profiler are never bench values)")
     args = ap.parse_args()
     cfgd = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -228,7 +230,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, cfgd, rank)
         return
-    if args.warmup < 3:
+    if args.warmup < 3 and not args.ncu_mode:
         args.warmup = 3
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
@@ -327,6 +329,13 @@ def main():
     l0 = model.estimator.launch_count()
     ms_dev, out_dev = timed(step_device, args.steps)
     launches = model.estimator.launch_count() - l0
+    if args.ncu_mode:
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"ncu_mode": True, "ms_per_step_under_profiler": ms_dev / args.steps, "gpu_launches": int(launches)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     for _ in range(1):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
