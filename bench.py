@@ -142,20 +142,9 @@ class ClockSampler:
 
 
 def cpu_threads() -> int:
-    """Host threads actually usable: min(affinity mask, cgroup CPU quota).  os.cpu_count() over-reports
-    inside a container (the GPU box shows 128 CPUs under a 16-CPU cgroup quota; 128 torch threads there
-    throttle to a crawl)."""
-    try:
-        n = max(1, len(os.sched_getaffinity(0)))
-    except Exception:
-        n = os.cpu_count() or 1
-    try:
-        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
-        if quota != "max":
-            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
-    except Exception:
-        pass
-    return n
+    """Host threads actually usable: min(affinity mask, cgroup CPU quota) — see oracle.usable_cpus()."""
+    from oracle import usable_cpus
+    return usable_cpus()
 
 
 def cpu_reference_solve(state, inp, cfgd, B, budget_s=25.0):

@@ -8,7 +8,10 @@
 //     K tile  [ 64 keys   ][64 dims]  channels [H + 64h, ...)       K-major B operand of S = Q·K^T
 //     V tile  [ 64 keys   ][64 dims]  channels [2H + 64h, ...)      MN-major B operand of O += P·V
 // One CTA per (128-query tile, head, batch row); warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM
-// alloc), warps 2-5 = softmax (thread = query row, reads its S row straight from TMEM).
+// alloc), warps 2-9 = softmax: TWO threads per query row, each owning one 32-key half of every 64-key
+// block with its OWN running max, row sum and O accumulator (O_A / O_B in TMEM; P·V is issued as two
+// K=32 halves), merged exactly at the end — no per-block exchange between the halves, half the serial
+// softmax latency per block, and the S row is read straight from TMEM (no cross-thread reductions).
 //   * S is double-buffered in TMEM and K in shared memory: S_{j+1}, S_{j+2} run on the tensor core
 //     while the softmax warps work on S_j;
 //   * O accumulates in TMEM (PV_j issued with accumulate) and the running max is LAZY: exponentials
@@ -43,12 +46,12 @@ using namespace ptx;
 constexpr int AQ = 128;          // queries per CTA (TMEM lanes)
 constexpr int AK = 64;           // keys per block
 constexpr int DH = 64;
-constexpr int A_THREADS = 192;
+constexpr int A_THREADS = 320;            // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (2 warps per TMEM lane quarter)
 constexpr int Q_BYTES = AQ * DH * 2;        // 16 KB per plane
 constexpr int K_BYTES = AK * DH * 2;        // 8 KB per plane
 constexpr int P_BYTES = AQ * AK * 2;        // 16 KB per plane
 constexpr int ATT_SMEM = 2 * Q_BYTES + 4 * K_BYTES + 2 * K_BYTES + 2 * P_BYTES + 1024;   // 112 KB + barriers/alignment
-constexpr int TMEM_COLS_ATT = 256;          // S0 [0,64) S1 [64,128) O [128,192)
+constexpr int TMEM_COLS_ATT = 256;          // S0 [0,64) S1 [64,128) O_A [128,192) O_B [192,256)
 constexpr float LAZY_THRESHOLD = 8.0f;      // log2 domain: p <= 2^8 between rescales
 
 struct AttMaps { CUtensorMap q_hi, q_lo, kv_hi, kv_lo, vt_hi, vt_lo; };
@@ -172,7 +175,7 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
     const int nb = (kvlen + AK - 1) / AK;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < 10; ++i) mbar_init(&bars[i], i == 9 ? 4 : 1);      // p_full: one arrive per softmax warp
+        for (int i = 0; i < 10; ++i) mbar_init(&bars[i], i == 9 ? 8 : 1);      // p_full: one arrive per softmax warp
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc_1sm<TMEM_COLS_ATT>(tmem_slot);
@@ -239,11 +242,12 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < AK / 16; ++k) {
+                for (int k = 0; k < AK / 16; ++k) {            // keys [0,32) -> O_A, keys [32,64) -> O_B
                     const uint64_t pa = (uint64_t)(k * 2), va = (uint64_t)k * v_adv;
-                    umma_bf16(tmem_O, dPl + pa, dVh + va, idesc_pv, (j | k) != 0);
-                    umma_bf16(tmem_O, dPh + pa, dVl + va, idesc_pv, 1);
-                    umma_bf16(tmem_O, dPh + pa, dVh + va, idesc_pv, 1);
+                    const uint32_t tO = tmem_O + (k >> 1) * 64;
+                    umma_bf16(tO, dPl + pa, dVh + va, idesc_pv, (j != 0) || (k & 1));
+                    umma_bf16(tO, dPh + pa, dVl + va, idesc_pv, 1);
+                    umma_bf16(tO, dPh + pa, dVh + va, idesc_pv, 1);
                 }
                 umma_commit(pv_done);
             }
@@ -256,11 +260,13 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
             }
         }
     } else {
-        // ================= softmax / epilogue: thread <-> query row =================
-        const int wq = warp & 3;
+        // ================= softmax / epilogue: thread <-> (query row, key half) =================
+        const int wq = warp & 3;                       // TMEM lane quarter (warps w and w+4 share it)
+        const int half = (warp - 2) >> 2;              // 0: keys [0,32) of every block -> O_A, 1: keys [32,64) -> O_B
         const int r = wq * 32 + lane;
         const int t = q0 + r;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const uint32_t tOh = tmem_O + half * 64 + lane_addr;     // this thread's O accumulator row (64 columns)
         const int prefix = p.prefix[b];
         const float* mrow = p.mask + (long)b * p.T;
         float m_used = -CUDART_INF_F, l_run = 0.f;
@@ -270,20 +276,19 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
         uint32_t v[32];
 
         for (int j = 0; j < nb; ++j) {
-            const int k0 = j * AK;
-            const uint32_t tS = tmem_base + (j & 1) * 64 + lane_addr;
+            const int k0 = j * AK + half * 32;
+            const uint32_t tS = tmem_base + (j & 1) * 64 + half * 32 + lane_addr;
             mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
-            // key validity of this block as two warp-uniform 32-bit words (only blocks reaching past the
+            // key validity of this half-block as a warp-uniform 32-bit word (only blocks reaching past the
             // all-ones prefix of the mask need it; interior blocks skip the test entirely)
-            const bool need_mask = k0 + AK > prefix;
-            uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu;
+            const bool need_mask = k0 + 32 > prefix;
+            uint32_t bits = 0xffffffffu;
             if (need_mask) {
-                const int ka = k0 + lane, kb = k0 + 32 + lane;
-                mb0 = __ballot_sync(0xffffffffu, ka < kvlen && __ldg(mrow + min(ka, p.T - 1)) != 0.f);
-                mb1 = __ballot_sync(0xffffffffu, kb < kvlen && __ldg(mrow + min(kb, p.T - 1)) != 0.f);
+                const int ka = k0 + lane;
+                bits = __ballot_sync(0xffffffffu, ka < kvlen && __ldg(mrow + min(ka, p.T - 1)) != 0.f);
             }
-            uint32_t hw[32], lw[32];                          // packed P row: 64 keys x (hi, lo)
+            uint32_t hw[16], lw[16];                          // packed P half-row: 32 keys x (hi, lo)
             float cand = -CUDART_INF_F, psum = 0.f;
             bool waited_pv = (j == 0);
             // single optimistic pass against the stale max; repeated once in the rare rescale case.
@@ -292,43 +297,39 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
             for (int attempt = 0; attempt < 2; ++attempt) {
                 const float m_eff = (m_used == -CUDART_INF_F) ? 0.f : m_used;
                 float c0 = -CUDART_INF_F, c1 = -CUDART_INF_F, ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;   // short dependency chains
+                tmem_ld32(tS, v);
+                tmem_ld_wait();
+                if (need_mask) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    tmem_ld32(tS + half * 32, v);
-                    tmem_ld_wait();
-                    if (need_mask) {
-                        const uint32_t bits = half ? mb1 : mb0;
+                    for (int i = 0; i < 32; ++i) if (!((bits >> i) & 1u)) v[i] = 0xff800000u;     // -inf
+                }
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) if (!((bits >> i) & 1u)) v[i] = 0xff800000u;     // -inf
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-                        const float s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
-                        c0 = fmaxf(c0, fmaxf(s0, s1)); c1 = fmaxf(c1, fmaxf(s2, s3));
-                        const float p0 = ex2_approx(s0 - m_eff), p1 = ex2_approx(s1 - m_eff);
-                        const float p2 = ex2_approx(s2 - m_eff), p3 = ex2_approx(s3 - m_eff);
-                        ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
-                        split_bf16x2(p0, p1, hw[half * 16 + i / 2], lw[half * 16 + i / 2]);
-                        split_bf16x2(p2, p3, hw[half * 16 + i / 2 + 1], lw[half * 16 + i / 2 + 1]);
-                    }
+                for (int i = 0; i < 32; i += 4) {
+                    const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+                    const float s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
+                    c0 = fmaxf(c0, fmaxf(s0, s1)); c1 = fmaxf(c1, fmaxf(s2, s3));
+                    const float p0 = ex2_approx(s0 - m_eff), p1 = ex2_approx(s1 - m_eff);
+                    const float p2 = ex2_approx(s2 - m_eff), p3 = ex2_approx(s3 - m_eff);
+                    ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
+                    split_bf16x2(p0, p1, hw[i / 2], lw[i / 2]);
+                    split_bf16x2(p2, p3, hw[i / 2 + 1], lw[i / 2 + 1]);
                 }
                 cand = fmaxf(c0, c1); psum = (ps0 + ps1) + (ps2 + ps3);
                 if (attempt == 1 || !__any_sync(0xffffffffu, cand > m_used + LAZY_THRESHOLD)) break;
                 const float m_new = fmaxf(m_used, cand);
                 const float factor = (m_new == -CUDART_INF_F) ? 1.f : ex2_approx(m_used - m_new);    // m_used = -inf -> 0
                 l_run *= factor;
-                if (j > 0) {                 // rescale O in TMEM: no PV may be in flight
+                if (j > 0) {                 // rescale this half's O accumulator in TMEM: no PV may be in flight
                     mbar_wait(pv_done, (j - 1) & 1);
                     tc_fence_after();
                     waited_pv = true;
 #pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
-                        tmem_ld32(tmem_O + lane_addr + half * 32, v);
+                    for (int hh = 0; hh < 2; ++hh) {
+                        tmem_ld32(tOh + hh * 32, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
-                        tmem_st32(tmem_O + lane_addr + half * 32, v);
+                        tmem_st32(tOh + hh * 32, v);
                     }
                     tmem_st_wait();
                 }
@@ -337,8 +338,8 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
             l_run += psum;
             if (!waited_pv) mbar_wait(pv_done, (j - 1) & 1);             // P buffer free (PV_{j-1} retired)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {                                 // 8 chunks of 8 keys = 16 B of bf16
-                const int off = ((c ^ sw) << 4);                          // 128B swizzle: chunk ^= (row & 7)
+            for (int c = 0; c < 4; ++c) {                                 // this half's 4 chunks of 8 keys (16 B of bf16)
+                const int off = (((half * 4 + c) ^ sw) << 4);             // 128B swizzle: chunk ^= (row & 7)
                 *reinterpret_cast<uint4*>(pr_hi + off) = make_uint4(hw[c * 4], hw[c * 4 + 1], hw[c * 4 + 2], hw[c * 4 + 3]);
                 *reinterpret_cast<uint4*>(pr_lo + off) = make_uint4(lw[c * 4], lw[c * 4 + 1], lw[c * 4 + 2], lw[c * 4 + 3]);
             }
@@ -348,34 +349,45 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
         }
-        // O complete after PV_{nb-1}
+        // O_A and O_B complete after PV_{nb-1}; merge the two halves of every row exactly:
+        //   out = (O_A 2^(mA-m) + O_B 2^(mB-m)) / (lA 2^(mA-m) + lB 2^(mB-m)),  m = max(mA, mB)
         mbar_wait(pv_done, (nb - 1) & 1);
         tc_fence_after();
-        const bool valid = t < p.T && mrow[min(t, p.T - 1)] != 0.f && l_run > 0.f;
-        const float inv = valid ? 1.0f / l_run : 0.f;
-        const long o = ((long)bb * p.T + t) * p.H + h * DH;
+        float2* xch = reinterpret_cast<float2*>(sPh);                     // P buffer is free now: [half][row] (m, l)
+        xch[half * AQ + r] = make_float2(m_used, l_run);
+        asm volatile("bar.sync 1, 256;" ::: "memory");                    // the 8 softmax warps only
+        const float2 oth = xch[(half ^ 1) * AQ + r];
+        const float mA = half ? oth.x : m_used, lA = half ? oth.y : l_run;
+        const float mB = half ? m_used : oth.x, lB = half ? l_run : oth.y;
+        const float mm = fmaxf(mA, mB);
+        const float fA = (mA == -CUDART_INF_F) ? 0.f : ex2_approx(mA - mm), fB = (mB == -CUDART_INF_F) ? 0.f : ex2_approx(mB - mm);
+        const float lsum = lA * fA + lB * fB;
+        const bool valid = t < p.T && mrow[min(t, p.T - 1)] != 0.f && lsum > 0.f;
+        const float inv = valid ? 1.0f / lsum : 0.f;
+        const float wA = fA * inv, wB = fB * inv;
+        // this thread emits output dims [32*half, 32*half + 32) of its row
+        uint32_t va[32];
+        tmem_ld32(tmem_O + lane_addr + half * 32, va);
+        tmem_ld32(tmem_O + 64 + lane_addr + half * 32, v);
+        tmem_ld_wait();
+        if (t < p.T) {
+            const long o = ((long)bb * p.T + t) * p.H + h * DH + half * 32;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            tmem_ld32(tmem_O + lane_addr + half * 32, v);
-            tmem_ld_wait();
-            if (t < p.T) {
+            for (int c = 0; c < 4; ++c) {
+                float f[8];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float f[8];
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(va[c * 8 + e]) * wA + __uint_as_float(v[c * 8 + e]) * wB;
+                const long oc = o + c * 8;
+                if (p.out_f32) {
+                    *reinterpret_cast<float4*>(p.out_f32 + oc) = make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4*>(p.out_f32 + oc + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                }
+                if (p.out_hi) {
+                    uint32_t h4[4], l4[4];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c * 8 + e]) * inv;
-                    const long oc = o + half * 32 + c * 8;
-                    if (p.out_f32) {
-                        *reinterpret_cast<float4*>(p.out_f32 + oc) = make_float4(f[0], f[1], f[2], f[3]);
-                        *reinterpret_cast<float4*>(p.out_f32 + oc + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                    }
-                    if (p.out_hi) {
-                        uint32_t h4[4], l4[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) split_bf16x2(f[2 * e], f[2 * e + 1], h4[e], l4[e]);
-                        *reinterpret_cast<uint4*>(p.out_hi + oc) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-                        *reinterpret_cast<uint4*>(p.out_lo + oc) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
-                    }
+                    for (int e = 0; e < 4; ++e) split_bf16x2(f[2 * e], f[2 * e + 1], h4[e], l4[e]);
+                    *reinterpret_cast<uint4*>(p.out_hi + oc) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                    *reinterpret_cast<uint4*>(p.out_lo + oc) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
                 }
             }
         }
