@@ -629,7 +629,11 @@ attention_tc4_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
                 tmem_st32(tS, pk);
                 tmem_st_wait();
             }
-            (void)waited_pv;
+            // Observe EVERY pv_done phase, in order, BEFORE signalling P_j: an mbarrier parity wait is only meaningful
+            // within one phase of the barrier, and P·V_j cannot be issued until this warp has arrived, so the barrier is
+            // at phase j-1 or j here — never further.  P·V_{j-1} was issued a whole softmax block ago (V is double
+            // buffered, so it did not wait for a load): this wait does not stall in steady state.
+            if (!waited_pv) mbar_wait(pv_done, (j - 1) & 1);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
