@@ -54,9 +54,12 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, int bb, int t0,
     const long obase = (long)bb * p.T * p.N;
     const bool plain = (p.flags & (EPI_FILM | EPI_MASK | EPI_GATE | EPI_RESID)) == 0;
 
+    // The two warps of a lane quarter split the 32-column chunks as {0,3,4,7,..} / {1,2,5,6,..}: with RoPE only
+    // the even chunks (first half of every 64-wide head) carry the rotation, and this split gives each warp half of them.
 #pragma unroll 1
-    for (int c0 = eh * 32; c0 < BN; c0 += 64) {
-        if (n0 + c0 >= p.N) break;             // warp-uniform
+    for (int kc = 0; kc < BN / 64; ++kc) {
+        const int c0 = (2 * kc + ((kc & 1) ^ eh)) * 32;
+        if (n0 + c0 >= p.N) continue;          // warp-uniform
         {
             uint32_t v[32];
             tmem_ld32(tmem_acc + (uint32_t)c0, v);
