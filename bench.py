@@ -308,15 +308,22 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                 # started BEFORE warm-up: nvidia-smi start-up stalls the driver for ~100 ms
-    tw0 = time.perf_counter()
-    n_warm = 0
     # at least W untimed steps AND ~2 s of load: under the 1 kW cap the SM clock needs about a second to settle
-    # (the first few hundred ms run at 1965 MHz, then the power controller pulls back and briefly overshoots)
-    while n_warm < args.warmup or (not args.ncu_mode and time.perf_counter() - tw0 < 2.0):
+    # (the first few hundred ms run at 1965 MHz, then the power controller pulls back and briefly overshoots).
+    # The extra count is decided on rank 0 and broadcast so every rank issues the same number of collectives.
+    tw0 = time.perf_counter()
+    for _ in range(args.warmup):
         step_device()
-        n_warm += 1
-        if n_warm % 4 == 0:
-            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    el = time.perf_counter() - tw0
+    extra = 0 if args.ncu_mode else int(max(0.0, 2.0 - el) / max(el / max(args.warmup, 1), 1e-4)) + 1
+    if world > 1:
+        ex_t = torch.tensor([extra], device=dev)
+        dist.broadcast(ex_t, 0)
+        extra = int(ex_t.item())
+    for _ in range(extra):
+        step_device()
+    n_warm = args.warmup + extra
     torch.cuda.synchronize()
     th0 = time.perf_counter()
     step_device()                       # host-side enqueue time of one step (no sync): launch-bound check
