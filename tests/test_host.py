@@ -124,3 +124,33 @@ def test_drop_in_inside_reference_stabletts(built):
     assert list(ours.state_dict().keys()) == keys_ref
     ours.load_state_dict(ref.state_dict(), strict=True)          # a reference checkpoint loads unchanged
     assert ref_fm.CFMDecoder is not stabletts_b200.CFMDecoder
+
+
+def _build_c_smoke():
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "c_abi_smoke")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    cmd = ["gcc", os.path.join(root, "tests", "c_abi_smoke.c"), "-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include",
+           "-L" + os.path.join(root, "stabletts_b200"), "-lstabletts_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-lm",
+           "-Wl,-rpath," + os.path.join(root, "stabletts_b200"), "-o", exe]
+    subprocess.run(cmd, check=True, capture_output=True)
+    return exe
+
+
+def test_pure_c_consumer_without_gpu(built):
+    """A plain C program (no Python, no torch) links against the C ABI; without a GPU st_create must fail loudly."""
+    import subprocess
+    if torch.cuda.is_available():
+        pytest.skip("GPU present (covered by the gpu test)")
+    r = subprocess.run([_build_c_smoke()], capture_output=True, text=True)
+    assert r.returncode == 0 and "no CUDA device" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_pure_c_consumer_on_gpu(built):
+    import subprocess
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    r = subprocess.run([_build_c_smoke()], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
