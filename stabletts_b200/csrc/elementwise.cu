@@ -79,75 +79,87 @@ template <int H>
 __global__ void __launch_bounds__(256) film_ln_mod_kernel(LnArgs a) {
     pdl_trigger(); pdl_wait();
     constexpr int V = H / 32;          // channels per lane
+    constexpr int R = 2;               // frames per warp: two independent 1 KB row streams in flight per warp
     static_assert(V % 4 == 0, "H must be a multiple of 128");
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const long rows = (long)a.BB * a.T;
-    if (warp >= rows) return;
-    const int bb = warp / a.T, t = warp - bb * a.T;
-    const float m = a.mask[(long)(bb % a.B) * a.T + t];
-    const int cb = min(bb, a.c_clamp);
-    const float* xr = a.xin + (long)warp * H;
-    float x[V];
+    const long row0 = warp * R;
+    if (row0 >= rows) return;
+    float x[R][V];
+    float m[R];
+    int cb[R];
+    bool ok[R];
 #pragma unroll
-    for (int j = 0; j < V / 4; ++j) {
-        float4 v = *reinterpret_cast<const float4*>(xr + (j * 32 + lane) * 4);
-        x[j * 4 + 0] = v.x; x[j * 4 + 1] = v.y; x[j * 4 + 2] = v.z; x[j * 4 + 3] = v.w;
+    for (int r = 0; r < R; ++r) {
+        const long row = row0 + r;
+        ok[r] = row < rows;
+        const long rw = ok[r] ? row : rows - 1;
+        const int bb = (int)(rw / a.T), t = (int)(rw - (long)bb * a.T);
+        m[r] = a.mask[(long)(bb % a.B) * a.T + t];
+        cb[r] = min(bb, a.c_clamp);
+        const float* xr = a.xin + rw * H;
+#pragma unroll
+        for (int j = 0; j < V / 4; ++j) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(xr + (j * 32 + lane) * 4));
+            x[r][j * 4 + 0] = v.x; x[r][j * 4 + 1] = v.y; x[r][j * 4 + 2] = v.z; x[r][j * 4 + 3] = v.w;
+        }
     }
-    if (a.has_film) {
-        const float* f = a.film + (long)(bb % a.B) * a.film_bstride;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (!ok[r]) continue;
+        const long row = row0 + r;
+        const int bb = (int)(row / a.T);
+        if (a.has_film) {
+            const float* f = a.film + (long)(bb % a.B) * a.film_bstride;
+#pragma unroll
+            for (int j = 0; j < V / 4; ++j) {
+                int c = (j * 32 + lane) * 4;
+                float4 g = __ldg(reinterpret_cast<const float4*>(f + c));
+                float4 be = __ldg(reinterpret_cast<const float4*>(f + H + c));
+                x[r][j * 4 + 0] = (g.x * x[r][j * 4 + 0] + be.x) * m[r];
+                x[r][j * 4 + 1] = (g.y * x[r][j * 4 + 1] + be.y) * m[r];
+                x[r][j * 4 + 2] = (g.z * x[r][j * 4 + 2] + be.z) * m[r];
+                x[r][j * 4 + 3] = (g.w * x[r][j * 4 + 3] + be.w) * m[r];
+            }
+            float* xo = a.xout + row * H;
+#pragma unroll
+            for (int j = 0; j < V / 4; ++j)
+                *reinterpret_cast<float4*>(xo + (j * 32 + lane) * 4) =
+                    make_float4(x[r][j * 4 + 0], x[r][j * 4 + 1], x[r][j * 4 + 2], x[r][j * 4 + 3]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) sum += x[r][j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * (1.0f / H);
+        float var = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) { float d = x[r][j] - mean; var += d * d; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+        const float rstd = rsqrtf(var * (1.0f / H) + 1e-5f);
+        const float* sh = a.shift + (long)cb[r] * a.ada_bstride;
+        const float* sc = a.scale + (long)cb[r] * a.ada_bstride;
+        const float mo = a.mask_out ? m[r] : 1.0f;
 #pragma unroll
         for (int j = 0; j < V / 4; ++j) {
             int c = (j * 32 + lane) * 4;
-            float4 g = *reinterpret_cast<const float4*>(f + c);
-            float4 be = *reinterpret_cast<const float4*>(f + H + c);
-            x[j * 4 + 0] = (g.x * x[j * 4 + 0] + be.x) * m;
-            x[j * 4 + 1] = (g.y * x[j * 4 + 1] + be.y) * m;
-            x[j * 4 + 2] = (g.z * x[j * 4 + 2] + be.z) * m;
-            x[j * 4 + 3] = (g.w * x[j * 4 + 3] + be.w) * m;
-        }
-        float* xo = a.xout + (long)warp * H;
-#pragma unroll
-        for (int j = 0; j < V / 4; ++j)
-            *reinterpret_cast<float4*>(xo + (j * 32 + lane) * 4) =
-                make_float4(x[j * 4 + 0], x[j * 4 + 1], x[j * 4 + 2], x[j * 4 + 3]);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < V; ++j) sum += x[j];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum * (1.0f / H);
-    float var = 0.f;
-#pragma unroll
-    for (int j = 0; j < V; ++j) { float d = x[j] - mean; var += d * d; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-    const float rstd = rsqrtf(var * (1.0f / H) + 1e-5f);
-    const float* sh = a.shift + (long)cb * a.ada_bstride;
-    const float* sc = a.scale + (long)cb * a.ada_bstride;
-    const float mo = a.mask_out ? m : 1.0f;
-#pragma unroll
-    for (int j = 0; j < V / 4; ++j) {
-        int c = (j * 32 + lane) * 4;
-        float4 s4 = *reinterpret_cast<const float4*>(sh + c);
-        float4 c4 = *reinterpret_cast<const float4*>(sc + c);
-        float u0 = ((x[j * 4 + 0] - mean) * rstd * (1.f + c4.x) + s4.x) * mo;
-        float u1 = ((x[j * 4 + 1] - mean) * rstd * (1.f + c4.y) + s4.y) * mo;
-        float u2 = ((x[j * 4 + 2] - mean) * rstd * (1.f + c4.z) + s4.z) * mo;
-        float u3 = ((x[j * 4 + 3] - mean) * rstd * (1.f + c4.w) + s4.w) * mo;
-        long o = (long)warp * H + c;
-        if (a.u_f32) *reinterpret_cast<float4*>(a.u_f32 + o) = make_float4(u0, u1, u2, u3);
-        if (a.u_hi) {
-            bf16 h0, h1, h2, h3, l0, l1, l2, l3;
-            split_bf16(u0, h0, l0); split_bf16(u1, h1, l1); split_bf16(u2, h2, l2); split_bf16(u3, h3, l3);
-            __nv_bfloat162 hp0 = __halves2bfloat162(h0, h1), hp1 = __halves2bfloat162(h2, h3);
-            __nv_bfloat162 lp0 = __halves2bfloat162(l0, l1), lp1 = __halves2bfloat162(l2, l3);
-            uint2 hv, lv;
-            hv.x = *reinterpret_cast<uint32_t*>(&hp0); hv.y = *reinterpret_cast<uint32_t*>(&hp1);
-            lv.x = *reinterpret_cast<uint32_t*>(&lp0); lv.y = *reinterpret_cast<uint32_t*>(&lp1);
-            *reinterpret_cast<uint2*>(a.u_hi + o) = hv;
-            *reinterpret_cast<uint2*>(a.u_lo + o) = lv;
+            float4 s4 = __ldg(reinterpret_cast<const float4*>(sh + c));
+            float4 c4 = __ldg(reinterpret_cast<const float4*>(sc + c));
+            float u0 = ((x[r][j * 4 + 0] - mean) * rstd * (1.f + c4.x) + s4.x) * mo;
+            float u1 = ((x[r][j * 4 + 1] - mean) * rstd * (1.f + c4.y) + s4.y) * mo;
+            float u2 = ((x[r][j * 4 + 2] - mean) * rstd * (1.f + c4.z) + s4.z) * mo;
+            float u3 = ((x[r][j * 4 + 3] - mean) * rstd * (1.f + c4.w) + s4.w) * mo;
+            long o = row * H + c;
+            if (a.u_f32) *reinterpret_cast<float4*>(a.u_f32 + o) = make_float4(u0, u1, u2, u3);
+            if (a.u_hi) {
+                uint32_t h01, l01, h23, l23;
+                split_bf16x2(u0, u1, h01, l01); split_bf16x2(u2, u3, h23, l23);
+                *reinterpret_cast<uint2*>(a.u_hi + o) = make_uint2(h01, h23);
+                *reinterpret_cast<uint2*>(a.u_lo + o) = make_uint2(l01, l23);
+            }
         }
     }
 }
@@ -156,7 +168,7 @@ cudaError_t launch_film_ln_mod(const LnArgs& a, cudaStream_t s) {
     if (a.H != 256) return cudaErrorInvalidValue;
     long rows = (long)a.BB * a.T;
     if (rows == 0) return cudaSuccess;
-    int blocks = (int)((rows * 32 + 255) / 256);
+    int blocks = (int)((((rows + 1) / 2) * 32 + 255) / 256);      // two frames per warp
     return launch_k(film_ln_mod_kernel<256>, dim3(blocks), dim3(256), 0, s, a);
 }
 
