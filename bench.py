@@ -102,10 +102,21 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+            return
+        # nvidia-smi takes seconds to initialise NVML on an 8-GPU host and its first query stalls the driver for
+        # hundreds of ms: wait for the first sample so that this start-up never lands inside a timed region
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 20.0:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    break
+            except OSError:
+                pass
+            time.sleep(0.1)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
