@@ -34,100 +34,128 @@ inline void fill_tc_params(TcParams& p, const GemmArgs& g) {
 // softmax scale folded into q: 1/sqrt(64) * log2(e) (attention runs in the exp2 domain)
 constexpr float kQScale = 0.125f * 1.4426950408889634f;
 
+// Per-tile RoPE table prefetch for the QKV GEMM: the (cos, sin) pairs a lane needs depend only on its frames
+// (t0 + 4*it + rs) and its pair group (c4 & 3), not on the column chunk, so they are loaded ONCE per tile --
+// before the wait on the accumulator barrier, which hides their L2 latency behind the MMAs.
+struct RopeRegs { float4 a[8], b[8]; };
+__device__ __forceinline__ void epilogue_rope_prefetch(const TcParams& p, int t0, int lane, RopeRegs& r) {
+    const int rs = lane >> 3, c4 = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int tc = min(t0 + it * 4 + rs, p.T - 1);
+        const float* q = p.rope_cs + ((long)tc * 16 + (c4 & 3) * 4) * 2;
+        r.a[it] = __ldg(reinterpret_cast<const float4*>(q));
+        r.b[it] = __ldg(reinterpret_cast<const float4*>(q + 4));
+    }
+}
+
 // bb: batch row, t0: first frame of this warp's 32-frame slab, n0: first column of the tile,
 // tmem_acc: TMEM address of (lane quarter, accumulator column 0), stg: this warp's 4 KB staging.
-template <int BN>
+// ROPE = true is the QKV variant (bias + partial RoPE + q pre-scale only; launch_gemm_tc rejects EPI_ROPE
+// combined with SiLU/FiLM/mask/gate/residual); ROPE = false is everything else.  Two instances keep each
+// one's registers and instruction footprint small; a launch only ever executes one of them.
+template <int BN, bool ROPE>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, int bb, int t0, int n0, uint32_t tmem_acc, float4* stg,
-                                              int eh, int lane) {
+                                              int eh, int lane, const RopeRegs* rr) {
     using namespace ptx;
     const int rs = lane >> 3, c4 = lane & 7;
     const int mb = bb % p.B;
-    float mrow[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int t = t0 + it * 4 + rs;
-        mrow[it] = ((p.flags & EPI_MASK) && t < p.T) ? __ldg(p.mask + (long)mb * p.T + t) : 1.f;
-    }
-    const float* film = p.film + (long)mb * p.film_bstride;
-    const float* gate = p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride;
-    const float* resid = p.resid + (long)min(bb, p.resid_clamp) * p.T * p.N;
     const long obase = (long)bb * p.T * p.N;
-    const bool plain = (p.flags & (EPI_FILM | EPI_MASK | EPI_GATE | EPI_RESID)) == 0;
-
     // The two warps of a lane quarter split the 32-column chunks as {0,3,4,7,..} / {1,2,5,6,..}: with RoPE only
     // the even chunks (first half of every 64-wide head) carry the rotation, and this split gives each warp half of them.
+    auto chunk_col = [eh](int kc) { return (2 * kc + ((kc & 1) ^ eh)) * 32; };   // increasing in kc
+    uint32_t v[32];
+    if (n0 + chunk_col(0) < p.N) tmem_ld32(tmem_acc + (uint32_t)chunk_col(0), v);
+
+    float mrow[8];
+    const float *film = nullptr, *gate = nullptr, *resid = nullptr;
+    bool plain = true;
+    if constexpr (!ROPE) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int t = t0 + it * 4 + rs;
+            mrow[it] = ((p.flags & EPI_MASK) && t < p.T) ? __ldg(p.mask + (long)mb * p.T + t) : 1.f;
+        }
+        film = p.film + (long)mb * p.film_bstride;
+        gate = p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride;
+        resid = p.resid + (long)min(bb, p.resid_clamp) * p.T * p.N;
+        plain = (p.flags & (EPI_FILM | EPI_MASK | EPI_GATE | EPI_RESID)) == 0;
+    }
+
 #pragma unroll 1
     for (int kc = 0; kc < BN / 64; ++kc) {
-        const int c0 = (2 * kc + ((kc & 1) ^ eh)) * 32;
-        if (n0 + c0 >= p.N) continue;          // warp-uniform
-        {
-            uint32_t v[32];
-            tmem_ld32(tmem_acc + (uint32_t)c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                stg[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
-                                                               __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
-        }
-        __syncwarp();
+        const int c0 = chunk_col(kc);
+        if (n0 + c0 >= p.N) break;             // warp-uniform; later chunks lie further right
         const int nb = n0 + c0;                // chunk base column (multiple of 32), warp-uniform
         const int n = nb + c4 * 4;
+        const bool col_ok = n < p.N;           // N % 4 == 0: a float4 column group is all-in or all-out
+        // per-column vectors: issued before the TMEM wait so their latency overlaps it
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = b4, bp4 = b4;
         // RoPE applies to the first 32 dims of every 64-wide head of q and k (columns [0, 2H));
         // pairs (j, j+16) live in lanes c4 and c4^4 of the same frame (models/diffusion_transformer.py:173-198)
-        const bool rope = (p.flags & EPI_ROPE) && nb < 2 * p.rope_H && (nb & 63) == 0;
-        const float post = ((p.flags & EPI_ROPE) && nb < p.rope_H) ? kQScale : 1.0f;
-        const bool col_ok = n < p.N;           // N % 4 == 0: a float4 column group is all-in or all-out
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = b4, bp4 = b4;
+        const bool rope = ROPE && nb < 2 * p.rope_H && (nb & 63) == 0;
+        const float post = (ROPE && nb < p.rope_H) ? kQScale : 1.0f;
         if (col_ok) {
             if (p.flags & EPI_BIAS) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            if (rope && (p.flags & EPI_BIAS)) bp4 = __ldg(reinterpret_cast<const float4*>(p.bias + (n ^ 16)));   // RoPE partner column
-            if (p.flags & EPI_GATE) g4 = __ldg(reinterpret_cast<const float4*>(gate + n));
-            if (p.flags & EPI_FILM) {
-                fg = __ldg(reinterpret_cast<const float4*>(film + n));
-                fb = __ldg(reinterpret_cast<const float4*>(film + p.film_H + n));
+            if constexpr (ROPE) {
+                if (rope && (p.flags & EPI_BIAS)) bp4 = __ldg(reinterpret_cast<const float4*>(p.bias + (n ^ 16)));   // partner column
+            } else {
+                if (p.flags & EPI_GATE) g4 = __ldg(reinterpret_cast<const float4*>(gate + n));
+                if (p.flags & EPI_FILM) {
+                    fg = __ldg(reinterpret_cast<const float4*>(film + n));
+                    fb = __ldg(reinterpret_cast<const float4*>(film + p.film_H + n));
+                }
             }
         }
-#pragma unroll 1
-        for (int hf = 0; hf < 2; ++hf) {                 // not unrolled: keeps the epilogue inside the instruction cache
-            float4 sv[4], rv[4];
+        float4 rv[8];
+        if constexpr (!ROPE) {                 // residual rows of the whole chunk, also ahead of the TMEM wait
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int rl = (hf * 4 + i) * 4 + rs;
-                sv[i] = stg[rl * 8 + (c4 ^ (rl & 7))];
-                rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((p.flags & EPI_RESID) && col_ok && t0 + rl < p.T)
-                    rv[i] = __ldg(reinterpret_cast<const float4*>(resid + (long)(t0 + rl) * p.N + n));
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int it = hf * 4 + i;
+            for (int it = 0; it < 8; ++it) {
                 const int t = t0 + it * 4 + rs;
-                float x[4] = {sv[i].x + b4.x, sv[i].y + b4.y, sv[i].z + b4.z, sv[i].w + b4.w};
-                if (p.flags & EPI_SILU) {
+                rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((p.flags & EPI_RESID) && col_ok && t < p.T)
+                    rv[it] = __ldg(reinterpret_cast<const float4*>(resid + (long)t * p.N + n));
+            }
+        }
+        tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
-                }
+        for (int q = 0; q < 8; ++q)
+            stg[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                                           __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+        if (kc + 1 < BN / 64 && n0 + chunk_col(kc + 1) < p.N)      // next chunk's TMEM read flies during phase B
+            tmem_ld32(tmem_acc + (uint32_t)chunk_col(kc + 1), v);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int rl = it * 4 + rs;
+            const int t = t0 + rl;
+            const float4 sv = stg[rl * 8 + (c4 ^ (rl & 7))];
+            float x[4] = {sv.x + b4.x, sv.y + b4.y, sv.z + b4.z, sv.w + b4.w};
+            if constexpr (ROPE) {
                 if (rope) {                    // warp-uniform branch
-                    const int tc = min(t, p.T - 1), rl = it * 4 + rs;
-                    const float4 cs0 = __ldg(reinterpret_cast<const float4*>(p.rope_cs + ((long)tc * 16 + (c4 & 3) * 4) * 2));
-                    const float4 cs1 = __ldg(reinterpret_cast<const float4*>(p.rope_cs + ((long)tc * 16 + (c4 & 3) * 4) * 2 + 4));
                     const float4 pv = stg[rl * 8 + ((c4 ^ 4) ^ (rl & 7))];      // partner dims (j +- 16) of the same frame
                     const float sgn = (c4 < 4) ? -1.f : 1.f;      // r_j = -x_{j+16} (j<16), +x_{j-16} (j>=16)
+                    const float4 cs0 = rr->a[it], cs1 = rr->b[it];
                     x[0] = x[0] * cs0.x + sgn * (pv.x + bp4.x) * cs0.y;
                     x[1] = x[1] * cs0.z + sgn * (pv.y + bp4.y) * cs0.w;
                     x[2] = x[2] * cs1.x + sgn * (pv.z + bp4.z) * cs1.y;
                     x[3] = x[3] * cs1.z + sgn * (pv.w + bp4.w) * cs1.w;
                 }
-                if (t >= p.T || !col_ok) continue;
-                if (plain) {                   // bias / SiLU / RoPE only (QKV, cond_proj): skip the neutral FiLM·mask·gate+resid chain
-                    x[0] *= post; x[1] *= post; x[2] *= post; x[3] *= post;
-                } else {
-                    const float m = hf ? mrow[4 + i] : mrow[i];      // static indices: mrow stays in registers
-                    x[0] = (fg.x * x[0] + fb.x) * m * g4.x + rv[i].x;
-                    x[1] = (fg.y * x[1] + fb.y) * m * g4.y + rv[i].y;
-                    x[2] = (fg.z * x[2] + fb.z) * m * g4.z + rv[i].z;
-                    x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[i].w;
+                x[0] *= post; x[1] *= post; x[2] *= post; x[3] *= post;
+            } else {
+                if (p.flags & EPI_SILU) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
                 }
+                if (!plain) {                  // bias / SiLU only (cond_proj) skips the neutral FiLM·mask·gate+resid chain
+                    const float m = mrow[it];
+                    x[0] = (fg.x * x[0] + fb.x) * m * g4.x + rv[it].x;
+                    x[1] = (fg.y * x[1] + fb.y) * m * g4.y + rv[it].y;
+                    x[2] = (fg.z * x[2] + fb.z) * m * g4.z + rv[it].z;
+                    x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[it].w;
+                }
+            }
+            if (t < p.T && col_ok) {
                 const long o = obase + (long)t * p.N + n;
                 if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
                 if (p.out_hi) {

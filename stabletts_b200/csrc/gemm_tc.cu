@@ -249,9 +249,18 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
             const int bb = m_tile / p.m_tiles_per_b, t0 = (m_tile % p.m_tiles_per_b) * BLOCK_M + wq * 32;
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-            epilogue_tile<BN>(p, bb, t0, n_tile * BN, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN), stg, eh, lane);
+            const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN);
+            if (p.flags & EPI_ROPE) {                  // kernel-uniform
+                RopeRegs rr;
+                epilogue_rope_prefetch(p, t0, lane, rr);
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                epilogue_tile<BN, true>(p, bb, t0, n_tile * BN, tacc, stg, eh, lane, &rr);
+            } else {
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                epilogue_tile<BN, false>(p, bb, t0, n_tile * BN, tacc, stg, eh, lane, nullptr);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -382,6 +391,11 @@ static int tc2_mode() {
 
 cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s) {
     if (g.BB == 0 || g.T == 0) return cudaSuccess;
+    if ((g.flags & EPI_ROPE) && (g.flags & (EPI_SILU | EPI_FILM | EPI_MASK | EPI_GATE | EPI_RESID))) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_err = "EPI_ROPE combines with EPI_BIAS only (the QKV epilogue variant)";
+        return cudaErrorInvalidValue;
+    }
     {
         const int mode = tc2_mode();
         bool ok = g.A_hi[0] && g.W_hi && g.N >= 256 && g.N % 128 == 0 && g.Ktot % 8 == 0 && g.Cs[0] % 8 == 0 &&

@@ -146,9 +146,18 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
             const int bb = m_tile / p.m_tiles_per_b;
             const int t0 = (m_tile % p.m_tiles_per_b) * (2 * BM) + (int)rank * BM + wq * 32;
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-            epilogue_tile<BN2>(p, bb, t0, n_tile * BN2, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN2), stg, eh, lane);
+            const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN2);
+            if (p.flags & EPI_ROPE) {                  // kernel-uniform
+                RopeRegs rr;
+                epilogue_rope_prefetch(p, t0, lane, rr);
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                epilogue_tile<BN2, true>(p, bb, t0, n_tile * BN2, tacc, stg, eh, lane, &rr);
+            } else {
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                epilogue_tile<BN2, false>(p, bb, t0, n_tile * BN2, tacc, stg, eh, lane, nullptr);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);      // the LEADER's barrier gates the next MMA

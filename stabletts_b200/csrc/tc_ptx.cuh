@@ -26,7 +26,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
         "{\n\t"
         ".reg .b32 remAddr32;\n\t"
         "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
