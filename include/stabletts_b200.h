@@ -86,6 +86,13 @@ int st_attach_workspace(st_handle* h, void* dev_ptr, size_t bytes);
 int st_estimator_forward(st_handle* h, const float* t, int t_count, const float* x, const float* mask,
                          const float* mu, const float* c, float* out, int B, int T, void* stream);
 
+/* Replaces: the forward VALUE of CFMDecoder.compute_loss (models/flow_matching.py:69-100) in eval mode (no dropout,
+ * no autograd): given the caller's draws t (B values, already cosine-warped, :92-93) and z (:96) it forms
+ * y = (1-(1-sigma_min) t) z + t x1 (written to y_out, (B, n_mel, T)), evaluates the estimator at per-sample t and writes
+ * sum((v - u)^2) / (sum(mask) * n_mel), u = x1 - (1-sigma_min) z, to the DEVICE scalar loss_out.  No host sync. */
+int st_cfm_loss(st_handle* h, const float* x1, const float* z, const float* t, const float* mask, const float* mu,
+                const float* c, float sigma_min, float* y_out, float* loss_out, int B, int T, void* stream);
+
 /* Replaces: CFMDecoder.forward's `odeint(estimator | cfg_wrapper, z, t_span, method=solver)` and
  * `trajectory[-1]` (models/flow_matching.py:46-55) together with cfg_wrapper (:58-67).
  *   z_inout: (B, n_mel, T) — in: z = randn_like(mu)*temperature (UNMASKED, :45); out: the sample

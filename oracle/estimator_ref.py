@@ -235,3 +235,16 @@ def cfm_forward(state: State, mu: torch.Tensor, mask: torch.Tensor, n_timesteps:
                                        cfg["cfg_strength"], n_heads)
     with torch.inference_mode():
         return odeint_fixed(f, z, t_span, method)
+
+
+def cfm_loss(state: State, x1: torch.Tensor, mask: torch.Tensor, mu: torch.Tensor, c: torch.Tensor, u01: torch.Tensor,
+             z: torch.Tensor, sigma_min: float = 1e-4, n_heads: int = 4):
+    """models/flow_matching.py:69-100 (eval mode, no autograd) with the two random draws passed in:
+    ``u01`` = the ``torch.rand([b,1,1])`` draw (:92), ``z`` = ``randn_like(x1)`` (:96).  Returns (loss, y)."""
+    t = 1 - torch.cos(u01 * 0.5 * torch.pi)                                     # :93
+    y = (1 - (1 - sigma_min) * t) * z + t * x1                                  # :98
+    u = x1 - (1 - sigma_min) * z                                                # :99
+    with torch.inference_mode():
+        v = estimator_forward(state, t.squeeze(), y, mask, mu, c, n_heads)
+    loss = F.mse_loss(v, u, reduction="sum") / (torch.sum(mask) * u.size(1))    # :101
+    return loss, y

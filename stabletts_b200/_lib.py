@@ -15,7 +15,7 @@ ST_PROF_NCAT = len(ST_PROF_NAMES)
 # every symbol include/stabletts_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "st_create", "st_destroy", "st_last_error", "st_version", "st_load_weight", "st_finalize_weights",
-    "st_set_engine", "st_workspace_bytes", "st_attach_workspace", "st_estimator_forward", "st_solve",
+    "st_set_engine", "st_workspace_bytes", "st_attach_workspace", "st_estimator_forward", "st_cfm_loss", "st_solve",
     "st_solve_host", "st_solve_adaptive", "st_align_lengths", "st_align_expand", "st_create_text_encoder", "st_text_encoder_forward", "st_launch_count", "st_profile_begin", "st_profile_end", "st_test_gemm", "st_test_conv", "st_test_attention", "st_bench_conv",
 ]
 
@@ -52,6 +52,7 @@ def load_library() -> C.CDLL:
     lib.st_workspace_bytes.restype = C.c_size_t
     lib.st_attach_workspace.argtypes = [vp, vp, C.c_size_t]
     lib.st_estimator_forward.argtypes = [vp, f32p, i32, f32p, f32p, f32p, f32p, f32p, i32, i32, vp]
+    lib.st_cfm_loss.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, C.c_float, f32p, f32p, i32, i32, vp]
     lib.st_solve.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, C.c_float, C.POINTER(C.c_float), i32, i32, i32, i32, vp]
     lib.st_solve_host.argtypes = lib.st_solve.argtypes
     lib.st_solve_adaptive.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, C.c_float, C.c_double, C.c_double, C.c_double, C.c_double,

@@ -678,6 +678,24 @@ int st_estimator_forward(st_handle* h, const float* t, int t_count, const float*
     return 0;
 }
 
+// CFMDecoder.compute_loss's forward value (models/flow_matching.py:69-100) for given draws t (already warped, :92-93)
+// and z (:96): y = (1-(1-sigma)t) z + t x1 -> estimator(t, y, mask, mu, c) -> sum((v-u)^2) / (sum(mask) * n_mel).
+int st_cfm_loss(st_handle* h, const float* x1, const float* z, const float* t, const float* mask, const float* mu, const float* c,
+                float sigma_min, float* y_out, float* loss_out, int B, int T, void* stream) {
+    if (check_common(h, B, T)) return 1;
+    if (h->kind != 0) return fail(h, "handle is not a CFM estimator");
+    if (!x1 || !z || !t || !mask || !mu || !c || !y_out || !loss_out) return fail(h, "st_cfm_loss: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const st_dims& d = h->d;
+    ST_LAUNCH(launch_cfm_mix(x1, z, t, sigma_min, B, (long)d.n_mel * T, y_out, s));
+    Workspace w;
+    if (ensure_ws(h, w, B, T, 0)) return 1;
+    // the estimator's (B, n_mel, T) output lands in the workspace (Kst[0] is only used by the ODE drivers)
+    if (st_estimator_forward(h, t, B, y_out, mask, mu, c, w.Kst[0], B, T, stream)) return 1;
+    ST_LAUNCH(launch_cfm_loss(w.Kst[0], x1, z, mask, sigma_min, B, d.n_mel, T, w.dscal, loss_out, s));
+    return 0;
+}
+
 // enqueues one complete solve on `s` (no host synchronisation, capturable into a CUDA graph)
 static int solve_impl(st_handle* h, Workspace& w, float* z_inout, const float* mu, const float* mask, const float* c,
                       const float* fake_content, const float* fake_speaker, float cfg_strength, const float* t_span_host,

@@ -109,6 +109,10 @@ cudaError_t launch_embed(const int64_t* ids, const int64_t* lens, const float* e
 cudaError_t launch_scaled_sumsq(const float* const* K, const float* coef, int n, const float* u, const float* v, float atol,
                                 float rtol, long numel, double* out, cudaStream_t s);
 // fp32 -> split bf16 planes
+cudaError_t launch_cfm_mix(const float* x1, const float* z, const float* t, float sigma_min, int B, long per_batch, float* y,
+                           cudaStream_t s);
+cudaError_t launch_cfm_loss(const float* v, const float* x1, const float* z, const float* mask, float sigma_min, int B, int C,
+                            int T, double* acc2, float* loss, cudaStream_t s);
 cudaError_t launch_split(const float* in, bf16* hi, bf16* lo, long numel, cudaStream_t s);
 
 // duration -> alignment -> mu_y expansion (align.cu; models/model.py:81-95)

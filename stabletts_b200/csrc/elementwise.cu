@@ -387,4 +387,64 @@ cudaError_t launch_split(const float* in, bf16* hi, bf16* lo, long numel, cudaSt
     return launch_k(split_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, s, in, hi, lo, numel);
 }
 
+// ----- conditional-flow-matching objective (models/flow_matching.py:69-100), forward value only -----
+// y = (1 - (1 - sigma_min) t_b) z + t_b x1  on (B, C, T) tensors, t per sample (:96)
+__global__ void cfm_mix_kernel(const float* __restrict__ x1, const float* __restrict__ z, const float* __restrict__ t,
+                               float sigma_min, long per_batch, long numel, float* __restrict__ y) {
+    pdl_trigger(); pdl_wait();
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numel) return;
+    const float tb = t[i / per_batch];
+    y[i] = (1.f - (1.f - sigma_min) * tb) * z[i] + tb * x1[i];
+}
+
+cudaError_t launch_cfm_mix(const float* x1, const float* z, const float* t, float sigma_min, int B, long per_batch, float* y,
+                           cudaStream_t s) {
+    const long n = (long)B * per_batch;
+    if (n == 0) return cudaSuccess;
+    return launch_k(cfm_mix_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, x1, z, t, sigma_min, per_batch, n, y);
+}
+
+// acc[0] += sum (v - u)^2 with u = x1 - (1 - sigma_min) z over ALL positions (the reference's mse_loss(reduction="sum")
+// runs over padded frames too, :97-99); acc[1] += sum(mask).  v, x1, z: (B, C, T); mask: (B, 1, T).
+__global__ void cfm_loss_kernel(const float* __restrict__ v, const float* __restrict__ x1, const float* __restrict__ z,
+                                const float* __restrict__ mask, float sigma_min, long numel, long n_mask,
+                                double* __restrict__ acc) {
+    pdl_trigger(); pdl_wait();
+    double a = 0.0, m = 0.0;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+        const float d = v[i] - (x1[i] - (1.f - sigma_min) * z[i]);
+        a += (double)d * (double)d;
+    }
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_mask; i += stride) m += (double)mask[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); m += __shfl_xor_sync(0xffffffffu, m, o); }
+    __shared__ double red[2][8];
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = m; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0.0, tm = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ta += red[0][w]; tm += red[1][w]; }
+        atomicAdd(acc, ta); atomicAdd(acc + 1, tm);
+    }
+}
+
+// loss = sumsq / (sum(mask) * C)   (:97-99)
+__global__ void cfm_loss_final_kernel(const double* __restrict__ acc, int C, float* __restrict__ loss) {
+    pdl_trigger(); pdl_wait();
+    if (threadIdx.x == 0 && blockIdx.x == 0) loss[0] = (float)(acc[0] / (acc[1] * (double)C));
+}
+
+cudaError_t launch_cfm_loss(const float* v, const float* x1, const float* z, const float* mask, float sigma_min, int B, int C,
+                            int T, double* acc2, float* loss, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(acc2, 0, 2 * sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    const long numel = (long)B * C * T, n_mask = (long)B * T;
+    const int blocks = (int)std::max<long>(1, std::min<long>((numel + 255) / 256, 592));
+    e = launch_k(cfm_loss_kernel, dim3(blocks), dim3(256), 0, s, v, x1, z, mask, sigma_min, numel, n_mask, acc2);
+    if (e != cudaSuccess) return e;
+    return launch_k(cfm_loss_final_kernel, dim3(1), dim3(32), 0, s, (const double*)acc2, C, loss);
+}
+
 }  // namespace st

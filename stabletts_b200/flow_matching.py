@@ -107,8 +107,35 @@ class CFMDecoder(nn.Module):
         uncond_output = self.estimator(t, x, mask, fake_content, fake_speaker)
         return uncond_output + cfg_strength * (cond_output - uncond_output)
 
+    @torch.no_grad()
     def compute_loss(self, x1, mask, mu, c):
-        """models/flow_matching.py:69-100 is the TRAINING objective (needs autograd through the
-        estimator).  Training is outside this library's hot-path scope."""
-        raise NotImplementedError("compute_loss (training) is out of scope for the inference-only B200 path; "
-                                  "train with the reference CFMDecoder and load the checkpoint here")
+        """models/flow_matching.py:69-100, FORWARD VALUE ONLY: ``(loss, y)`` as the reference returns them from
+        an ``eval()`` model under ``no_grad`` (a validation loss).  ``t`` and ``z`` are drawn exactly as the
+        reference draws them (global generator, ``rand`` then ``randn_like``, :92-96); the mix, the estimator at
+        per-sample ``t`` and the masked-sum reduction run in the CUDA library (``st_cfm_loss``).  Training —
+        dropout and the backward pass — is outside this library's scope: in ``train()``
+        mode this raises instead of silently returning a loss that cannot be differentiated."""
+        if self.training:
+            raise NotImplementedError("compute_loss in train() mode needs dropout + backward kernels, which are out of scope "
+                                      "for the inference-only B200 path; call .eval() for the validation loss, or train with "
+                                      "the reference CFMDecoder and load the checkpoint here")
+        est = self.estimator
+        if mu.device.type != "cuda":
+            raise RuntimeError("stabletts_b200 runs on CUDA (B200) only: there is no CPU fallback")
+        B, M, T = mu.shape
+        t = torch.rand([B, 1, 1], device=mu.device, dtype=mu.dtype)                  # :92
+        t = 1 - torch.cos(t * 0.5 * torch.pi)                                        # :93
+        z = torch.randn_like(x1)                                                     # :96
+        x1_ = est._f32c("x1", x1, (B, M, T))
+        z_ = est._f32c("z", z, (B, M, T))
+        t_ = t.reshape(B).float().contiguous()
+        mu_ = est._f32c("mu", mu, (B, est.cond_channels, T))
+        mask_ = est._f32c("mask", mask, (B, 1, T))
+        c_ = est._f32c("c", c, (B, est.gin_channels))
+        y = torch.empty_like(x1_)
+        loss = torch.empty((), device=mu.device, dtype=torch.float32)
+        lib, h, stream = est._prepare(mu_, B, T, 0)
+        rc = lib.st_cfm_loss(h, x1_.data_ptr(), z_.data_ptr(), t_.data_ptr(), mask_.data_ptr(), mu_.data_ptr(), c_.data_ptr(),
+                             float(self.sigma_min), y.data_ptr(), loss.data_ptr(), B, T, stream)
+        _lib.check(lib, h, rc, "st_cfm_loss")
+        return loss.to(mu.dtype), y.to(mu.dtype)

@@ -216,3 +216,25 @@ def test_general_binary_mask_and_weight_update(dev):
         m2.estimator.final_proj.bias.mul_(2.0)
     b = m2.estimator(*args)
     assert rel_errs(b, 2.0 * a)[0] < 1e-5
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["loss_b3_ragged", "loss_b1", "loss_b2_mel128"])
+def test_compute_loss_vs_reference_golden(name, engine, dev, golden_dir):
+    """CFMDecoder.compute_loss (eval, forward value) against the unmodified reference's compute_loss on the same
+    injected draws (oracle/make_golden_loss.py): y to fp32 rounding, loss to 1e-3 (measured ~1e-5)."""
+    from oracle.make_golden_loss import LOSS_CASES, loss_draws, inject_draws
+    cs = LOSS_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    m = model_for(cs["n_mel"], engine, dev)
+    inp = weights.make_inputs(cs["seed"], cs["lengths"], cs["T"], cs["n_mel"])
+    x1 = inp["x"] * inp["mask"]
+    u, z = loss_draws(cs["seed"], len(cs["lengths"]), cs["n_mel"], cs["T"])
+    with inject_draws(u, z):
+        loss, y = m.compute_loss(x1.to(dev), inp["mask"].to(dev), inp["mu"].to(dev), inp["c"].to(dev))
+    assert loss.dim() == 0 and y.shape == x1.shape
+    assert np.abs(y.cpu().numpy() - g["y"]).max() <= 2e-6
+    assert abs(float(loss) - float(g["loss"])) <= TOL[engine] * abs(float(g["loss"])), (float(loss), float(g["loss"]))
+    with pytest.raises(NotImplementedError):
+        m.train().compute_loss(x1.to(dev), inp["mask"].to(dev), inp["mu"].to(dev), inp["c"].to(dev))
+    m.eval()

@@ -75,8 +75,10 @@ def test_no_cpu_fallback(built):
         m.estimator(inp["t"], inp["x"], inp["mask"], inp["mu"], inp["c"])
     with pytest.raises(RuntimeError, match="CUDA"):
         m(inp["mu"], inp["mask"], 2, 1.0, inp["c"], "euler")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):          # eval mode: forward value, CUDA only
         m.compute_loss(inp["x"], inp["mask"], inp["mu"], inp["c"])
+    with pytest.raises(NotImplementedError):                 # train mode: dropout + backward are out of scope
+        m.train().compute_loss(inp["x"], inp["mask"], inp["mu"], inp["c"])
 
 
 def test_solver_names():

@@ -96,3 +96,19 @@ def test_padding_is_not_inert():
         a = R.estimator_forward(st, inp["t"], inp["x"], inp["mask"], inp["mu"], inp["c"])
         b = R.estimator_forward(st, inp["t"], x2, inp["mask"], inp["mu"], inp["c"])
     assert float((a - b)[:, :, :40].abs().max()) > 1e-3
+
+
+@pytest.mark.parametrize("name", ["loss_b3_ragged", "loss_b1", "loss_b2_mel128"])
+def test_cfm_loss_restatement_vs_reference_golden(name, golden_dir):
+    """oracle.cfm_loss against fixtures produced by the unmodified reference compute_loss (make_golden_loss.py)"""
+    from oracle.make_golden_loss import LOSS_CASES, loss_draws
+    cs = LOSS_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    st = weights.make_state(cases.WEIGHT_SEED, cs["n_mel"])
+    inp = weights.make_inputs(cs["seed"], cs["lengths"], cs["T"], cs["n_mel"])
+    x1 = inp["x"] * inp["mask"]
+    u, z = loss_draws(cs["seed"], len(cs["lengths"]), cs["n_mel"], cs["T"])
+    assert abs(weights.checksum([x1, inp["mu"], inp["c"], u, z]) - float(g["input_checksum"])) < 1e-6 * max(1.0, abs(float(g["input_checksum"])))
+    loss, y = R.cfm_loss(st, x1, inp["mask"], inp["mu"], inp["c"], u, z)
+    assert abs(float(loss) - float(g["loss"])) <= 2e-5 * abs(float(g["loss"]))
+    assert np.abs(y.numpy() - g["y"]).max() <= 1e-6
