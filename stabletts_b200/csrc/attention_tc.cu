@@ -52,7 +52,8 @@ constexpr int K_BYTES = AK * DH * 2;        // 8 KB per plane
 constexpr int P_BYTES = AQ * AK * 2;        // 16 KB per plane
 constexpr int ATT_SMEM = 2 * Q_BYTES + 4 * K_BYTES + 2 * K_BYTES + 2 * P_BYTES + 1024;   // 112 KB + barriers/alignment
 constexpr int TMEM_COLS_ATT = 256;          // S0 [0,64) S1 [64,128) O_A [128,192) O_B [192,256)
-constexpr float LAZY_THRESHOLD = 8.0f;      // log2 domain: p <= 2^8 between rescales
+constexpr float LAZY_THRESHOLD = 8.0f;      // log2 domain: p <= 2^8 between rescales (v3 kernel)
+constexpr float LAZY4 = 32.0f;              // v4 kernel: the running max moves only when a block max exceeds it by 2^32
 
 struct AttMaps { CUtensorMap q_hi, q_lo, kv_hi, kv_lo, vt_hi, vt_lo; };
 
@@ -572,43 +573,36 @@ attention_tc4_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
                 const int ka = k0 + lane;
                 bits = __ballot_sync(0xffffffffu, ka < kvlen && __ldg(mrow + min(ka, p.T - 1)) != 0.f);
             }
-            uint32_t hw[16], lw[16];                          // packed P half-row: 32 keys x (hi, lo)
-            float cand = -CUDART_INF_F, psum = 0.f;
+            // max first, then ONE exp pass (no optimistic retry): the row max of this half-block decides whether the
+            // running max moves.  It only moves when the block max exceeds the max in use by 2^LAZY4 — p and the
+            // partial sums stay far inside fp32/bf16 exponent range, so this is exact up to rounding and rare.
             bool waited_pv = (j == 0);
-            // single optimistic pass against the stale max; repeated once in the rare rescale case.
-            // (one code instance on purpose: the kernel must stay inside the instruction cache)
-#pragma unroll 1
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                const float m_eff = (m_used == -CUDART_INF_F) ? 0.f : m_used;
-                float c0 = -CUDART_INF_F, c1 = -CUDART_INF_F, ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;   // short dependency chains
+            auto load_scores = [&]() {
                 tmem_ld32(tS, v);
                 tmem_ld_wait();
                 if (need_mask) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) if (!((bits >> i) & 1u)) v[i] = 0xff800000u;     // -inf
                 }
+            };
+            load_scores();
+            float c0 = -CUDART_INF_F, c1 = -CUDART_INF_F;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-                    const float s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
-                    c0 = fmaxf(c0, fmaxf(s0, s1)); c1 = fmaxf(c1, fmaxf(s2, s3));
-                    const float p0 = ex2_approx(s0 - m_eff), p1 = ex2_approx(s1 - m_eff);
-                    const float p2 = ex2_approx(s2 - m_eff), p3 = ex2_approx(s3 - m_eff);
-                    ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
-                    split_bf16x2(p0, p1, hw[i / 2], lw[i / 2]);
-                    split_bf16x2(p2, p3, hw[i / 2 + 1], lw[i / 2 + 1]);
-                }
-                cand = fmaxf(c0, c1); psum = (ps0 + ps1) + (ps2 + ps3);
-                if (attempt == 1 || !__any_sync(0xffffffffu, cand > m_used + LAZY_THRESHOLD)) break;
-                const float m_new = fmaxf(m_used, cand);
-                const float factor = (m_new == -CUDART_INF_F) ? 1.f : ex2_approx(m_used - m_new);    // m_used = -inf -> 0
-                l_run *= factor;
+            for (int i = 0; i < 32; i += 4) {
+                c0 = fmaxf(c0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                c1 = fmaxf(c1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+            }
+            const float cand = fmaxf(c0, c1);
+            if (__any_sync(0xffffffffu, cand > m_used + LAZY4)) {
+                const float m_new = (cand > m_used + LAZY4) ? cand : m_used;     // rows below the threshold keep their max
+                const float factor = (m_new == -CUDART_INF_F || m_used == -CUDART_INF_F) ? 1.f : ex2_approx(m_used - m_new);
+                l_run *= factor;                                                  // (m_used = -inf: l_run = 0, O = 0)
                 if (j > 0) {                 // rescale this half's O accumulator in TMEM: no PV may be in flight
                     mbar_wait(pv_done, (j - 1) & 1);
                     tc_fence_after();
                     waited_pv = true;
 #pragma unroll 1
-                    for (int hh = 0; hh < 2; ++hh) {
+                    for (int hh = 0; hh < 2; ++hh) {          // (v is the scratch: the scores are re-read below)
                         tmem_ld32(tOh + hh * 32, v);
                         tmem_ld_wait();
 #pragma unroll
@@ -616,8 +610,24 @@ attention_tc4_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
                         tmem_st32(tOh + hh * 32, v);
                     }
                     tmem_st_wait();
+                    load_scores();
                 }
                 m_used = m_new;
+            }
+            uint32_t hw[16], lw[16];                          // packed P half-row: 32 keys x (hi, lo)
+            float psum;
+            {
+                const float m_eff = (m_used == -CUDART_INF_F) ? 0.f : m_used;
+                float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;   // short dependency chains
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float p0 = ex2_approx(__uint_as_float(v[i]) - m_eff), p1 = ex2_approx(__uint_as_float(v[i + 1]) - m_eff);
+                    const float p2 = ex2_approx(__uint_as_float(v[i + 2]) - m_eff), p3 = ex2_approx(__uint_as_float(v[i + 3]) - m_eff);
+                    ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
+                    split_bf16x2(p0, p1, hw[i / 2], lw[i / 2]);
+                    split_bf16x2(p2, p3, hw[i / 2 + 1], lw[i / 2 + 1]);
+                }
+                psum = (ps0 + ps1) + (ps2 + ps3);
             }
             l_run += psum;
             // P_j overwrites this thread's own 32 S_j columns in TMEM (hi in [0,16), lo in [16,32)): no shared-memory
