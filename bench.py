@@ -302,15 +302,16 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
         out = None
-        for _ in range(steps):
+        for i in range(steps):
             flush.zero_()
             out = fn()
-        e1.record()
+            ev[i + 1].record()
         torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([ev[0].elapsed_time(ev[steps])], device=dev)
+        timed.per_step = [round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(steps)]    # diagnostics (this rank)
         if world > 1:
             dist.barrier()
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -345,6 +346,7 @@ def main():
     torch.cuda.synchronize()
     l0 = model.estimator.launch_count()
     ms_dev, out_dev = timed(step_device, args.steps)
+    per_step_dev = list(timed.per_step)
     launches = model.estimator.launch_count() - l0
     if args.ncu_mode:
         if rank == 0:
@@ -356,6 +358,7 @@ def main():
     for _ in range(1):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
+    per_step_e2e = list(timed.per_step)
     clocks = sampler.stop() if rank == 0 else None
 
     # instrumented solve: per-class CUDA-event timing of every launch (roofline)
@@ -438,6 +441,7 @@ def main():
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 2),
+        "step_ms": {"value": per_step_dev[:32], "e2e": per_step_e2e[:32]},
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 split-bf16 conv-GEMM, all launches of one solve)",
                      "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
                      "traffic_note": "dram__bytes_read+write per launch, mean over the ncu --set full capture in profiles/gemm_traffic.json",
