@@ -171,6 +171,9 @@ int st_bench_conv(st_handle* h, int B, int Cin, int Cout, int T, int k, int epi,
 /* Masked multi-head attention with partial RoPE on packed qkv (B,T,3*hidden) -> (B,T,hidden). */
 int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* out, int B, int T,
                       void* stream);
+/* Debug hook: with STABLETTS_B200_ATT_TRACE=1 the attention kernel records clock64 stamps of one CTA's softmax and
+ * MMA warps per key block; this copies the last launch's [32 blocks][16 slots] table to the host. */
+int st_test_attention_trace(long long* host_out);
 
 #ifdef __cplusplus
 }

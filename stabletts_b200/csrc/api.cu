@@ -1171,6 +1171,8 @@ int st_bench_conv(st_handle* h, int B, int Cin, int Cout, int T, int k, int epi,
     return rc;
 }
 
+int st_test_attention_trace(long long* host_out) { return st::attention_tc_read_trace(host_out); }
+
 int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* out, int B, int T, void* stream) {
     if (!h) return 1;
     ST_CUDA(cudaSetDevice(h->device));

@@ -146,6 +146,7 @@ cudaError_t launch_attention_tc(const AttnArgs& a, const AttnTcScratch& sc, cuda
 // fp32 packed qkv -> RoPE'd, q-scaled split planes (what the QKV GEMM epilogue emits on the product path)
 cudaError_t launch_rope_split(const float* qkv, const float* rope_cs, bf16* hi, bf16* lo, int BB, int T, int H, cudaStream_t s);
 const char* attention_tc_last_error();
+int attention_tc_read_trace(long long* host_out);
 
 // ----------------------------------------------------------------------------------------------
 // Programmatic dependent launch: every kernel of the path (1) lets its successor start launching

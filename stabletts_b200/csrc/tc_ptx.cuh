@@ -34,11 +34,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"      // suspend-time hint: fewer spin issues
         "@P1 bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 // cluster-scope acquire variant: pairs with remote arrives / multicast commits from the peer CTA
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
