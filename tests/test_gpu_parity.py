@@ -238,3 +238,19 @@ def test_compute_loss_vs_reference_golden(name, engine, dev, golden_dir):
     with pytest.raises(NotImplementedError):
         m.train().compute_loss(x1.to(dev), inp["mask"].to(dev), inp["mu"].to(dev), inp["c"].to(dev))
     m.eval()
+
+
+def test_long_and_wide_shapes_vs_oracle(dev):
+    """BASELINE cfg3's longest bucket (T = 2000, ragged) and the reference's own n_mel = 128 at T = 1000, against the
+    oracle computed on the host in the same test (a few seconds of CPU): the maximum sizes of the path, not only
+    size-independent properties."""
+    for n_mel, lengths, T, seed in [(80, [2000, 1337], 2000, 91), (128, [1000, 777], 1000, 92)]:
+        st = weights.make_state(cases.WEIGHT_SEED, n_mel)
+        m = model_for(n_mel, "tcgen05", dev)
+        inp = weights.make_inputs(seed, lengths, T, n_mel, t_per_sample=True)
+        with torch.inference_mode():
+            ref = R.estimator_forward(st, inp["t"], inp["x"], inp["mask"], inp["mu"], inp["c"])
+        out = m.estimator(inp["t"].to(dev), inp["x"].to(dev), inp["mask"].to(dev), inp["mu"].to(dev), inp["c"].to(dev))
+        e = rel_errs(out, ref)
+        assert max(e) < 1e-3, (n_mel, T, e)
+        assert float((out.cpu() * (1 - inp["mask"])).abs().max()) == 0.0
