@@ -10,6 +10,7 @@
 //   v = (gamma*v + beta) * mask * gate + resid  -> fp32 and/or split-bf16 planes.
 #pragma once
 #include "common.cuh"
+#include <cstdlib>
 #include "tc_ptx.cuh"
 
 namespace st {
@@ -17,7 +18,7 @@ namespace st {
 struct TcParams {
     int n_src, Cs0, Cs1, taps, N, a_bmod, BB, T;
     int m_tiles_per_b, n_tiles, total_tiles;
-    int flags, B, film_H, c_clamp, resid_clamp, rope_H;
+    int flags, B, film_H, c_clamp, resid_clamp, rope_H, tap_outer;
     long film_bstride, gate_bstride;
     const float *bias, *mask, *film, *gate, *resid, *rope_cs;
     float* out_f32; bf16* out_hi; bf16* out_lo;
@@ -29,6 +30,9 @@ inline void fill_tc_params(TcParams& p, const GemmArgs& g) {
     p.film_bstride = g.film_bstride; p.gate_bstride = g.gate_bstride;
     p.bias = g.bias; p.mask = g.mask; p.film = g.film; p.gate = g.gate; p.resid = g.resid; p.rope_cs = g.rope_cs;
     p.out_f32 = g.out_f32; p.out_hi = g.out_hi; p.out_lo = g.out_lo;
+    static int tap_outer = -1;
+    if (tap_outer < 0) { const char* e = getenv("STABLETTS_B200_TAP_OUTER"); tap_outer = (e && e[0] == '1') ? 1 : 0; }
+    p.tap_outer = tap_outer;
 }
 
 // softmax scale folded into q: 1/sqrt(64) * log2(e) (attention runs in the exp2 domain)

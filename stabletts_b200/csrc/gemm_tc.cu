@@ -190,8 +190,13 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
                 const int bb = m_tile / p.m_tiles_per_b, t0 = (m_tile % p.m_tiles_per_b) * BLOCK_M;
                 const int ab = bb % p.a_bmod, n0 = n_tile * BN;
-                for (int tap = 0; tap < p.taps; ++tap) {
-                    for (int kb = 0; kb < kb_per_tap; ++kb) {
+                // channel block OUTER, tap INNER: the k taps of one channel block read the same A rows shifted by one
+                // frame, back to back, so taps 1.. hit L2 (tap-outer order re-read the whole A slab from HBM per tap)
+                // (p.tap_outer = 1 restores the old order for A/B runs: STABLETTS_B200_TAP_OUTER=1)
+                for (int it = 0; it < num_kb; ++it) {
+                    {
+                        const int kb = p.tap_outer ? it % kb_per_tap : it / p.taps;
+                        const int tap = p.tap_outer ? it / kb_per_tap : it % p.taps;
                         const int src = kb >= kb0 ? 1 : 0;
                         const int kc = (src ? kb - kb0 : kb) * BLOCK_K;          // channel offset inside the source
                         const int kw = (src ? p.Cs0 : 0) + kc;                   // column in the packed weight
