@@ -15,6 +15,7 @@
 #include "tc_ptx.cuh"
 #include "gemm_epilogue.cuh"
 #include <string>
+#include <cstdlib>
 
 namespace st {
 
@@ -27,22 +28,31 @@ namespace {
 using namespace ptx;
 
 constexpr int BM = 128;                 // rows per CTA (pair tile: 256)
-constexpr int BN2 = 256;                // pair tile width; each CTA stages 128 B rows
 constexpr int BK = 64;
 constexpr int UK = 16;
 constexpr int THREADS = 384;            // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue
-constexpr int TILE_BYTES = 128 * BK * 2;            // 16 KB: A plane tile and B-half plane tile
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // A_hi, A_lo, Bh_hi, Bh_lo = 64 KB
-constexpr int STAGES = 3;
-constexpr int TMEM_COLS = 512;                      // two 256-column accumulator stages
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 4096;
+constexpr int TILE_BYTES = 128 * BK * 2;            // 16 KB: one A plane tile (128 frames x 64 channels)
+
+// BN2 = pair tile width: 256 (each CTA stages 128 weight rows) or 128 (64 weight rows; twice as many, half as long
+// tiles — chosen when that shortens the partial last wave, e.g. N = 256 outputs at cfg1: 250 tiles = 3.4 waves of 74
+// CTA pairs -> 500 half tiles = 6.8 half waves)
+template <int BN2> struct Cfg2 {
+    static constexpr int B_TILE_BYTES = (BN2 / 2) * BK * 2;                  // B-half plane tile
+    static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;    // A_hi, A_lo, Bh_hi, Bh_lo: 64 / 48 KB
+    static constexpr int STAGES = BN2 == 256 ? 3 : 4;
+    static constexpr int TMEM_COLS = 2 * BN2;                                // two accumulator stages
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 4096;
+};
 
 struct Maps2 { CUtensorMap a_hi[2], a_lo[2], w_hi, w_lo; };
 
 typedef TcParams Params2;
 
+template <int BN2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
+    constexpr int B_TILE_BYTES = Cfg2<BN2>::B_TILE_BYTES, STAGE_BYTES = Cfg2<BN2>::STAGE_BYTES, STAGES = Cfg2<BN2>::STAGES;
+    constexpr int TMEM_COLS = Cfg2<BN2>::TMEM_COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -85,7 +95,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
             for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
                 const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
                 const int bb = m_tile / p.m_tiles_per_b, t0 = (m_tile % p.m_tiles_per_b) * (2 * BM) + (int)rank * BM;
-                const int ab = bb % p.a_bmod, n0 = n_tile * BN2 + (int)rank * 128;
+                const int ab = bb % p.a_bmod, n0 = n_tile * BN2 + (int)rank * (BN2 / 2);
                 // channel block OUTER, tap INNER: the k taps of one channel block read the same A rows shifted by one
                 // frame, back to back, so taps 1.. hit L2 (tap-outer order re-read the whole A slab from HBM per tap)
                 // (p.tap_outer = 1 restores the old order for A/B runs: STABLETTS_B200_TAP_OUTER=1)
@@ -102,7 +112,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
                         tma_load_3d_2sm(&maps.a_hi[src], &full_bar[stage], s, kc, t0 + tap - pad, ab);
                         tma_load_3d_2sm(&maps.a_lo[src], &full_bar[stage], s + TILE_BYTES, kc, t0 + tap - pad, ab);
                         tma_load_2d_2sm(&maps.w_hi, &full_bar[stage], s + 2 * TILE_BYTES, kw, tap * p.N + n0);
-                        tma_load_2d_2sm(&maps.w_lo, &full_bar[stage], s + 3 * TILE_BYTES, kw, tap * p.N + n0);
+                        tma_load_2d_2sm(&maps.w_lo, &full_bar[stage], s + 2 * TILE_BYTES + B_TILE_BYTES, kw, tap * p.N + n0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -124,7 +134,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
                     if (elect_one()) {
                         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                         const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + TILE_BYTES);
-                        const uint64_t b_hi = make_sw128_desc(sa + 2 * TILE_BYTES), b_lo = make_sw128_desc(sa + 3 * TILE_BYTES);
+                        const uint64_t b_hi = make_sw128_desc(sa + 2 * TILE_BYTES), b_lo = make_sw128_desc(sa + 2 * TILE_BYTES + B_TILE_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / UK; ++k) {
                             const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);
@@ -178,7 +188,6 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
     }
 }
 
-bool g_attr2 = false;
 std::string g_err2;
 
 }  // namespace
@@ -192,8 +201,36 @@ bool gemm_tc2_eligible(const GemmArgs& g, int num_sms) {
     return pair_tiles >= (num_sms / 2);
 }
 
+// pair-tile width: 128 when halving the tiles shortens the partial last wave by more than the ~3 % the narrower
+// MMAs and the doubled A re-reads (L2 hits) cost; STABLETTS_B200_TC2_BN=128|256 forces one (A/B runs)
+static int pick_bn2(const GemmArgs& g, int pairs) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("STABLETTS_B200_TC2_BN"); forced = e ? atoi(e) : 0; }
+    if (forced == 128 || forced == 256) return forced;
+    const long m_tiles = (long)g.BB * ((g.T + 2 * BM - 1) / (2 * BM));
+    const long t256 = m_tiles * ((g.N + 255) / 256), t128 = m_tiles * ((g.N + 127) / 128);
+    const double w256 = (double)((t256 + pairs - 1) / pairs), w128 = 0.515 * (double)((t128 + pairs - 1) / pairs);
+    return w128 < 0.97 * w256 ? 128 : 256;
+}
+
+template <int BN2>
+static cudaError_t launch_tc2_bn(const Maps2& maps, Params2& p, const GemmArgs& g, int pairs, cudaStream_t s) {
+    static bool attr = false;
+    p.n_tiles = (g.N + BN2 - 1) / BN2;
+    p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN2>::SMEM_BYTES);
+        if (e != cudaSuccess) { g_err2 = "cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc2_kernel"; return e; }
+        attr = true;
+    }
+    const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
+    return launch_k(gemm_tc2_kernel<BN2>, dim3(2 * clusters), dim3(THREADS), (size_t)Cfg2<BN2>::SMEM_BYTES, s, maps, p);
+}
+
 cudaError_t launch_gemm_tc2(const GemmArgs& g, int num_sms, cudaStream_t s) {
     Maps2 maps;
+    const int pairs = num_sms / 2;
+    const int bn2 = pick_bn2(g, pairs);
     for (int i = 0; i < g.n_src; ++i) {
         if (!tmap_encode_bf16(g.A_hi[i], 3, (uint64_t)g.Cs[i], (uint64_t)g.T, (uint64_t)g.a_bmod, BK, BM, &maps.a_hi[i]) ||
             !tmap_encode_bf16(g.A_lo[i], 3, (uint64_t)g.Cs[i], (uint64_t)g.T, (uint64_t)g.a_bmod, BK, BM, &maps.a_lo[i])) {
@@ -201,23 +238,14 @@ cudaError_t launch_gemm_tc2(const GemmArgs& g, int num_sms, cudaStream_t s) {
         }
     }
     if (g.n_src == 1) { maps.a_hi[1] = maps.a_hi[0]; maps.a_lo[1] = maps.a_lo[0]; }
-    if (!tmap_encode_bf16(g.W_hi, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BK, 128, &maps.w_hi) ||
-        !tmap_encode_bf16(g.W_lo, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BK, 128, &maps.w_lo)) {
+    if (!tmap_encode_bf16(g.W_hi, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BK, bn2 / 2, &maps.w_hi) ||
+        !tmap_encode_bf16(g.W_lo, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BK, bn2 / 2, &maps.w_lo)) {
         g_err2 = gemm_tc_last_error(); return cudaErrorInvalidValue;
     }
     Params2 p;
     fill_tc_params(p, g);
     p.m_tiles_per_b = (g.T + 2 * BM - 1) / (2 * BM);
-    p.n_tiles = (g.N + BN2 - 1) / BN2;
-    p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
-    if (!g_attr2) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) { g_err2 = "cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc2_kernel"; return e; }
-        g_attr2 = true;
-    }
-    const int pairs = num_sms / 2;
-    const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
-    return launch_k(gemm_tc2_kernel, dim3(2 * clusters), dim3(THREADS), (size_t)SMEM_BYTES, s, maps, p);
+    return bn2 == 128 ? launch_tc2_bn<128>(maps, p, g, pairs, s) : launch_tc2_bn<256>(maps, p, g, pairs, s);
 }
 
 }  // namespace st
