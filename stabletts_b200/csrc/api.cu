@@ -50,7 +50,6 @@ struct Workspace {
     float* Kst[10] = {};               // RK stage derivatives (+ spare state buffers for the adaptive solver)
     double* dscal = nullptr;           // device scalar for norm reductions
     int* kvlen = nullptr; int* prefix = nullptr;
-    AttnTcScratch att;
     float *rope_cs = nullptr, *temb = nullptr, *tmid = nullptr, *tvec = nullptr, *film = nullptr, *ada = nullptr;
     float *cin = nullptr;    // (Bc, gin): c rows + fake_speaker row
     // host staging for st_solve_host
@@ -231,10 +230,6 @@ void layout_ws(const st_handle* h, Workspace& w, void* base, size_t cap, int B, 
     mk(w.Hid, bbt, d.filter, !tc, tc);
     w.kvlen = bp.take<int>(B);
     w.prefix = bp.take<int>(B);
-    if (tc && getenv("STABLETTS_B200_VT")) {
-        const size_t vt = attention_tc_scratch_elems(w.BB, T, d.hidden);
-        w.att.vt_hi = bp.take<bf16>(vt); w.att.vt_lo = bp.take<bf16>(vt);
-    }
     w.rope_cs = bp.take<float>((size_t)T * 32);
     w.temb = bp.take<float>((size_t)w.NT * d.hidden);
     w.tmid = bp.take<float>((size_t)w.NT * d.filter);
@@ -366,7 +361,7 @@ int dit_block_core(st_handle* h, Workspace& w, int l, LnArgs ln, const float* ad
         a.out_f32 = w.AO.f32; a.out_hi = w.AO.hi; a.out_lo = w.AO.lo;
         a.BB = w.BB; a.B = w.B; a.T = w.T; a.H = H; a.n_heads = d.n_heads;
         if (h->engine == ST_ENGINE_TCGEN05) {
-            ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_tc(a, w.att, s));
+            ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_tc(a, s));
         } else {
             ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_simt(a, s));
         }
@@ -1181,13 +1176,9 @@ int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* 
     int *kvlen, *prefix; float* cs;
     ST_CUDA(cudaMalloc(&kvlen, sizeof(int) * B)); ST_CUDA(cudaMalloc(&prefix, sizeof(int) * B));
     ST_CUDA(cudaMalloc(&cs, sizeof(float) * T * 32));
-    AttnTcScratch sc;
     bf16 *qh = nullptr, *ql = nullptr;
-    const size_t nq = (size_t)B * T * 3 * h->d.hidden, vt = attention_tc_scratch_elems(B, T, h->d.hidden);
-    if (tc) {
-        ST_CUDA(cudaMalloc(&qh, nq * 2)); ST_CUDA(cudaMalloc(&ql, nq * 2));
-        ST_CUDA(cudaMalloc(&sc.vt_hi, vt * 2)); ST_CUDA(cudaMalloc(&sc.vt_lo, vt * 2));
-    }
+    const size_t nq = (size_t)B * T * 3 * h->d.hidden;
+    if (tc) { ST_CUDA(cudaMalloc(&qh, nq * 2)); ST_CUDA(cudaMalloc(&ql, nq * 2)); }
     int rc = 0;
     do {
         if (launch_mask_lengths(mask, kvlen, prefix, B, T, s) != cudaSuccess || launch_rope_table(cs, T, 32, s) != cudaSuccess) {
@@ -1197,14 +1188,14 @@ int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* 
         a.qkv = qkv; a.qkv_hi = qh; a.qkv_lo = ql; a.rope_cs = cs; a.mask = mask; a.kvlen = kvlen; a.prefix = prefix; a.out_f32 = out;
         a.BB = B; a.B = B; a.T = T; a.H = h->d.hidden; a.n_heads = h->d.n_heads;
         if (tc && launch_rope_split(qkv, cs, qh, ql, B, T, h->d.hidden, s) != cudaSuccess) { rc = fail(h, "rope_split failed"); break; }
-        cudaError_t e = tc ? launch_attention_tc(a, sc, s) : launch_attention_simt(a, s);
+        cudaError_t e = tc ? launch_attention_tc(a, s) : launch_attention_simt(a, s);
         if (e != cudaSuccess) { rc = fail(h, std::string("attention launch failed: ") + cudaGetErrorString(e) + " / " + attention_tc_last_error()); break; }
     } while (0);
     cudaStreamSynchronize(s);
     cudaError_t e = cudaGetLastError();
     if (!rc && e != cudaSuccess) rc = fail(h, std::string("st_test_attention: ") + cudaGetErrorString(e));
     cudaFree(kvlen); cudaFree(prefix); cudaFree(cs);
-    if (tc) { cudaFree(qh); cudaFree(ql); cudaFree(sc.vt_hi); cudaFree(sc.vt_lo); }
+    if (tc) { cudaFree(qh); cudaFree(ql); }
     return rc;
 }
 

@@ -9,18 +9,14 @@
 //     V tile  [ 64 keys   ][64 dims]  channels [2H + 64h, ...)      MN-major B operand of O += P·V
 // One CTA per (128-query tile, head, batch row); warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM
 // alloc), warps 2-9 = softmax: TWO threads per query row, each owning one 32-key half of every 64-key
-// block with its OWN running max, row sum and O accumulator (O_A / O_B in TMEM; P·V is issued as two
-// K=32 halves), merged exactly at the end — no per-block exchange between the halves, half the serial
-// softmax latency per block, and the S row is read straight from TMEM (no cross-thread reductions).
-//   * S is double-buffered in TMEM and K in shared memory: S_{j+1}, S_{j+2} run on the tensor core
-//     while the softmax warps work on S_j;
-//   * O accumulates in TMEM (PV_j issued with accumulate) and the running max is LAZY: exponentials
-//     use a stale max m_used; O and l are rescaled (tcgen05.ld/st) only when a block max exceeds it
-//     by more than 2^8, which after the first block is rare;
-//   * single softmax pass: p = ex2(s - m_used) is computed optimistically together with the block max
-//     and only redone in the rare rescale case; P goes to shared memory as split-bf16 in the 128B
-//     swizzled K-major layout the P·V MMA reads.
-//   112 KB smem + 256 TMEM columns per CTA -> two CTAs per SM.
+// block; the S row is read straight from TMEM (no cross-thread reductions inside a half).
+//   * S is double-buffered in TMEM and K, V in shared memory;
+//   * O accumulates in TMEM (PV_j issued with accumulate) and the running max is LAZY: the block max is
+//     reduced first and the max in use moves (O and l rescaled through tcgen05.ld/st) only when it is
+//     exceeded by 2^32 — one exp pass per block, never a retry;
+//   * P (split-bf16) overwrites the thread's own S columns in TMEM and is the A operand of P·V.
+// Two kernels: attention_tc5_kernel (default: Q also in TMEM, one O accumulator, per-block max exchange
+// between the two threads of a row) and attention_tc4_kernel (A/B: Q tile in shared memory, O_A / O_B).
 // Mask semantics: keys with mask == 0 get probability exactly 0; query rows with mask == 0 are written
 // as 0 (the reference multiplies them by the mask afterwards, :111).
 #include "common.cuh"
@@ -49,13 +45,10 @@ constexpr int DH = 64;
 constexpr int A_THREADS = 320;            // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (2 warps per TMEM lane quarter)
 constexpr int Q_BYTES = AQ * DH * 2;        // 16 KB per plane
 constexpr int K_BYTES = AK * DH * 2;        // 8 KB per plane
-constexpr int P_BYTES = AQ * AK * 2;        // 16 KB per plane
-constexpr int ATT_SMEM = 2 * Q_BYTES + 4 * K_BYTES + 2 * K_BYTES + 2 * P_BYTES + 1024;   // 112 KB + barriers/alignment
 constexpr int TMEM_COLS_ATT = 256;          // S0 [0,64) S1 [64,128) O_A [128,192) O_B [192,256)
-constexpr float LAZY_THRESHOLD = 8.0f;      // log2 domain: p <= 2^8 between rescales (v3 kernel)
-constexpr float LAZY4 = 32.0f;              // v4 kernel: the running max moves only when a block max exceeds it by 2^32
+constexpr float LAZY4 = 32.0f;              // log2 domain: the running max moves only when a block max exceeds it by 2^32
 
-struct AttMaps { CUtensorMap q_hi, q_lo, kv_hi, kv_lo, vt_hi, vt_lo; };
+struct AttMaps { CUtensorMap q_hi, q_lo, kv_hi, kv_lo; };
 
 struct AttParams {
     int BB, B, T, H, n_heads;
@@ -119,291 +112,6 @@ __global__ void rope_split_kernel(const float* __restrict__ qkv, const float* __
     *reinterpret_cast<uint32_t*>(lo + row * H3 + c) = l2;
 }
 
-// fallback only (STABLETTS_B200_VT=1): V part of the planes -> [BB*nh][64][Tpad] (keys contiguous)
-__global__ void vt_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, bf16* __restrict__ vt_hi,
-                          bf16* __restrict__ vt_lo, int T, int Tpad, int H, int n_heads) {
-    __shared__ bf16 sh[32][DH + 2], sl[32][DH + 2];
-    const int bb = blockIdx.z, h = blockIdx.y, t0 = blockIdx.x * 32;
-    for (int i = threadIdx.x; i < 32 * DH; i += blockDim.x) {
-        const int r = i / DH, d = i % DH, t = t0 + r;
-        const long src = ((long)bb * T + t) * 3 * H + 2 * H + h * DH + d;
-        sh[r][d] = t < T ? hi[src] : __float2bfloat16(0.f);
-        sl[r][d] = t < T ? lo[src] : __float2bfloat16(0.f);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 32 * DH; i += blockDim.x) {
-        const int d = i / 32, r = i % 32, t = t0 + r;
-        if (t < Tpad) {
-            const long dst = (((long)bb * n_heads + h) * DH + d) * Tpad + t;
-            vt_hi[dst] = sh[r][d]; vt_lo[dst] = sl[r][d];
-        }
-    }
-}
-
-// ----------------------------------------------------------------------------------------------
-template <bool V_MN>
-__global__ void __launch_bounds__(A_THREADS, 2)
-attention_tc_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);          // barriers + TMEM slot live in the alignment slack
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 160 + 1023) & ~uintptr_t(1023));
-    uint8_t* sQh = smem;                 uint8_t* sQl = sQh + Q_BYTES;
-    uint8_t* sK = sQl + Q_BYTES;         // ring of 2: [hi 8K | lo 8K]
-    uint8_t* sVh = sK + 4 * K_BYTES;     uint8_t* sVl = sVh + K_BYTES;
-    uint8_t* sPh = sVl + K_BYTES;        uint8_t* sPl = sPh + P_BYTES;
-    uint64_t *q_full = bars, *k_full = bars + 1 /*[2]*/, *k_empty = bars + 3 /*[2]*/, *v_full = bars + 5,
-             *pv_done = bars + 6, *s_full = bars + 7 /*[2]*/, *p_full = bars + 9;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-    if (sPl + P_BYTES > smem_raw + ATT_SMEM) __trap();               // dynamic smem base less aligned than assumed
-    pdl_trigger(); pdl_wait();         // (this kernel's prologue is tiny: wait up front, before the kvlen read)
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bb = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
-    const int b = bb % p.B;
-    const int kvlen = p.kvlen[b];
-    const int cq = h * DH, ck = p.H + h * DH, cv = 2 * p.H + h * DH;     // channel offsets of this head
-
-    if (q0 >= kvlen) {
-        // whole query tile is padding (or the utterance is empty): exact zeros, no pipeline needed
-        for (int i = threadIdx.x; i < AQ * (DH / 4); i += A_THREADS) {
-            const int r = i / (DH / 4), c4 = (i % (DH / 4)) * 4, t = q0 + r;
-            if (t < p.T) {
-                const long o = ((long)bb * p.T + t) * p.H + h * DH + c4;
-                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.out_hi) { *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(0, 0); *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(0, 0); }
-            }
-        }
-        return;
-    }
-    const int nb = (kvlen + AK - 1) / AK;
-
-    if (warp == 0 && lane == 0) {
-        for (int i = 0; i < 10; ++i) mbar_init(&bars[i], i == 9 ? 8 : 1);      // p_full: one arrive per softmax warp
-        mbar_fence_init();
-    }
-    if (warp == 1) tmem_alloc_1sm<TMEM_COLS_ATT>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_O = tmem_base + 128;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            mbar_expect_tx(q_full, 2 * Q_BYTES);
-            tma_load_3d(&maps.q_hi, q_full, sQh, cq, q0, bb);
-            tma_load_3d(&maps.q_lo, q_full, sQl, cq, q0, bb);
-            for (int j = 0; j < nb; ++j) {
-                const int slot = j & 1;
-                mbar_wait(&k_empty[slot], ((j >> 1) & 1) ^ 1);
-                mbar_expect_tx(&k_full[slot], 2 * K_BYTES);
-                tma_load_3d(&maps.kv_hi, &k_full[slot], sK + slot * 2 * K_BYTES, ck, j * AK, bb);
-                tma_load_3d(&maps.kv_lo, &k_full[slot], sK + slot * 2 * K_BYTES + K_BYTES, ck, j * AK, bb);
-                mbar_wait(pv_done, (j & 1) ^ 1);                 // PV_{j-1} finished reading V (and P)
-                mbar_expect_tx(v_full, 2 * K_BYTES);
-                if (V_MN) {
-                    tma_load_3d(&maps.kv_hi, v_full, sVh, cv, j * AK, bb);
-                    tma_load_3d(&maps.kv_lo, v_full, sVl, cv, j * AK, bb);
-                } else {
-                    tma_load_3d(&maps.vt_hi, v_full, sVh, j * AK, 0, bb * p.n_heads + h);
-                    tma_load_3d(&maps.vt_lo, v_full, sVl, j * AK, 0, bb * p.n_heads + h);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        constexpr uint32_t idesc_s = att_idesc(false), idesc_pv = att_idesc(V_MN);
-        // P·V k-step of 16 keys: K-major V^T tile -> +32 B inside the row; MN-major V tile -> 16 rows = +2048 B
-        constexpr uint64_t v_adv = V_MN ? (uint64_t)((16 * 128) >> 4) : 2;
-        const uint64_t dQh = make_sw128_desc(smem_u32(sQh)), dQl = make_sw128_desc(smem_u32(sQl));
-        const uint64_t dVh = make_sw128_desc(smem_u32(sVh)), dVl = make_sw128_desc(smem_u32(sVl));
-        const uint64_t dPh = make_sw128_desc(smem_u32(sPh)), dPl = make_sw128_desc(smem_u32(sPl));
-        auto issue_S = [&](int j) {          // S_j -> TMEM buffer j&1, from K ring slot j&1
-            const int slot = j & 1;
-            const uint64_t dKh = make_sw128_desc(smem_u32(sK + slot * 2 * K_BYTES));
-            const uint64_t dKl = make_sw128_desc(smem_u32(sK + slot * 2 * K_BYTES + K_BYTES));
-            const uint32_t tS = tmem_base + slot * 64;
-#pragma unroll
-            for (int k = 0; k < DH / 16; ++k) {
-                const uint64_t adv = (uint64_t)(k * 2);
-                umma_bf16(tS, dQl + adv, dKh + adv, idesc_s, k != 0);
-                umma_bf16(tS, dQh + adv, dKl + adv, idesc_s, 1);
-                umma_bf16(tS, dQh + adv, dKh + adv, idesc_s, 1);
-            }
-            umma_commit(&k_empty[slot]);
-            umma_commit(&s_full[slot]);
-        };
-        mbar_wait(q_full, 0);
-        for (int j = 0; j < 2 && j < nb; ++j) {
-            mbar_wait(&k_full[j], 0);
-            tc_fence_after();
-            if (elect_one()) issue_S(j);
-            __syncwarp();
-        }
-        for (int j = 0; j < nb; ++j) {
-            mbar_wait(p_full, j & 1);
-            mbar_wait(v_full, j & 1);
-            tc_fence_after();
-            if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < AK / 16; ++k) {            // keys [0,32) -> O_A, keys [32,64) -> O_B
-                    const uint64_t pa = (uint64_t)(k * 2), va = (uint64_t)k * v_adv;
-                    const uint32_t tO = tmem_O + (k >> 1) * 64;
-                    umma_bf16(tO, dPl + pa, dVh + va, idesc_pv, (j != 0) || (k & 1));
-                    umma_bf16(tO, dPh + pa, dVl + va, idesc_pv, 1);
-                    umma_bf16(tO, dPh + pa, dVh + va, idesc_pv, 1);
-                }
-                umma_commit(pv_done);
-            }
-            __syncwarp();
-            if (j + 2 < nb) {                // S buffer j&1 was consumed by softmax_j (implied by p_full_j)
-                mbar_wait(&k_full[j & 1], ((j + 2) >> 1) & 1);
-                tc_fence_after();
-                if (elect_one()) issue_S(j + 2);
-                __syncwarp();
-            }
-        }
-    } else {
-        // ================= softmax / epilogue: thread <-> (query row, key half) =================
-        const int wq = warp & 3;                       // TMEM lane quarter (warps w and w+4 share it)
-        const int half = (warp - 2) >> 2;              // 0: keys [0,32) of every block -> O_A, 1: keys [32,64) -> O_B
-        const int r = wq * 32 + lane;
-        const int t = q0 + r;
-        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        const uint32_t tOh = tmem_O + half * 64 + lane_addr;     // this thread's O accumulator row (64 columns)
-        const int prefix = p.prefix[b];
-        const float* mrow = p.mask + (long)b * p.T;
-        float m_used = -CUDART_INF_F, l_run = 0.f;
-        uint8_t* pr_hi = sPh + r * 128;
-        uint8_t* pr_lo = sPl + r * 128;
-        const int sw = r & 7;
-        uint32_t v[32];
-
-        for (int j = 0; j < nb; ++j) {
-            const int k0 = j * AK + half * 32;
-            const uint32_t tS = tmem_base + (j & 1) * 64 + half * 32 + lane_addr;
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            // key validity of this half-block as a warp-uniform 32-bit word (only blocks reaching past the
-            // all-ones prefix of the mask need it; interior blocks skip the test entirely)
-            const bool need_mask = k0 + 32 > prefix;
-            uint32_t bits = 0xffffffffu;
-            if (need_mask) {
-                const int ka = k0 + lane;
-                bits = __ballot_sync(0xffffffffu, ka < kvlen && __ldg(mrow + min(ka, p.T - 1)) != 0.f);
-            }
-            uint32_t hw[16], lw[16];                          // packed P half-row: 32 keys x (hi, lo)
-            float cand = -CUDART_INF_F, psum = 0.f;
-            bool waited_pv = (j == 0);
-            // single optimistic pass against the stale max; repeated once in the rare rescale case.
-            // (one code instance on purpose: the kernel must stay inside the instruction cache)
-#pragma unroll 1
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                const float m_eff = (m_used == -CUDART_INF_F) ? 0.f : m_used;
-                float c0 = -CUDART_INF_F, c1 = -CUDART_INF_F, ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;   // short dependency chains
-                tmem_ld32(tS, v);
-                tmem_ld_wait();
-                if (need_mask) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) if (!((bits >> i) & 1u)) v[i] = 0xff800000u;     // -inf
-                }
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-                    const float s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
-                    c0 = fmaxf(c0, fmaxf(s0, s1)); c1 = fmaxf(c1, fmaxf(s2, s3));
-                    const float p0 = ex2_approx(s0 - m_eff), p1 = ex2_approx(s1 - m_eff);
-                    const float p2 = ex2_approx(s2 - m_eff), p3 = ex2_approx(s3 - m_eff);
-                    ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
-                    split_bf16x2(p0, p1, hw[i / 2], lw[i / 2]);
-                    split_bf16x2(p2, p3, hw[i / 2 + 1], lw[i / 2 + 1]);
-                }
-                cand = fmaxf(c0, c1); psum = (ps0 + ps1) + (ps2 + ps3);
-                if (attempt == 1 || !__any_sync(0xffffffffu, cand > m_used + LAZY_THRESHOLD)) break;
-                const float m_new = fmaxf(m_used, cand);
-                const float factor = (m_new == -CUDART_INF_F) ? 1.f : ex2_approx(m_used - m_new);    // m_used = -inf -> 0
-                l_run *= factor;
-                if (j > 0) {                 // rescale this half's O accumulator in TMEM: no PV may be in flight
-                    mbar_wait(pv_done, (j - 1) & 1);
-                    tc_fence_after();
-                    waited_pv = true;
-#pragma unroll 1
-                    for (int hh = 0; hh < 2; ++hh) {
-                        tmem_ld32(tOh + hh * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
-                        tmem_st32(tOh + hh * 32, v);
-                    }
-                    tmem_st_wait();
-                }
-                m_used = m_new;
-            }
-            l_run += psum;
-            if (!waited_pv) mbar_wait(pv_done, (j - 1) & 1);             // P buffer free (PV_{j-1} retired)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {                                 // this half's 4 chunks of 8 keys (16 B of bf16)
-                const int off = (((half * 4 + c) ^ sw) << 4);             // 128B swizzle: chunk ^= (row & 7)
-                *reinterpret_cast<uint4*>(pr_hi + off) = make_uint4(hw[c * 4], hw[c * 4 + 1], hw[c * 4 + 2], hw[c * 4 + 3]);
-                *reinterpret_cast<uint4*>(pr_lo + off) = make_uint4(lw[c * 4], lw[c * 4 + 1], lw[c * 4 + 2], lw[c * 4 + 3]);
-            }
-            // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
-        }
-        // O_A and O_B complete after PV_{nb-1}; merge the two halves of every row exactly:
-        //   out = (O_A 2^(mA-m) + O_B 2^(mB-m)) / (lA 2^(mA-m) + lB 2^(mB-m)),  m = max(mA, mB)
-        mbar_wait(pv_done, (nb - 1) & 1);
-        tc_fence_after();
-        float2* xch = reinterpret_cast<float2*>(sPh);                     // P buffer is free now: [half][row] (m, l)
-        xch[half * AQ + r] = make_float2(m_used, l_run);
-        asm volatile("bar.sync 1, 256;" ::: "memory");                    // the 8 softmax warps only
-        const float2 oth = xch[(half ^ 1) * AQ + r];
-        const float mA = half ? oth.x : m_used, lA = half ? oth.y : l_run;
-        const float mB = half ? m_used : oth.x, lB = half ? l_run : oth.y;
-        const float mm = fmaxf(mA, mB);
-        const float fA = (mA == -CUDART_INF_F) ? 0.f : ex2_approx(mA - mm), fB = (mB == -CUDART_INF_F) ? 0.f : ex2_approx(mB - mm);
-        const float lsum = lA * fA + lB * fB;
-        const bool valid = t < p.T && mrow[min(t, p.T - 1)] != 0.f && lsum > 0.f;
-        const float inv = valid ? 1.0f / lsum : 0.f;
-        const float wA = fA * inv, wB = fB * inv;
-        // this thread emits output dims [32*half, 32*half + 32) of its row
-        uint32_t va[32];
-        tmem_ld32(tmem_O + lane_addr + half * 32, va);
-        tmem_ld32(tmem_O + 64 + lane_addr + half * 32, v);
-        tmem_ld_wait();
-        if (t < p.T) {
-            const long o = ((long)bb * p.T + t) * p.H + h * DH + half * 32;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(va[c * 8 + e]) * wA + __uint_as_float(v[c * 8 + e]) * wB;
-                const long oc = o + c * 8;
-                if (p.out_f32) {
-                    *reinterpret_cast<float4*>(p.out_f32 + oc) = make_float4(f[0], f[1], f[2], f[3]);
-                    *reinterpret_cast<float4*>(p.out_f32 + oc + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                }
-                if (p.out_hi) {
-                    uint32_t h4[4], l4[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) split_bf16x2(f[2 * e], f[2 * e + 1], h4[e], l4[e]);
-                    *reinterpret_cast<uint4*>(p.out_hi + oc) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-                    *reinterpret_cast<uint4*>(p.out_lo + oc) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc_1sm<TMEM_COLS_ATT>(tmem_base);
-    }
-}
-
 // ==============================================================================================
 // v4: P in TENSOR MEMORY.  Each softmax thread overwrites its own 32 fp32 S columns with its packed split-bf16
 // P half-row (tcgen05.st) and the P·V MMAs take their A operand from TMEM (tcgen05.mma [d], [a_tmem], b_desc):
@@ -423,7 +131,6 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 
 // ----------------------------------------------------------------------------------------------
-template <bool V_MN>
 __global__ void __launch_bounds__(A_THREADS, 2)
 attention_tc4_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -483,19 +190,13 @@ attention_tc4_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
                 mbar_wait(&v_empty[slot], ((j >> 1) & 1) ^ 1);   // PV_{j-2} finished reading this V slot
                 mbar_expect_tx(&v_full[slot], 2 * K_BYTES);
                 uint8_t* sVh = sV + slot * 2 * K_BYTES; uint8_t* sVl = sVh + K_BYTES;
-                if (V_MN) {
-                    tma_load_3d(&maps.kv_hi, &v_full[slot], sVh, cv, j * AK, bb);
-                    tma_load_3d(&maps.kv_lo, &v_full[slot], sVl, cv, j * AK, bb);
-                } else {
-                    tma_load_3d(&maps.vt_hi, &v_full[slot], sVh, j * AK, 0, bb * p.n_heads + h);
-                    tma_load_3d(&maps.vt_lo, &v_full[slot], sVl, j * AK, 0, bb * p.n_heads + h);
-                }
+                tma_load_3d(&maps.kv_hi, &v_full[slot], sVh, cv, j * AK, bb);
+                tma_load_3d(&maps.kv_lo, &v_full[slot], sVl, cv, j * AK, bb);
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc_s = att_idesc(false), idesc_pv = att_idesc(V_MN);
-        // P·V k-step of 16 keys: K-major V^T tile -> +32 B inside the row; MN-major V tile -> 16 rows = +2048 B
-        constexpr uint64_t v_adv = V_MN ? (uint64_t)((16 * 128) >> 4) : 2;
+        constexpr uint32_t idesc_s = att_idesc(false), idesc_pv = att_idesc(true);
+        constexpr uint64_t v_adv = (uint64_t)((16 * 128) >> 4);      // P·V k-step of 16 keys of the MN-major V tile: +2048 B
         const uint64_t dQh = make_sw128_desc(smem_u32(sQh)), dQl = make_sw128_desc(smem_u32(sQl));
         auto issue_S = [&](int j) {          // S_j -> TMEM buffer j&1, from K ring slot j&1
             const int slot = j & 1;
@@ -1017,11 +718,6 @@ int attention_tc_read_trace(long long* host_out) {
     return cudaMemcpy(host_out, g_att_trace, 32 * 16 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
 }
 
-size_t attention_tc_scratch_elems(int BB, int T, int H) {
-    const int Tpad = (T + 7) & ~7;
-    return (size_t)BB * H * Tpad;             // V^T fallback planes
-}
-
 cudaError_t launch_rope_split(const float* qkv, const float* rope_cs, bf16* hi, bf16* lo, int BB, int T, int H, cudaStream_t s) {
     const long rows = (long)BB * T, n = rows * (3 * H / 2);
     if (n == 0) return cudaSuccess;
@@ -1030,14 +726,11 @@ cudaError_t launch_rope_split(const float* qkv, const float* rope_cs, bf16* hi, 
 }
 
 // a.qkv_hi / a.qkv_lo: RoPE'd, q-scaled split planes (BB, T, 3H)
-cudaError_t launch_attention_tc(const AttnArgs& a, const AttnTcScratch& sc, cudaStream_t s) {
+cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t s) {
     std::lock_guard<std::mutex> lk(g_att_mu);
     if (a.H != a.n_heads * DH) return cudaErrorInvalidValue;
     if (a.BB == 0 || a.T == 0) return cudaSuccess;
     if (!a.qkv_hi || !a.qkv_lo) { g_att_err = "split qkv planes missing"; return cudaErrorInvalidValue; }
-    static int use_vt = -1;
-    if (use_vt < 0) { const char* e = getenv("STABLETTS_B200_VT"); use_vt = (e && !strcmp(e, "1")) ? 1 : 0; }
-    const int Tpad = (a.T + 7) & ~7;
     AttMaps maps;
     const uint64_t C3 = 3 * (uint64_t)a.H;
     bool ok = true;
@@ -1045,15 +738,6 @@ cudaError_t launch_attention_tc(const AttnArgs& a, const AttnTcScratch& sc, cuda
     ok = ok && tmap_encode_bf16(a.qkv_lo, 3, C3, (uint64_t)a.T, (uint64_t)a.BB, DH, AQ, &maps.q_lo);
     ok = ok && tmap_encode_bf16(a.qkv_hi, 3, C3, (uint64_t)a.T, (uint64_t)a.BB, DH, AK, &maps.kv_hi);
     ok = ok && tmap_encode_bf16(a.qkv_lo, 3, C3, (uint64_t)a.T, (uint64_t)a.BB, DH, AK, &maps.kv_lo);
-    if (ok) { maps.vt_hi = maps.kv_hi; maps.vt_lo = maps.kv_lo; }
-    if (ok && use_vt) {
-        if (!sc.vt_hi || !sc.vt_lo) { g_att_err = "V^T scratch missing"; return cudaErrorInvalidValue; }
-        dim3 grid((Tpad + 31) / 32, a.n_heads, a.BB);
-        vt_kernel<<<grid, 256, 0, s>>>(a.qkv_hi, a.qkv_lo, sc.vt_hi, sc.vt_lo, a.T, Tpad, a.H, a.n_heads);
-        const uint64_t heads = (uint64_t)a.BB * a.n_heads;
-        ok = ok && tmap_encode_bf16(sc.vt_hi, 3, (uint64_t)Tpad, DH, heads, AK, DH, &maps.vt_hi);
-        ok = ok && tmap_encode_bf16(sc.vt_lo, 3, (uint64_t)Tpad, DH, heads, AK, DH, &maps.vt_lo);
-    }
     if (!ok) { g_att_err = gemm_tc_last_error(); return cudaErrorInvalidValue; }
     AttParams p;
     p.BB = a.BB; p.B = a.B; p.T = a.T; p.H = a.H; p.n_heads = a.n_heads;
@@ -1066,32 +750,23 @@ cudaError_t launch_attention_tc(const AttnArgs& a, const AttnTcScratch& sc, cuda
         cudaMemsetAsync(g_att_trace, 0, 32 * 16 * sizeof(long long), s);
         p.trace = g_att_trace;
     }
-    static int p_smem = -1, use_v4 = -1;
+    static int use_v4 = -1;
     if (use_v4 < 0) { const char* e = getenv("STABLETTS_B200_ATT_V4"); use_v4 = (e && !strcmp(e, "1")) ? 1 : 0; }
-    if (p_smem < 0) { const char* e = getenv("STABLETTS_B200_ATT_PSMEM"); p_smem = (e && !strcmp(e, "1")) ? 1 : 0; }
     if (!g_att_attr) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attention_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT5_SMEM);
-        if (e != cudaSuccess) { g_att_err = "cudaFuncSetAttribute failed for attention_tc_kernel"; return e; }
+        if (e != cudaSuccess) { g_att_err = "cudaFuncSetAttribute failed for the attention kernels"; return e; }
         if (getenv("STABLETTS_B200_DEBUG")) {
             int occ = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attention_tc_kernel<true>, A_THREADS, ATT_SMEM);
-            fprintf(stderr, "[stabletts_b200] attention CTAs/SM: %d (V %s)\n", occ, use_vt ? "transposed" : "MN-major");
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attention_tc5_kernel, A_THREADS, ATT5_SMEM);
+            fprintf(stderr, "[stabletts_b200] attention CTAs/SM: %d\n", occ);
         }
         g_att_attr = true;
     }
     dim3 grid((a.T + AQ - 1) / AQ, a.n_heads, a.BB);
-    if (!p_smem && !use_v4 && !use_vt)      // default: Q and P in tensor memory, one O accumulator (v5)
-        return launch_k(attention_tc5_kernel, grid, dim3(A_THREADS), (size_t)ATT5_SMEM, s, maps, p);
-    if (!p_smem) {     // STABLETTS_B200_ATT_V4=1: P in tensor memory, Q tile in shared memory, O_A / O_B (v4)
-        if (use_vt) return launch_k(attention_tc4_kernel<false>, grid, dim3(A_THREADS), (size_t)ATT4_SMEM, s, maps, p);
-        return launch_k(attention_tc4_kernel<true>, grid, dim3(A_THREADS), (size_t)ATT4_SMEM, s, maps, p);
-    }
-    if (use_vt) return launch_k(attention_tc_kernel<false>, grid, dim3(A_THREADS), (size_t)ATT_SMEM, s, maps, p);
-    return launch_k(attention_tc_kernel<true>, grid, dim3(A_THREADS), (size_t)ATT_SMEM, s, maps, p);
+    if (use_v4)        // A/B only: Q tile in shared memory, O_A / O_B (v4)
+        return launch_k(attention_tc4_kernel, grid, dim3(A_THREADS), (size_t)ATT4_SMEM, s, maps, p);
+    return launch_k(attention_tc5_kernel, grid, dim3(A_THREADS), (size_t)ATT5_SMEM, s, maps, p);   // default (v5)
 }
 
 }  // namespace st

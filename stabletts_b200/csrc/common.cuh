@@ -138,11 +138,7 @@ struct AttnArgs {
 cudaError_t launch_attention_simt(const AttnArgs& a, cudaStream_t s);
 
 // tcgen05 engine (attention_tc.cu)
-struct AttnTcScratch {
-    bf16 *vt_hi = nullptr, *vt_lo = nullptr;     // [BB*nh][64][Tpad], only for the STABLETTS_B200_VT=1 fallback
-};
-size_t attention_tc_scratch_elems(int BB, int T, int H);    // elements per V^T plane
-cudaError_t launch_attention_tc(const AttnArgs& a, const AttnTcScratch& sc, cudaStream_t s);
+cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t s);
 // fp32 packed qkv -> RoPE'd, q-scaled split planes (what the QKV GEMM epilogue emits on the product path)
 cudaError_t launch_rope_split(const float* qkv, const float* rope_cs, bf16* hi, bf16* lo, int BB, int T, int H, cudaStream_t s);
 const char* attention_tc_last_error();
