@@ -820,7 +820,9 @@ int st_solve(st_handle* h, float* z_inout, const float* mu, const float* mask, c
     }
     std::string key((const char*)t_span_host, sizeof(float) * (n_steps + 1));
     char meta[160];
-    snprintf(meta, sizeof meta, "|%d,%d,%d,%d,%d,%d,%08x,%p", B, T, cfg, method, n_steps, h->engine, *(const unsigned*)&cfg_strength, h->ws_ptr);
+    unsigned cfg_bits;
+    memcpy(&cfg_bits, &cfg_strength, sizeof cfg_bits);
+    snprintf(meta, sizeof meta, "|%d,%d,%d,%d,%d,%d,%08x,%p", B, T, cfg, method, n_steps, h->engine, cfg_bits, h->ws_ptr);
     key += meta;
     st_handle::GraphEntry* ge = nullptr;
     for (auto& g : h->graphs) if (g.key == key) { ge = &g; break; }

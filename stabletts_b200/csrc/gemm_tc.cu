@@ -42,102 +42,12 @@ struct TcMaps {
 // ----------------------------------------------------------------------------------------------
 // PTX wrappers
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 rx;\n\t"
-        ".reg .pred px;\n\t"
-        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
-        "selp.b32 %0, 1, 0, px;\n\t"
-        "}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row (1024 B) swizzle atoms.
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
-//  layout_type=SWIZZLE_128B(2) [61,64))
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;             // SBO: 8 rows * 128 B
-    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
-    return d;
-}
-
-// cute::UMMA::InstrDescriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=BN
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-}
+using namespace ptx;     // PTX wrappers shared with the 2-CTA and attention kernels (tc_ptx.cuh)
 
 template <int BN> struct Cfg {
     static constexpr int B_TILE_BYTES = BN * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 2 : 3;
+    static constexpr int STAGES = 3;
     static constexpr int TMEM_COLS = 2 * BN;                 // two accumulator stages (power of 2 >= 32)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
 };
@@ -214,7 +124,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        constexpr uint32_t idesc = make_idesc(BN);
+        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -287,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 std::string g_err = "";
 std::mutex g_mu;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
-bool g_attr_set[2] = {false, false};
+bool g_attr_set = false;
 
 struct MapKey {
     const void* ptr; uint64_t d0, d1, d2; uint32_t b0, b1; int rank;
@@ -358,11 +268,10 @@ cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t s) {
     p.m_tiles_per_b = (g.T + BLOCK_M - 1) / BLOCK_M;
     p.n_tiles = (g.N + BN - 1) / BN;
     p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
-    constexpr int idx = BN == 256 ? 1 : 0;
-    if (!g_attr_set[idx]) {
+    if (!g_attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) { g_err = "cudaFuncSetAttribute(max dynamic smem) failed"; return e; }
-        g_attr_set[idx] = true;
+        g_attr_set = true;
     }
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     return launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, s, maps, p);
@@ -419,15 +328,9 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s) {
         if (i == 0 && g.n_src > 1 && g.Cs[0] % BLOCK_K) { g_err = "first concat source must be a multiple of 64 channels"; return cudaErrorInvalidValue; }
     }
     if (!g.W_hi || !g.W_lo || g.Ktot % 8 || g.N % 8) { g_err = "bad weight operand"; return cudaErrorInvalidValue; }
-    // tile-width choice: wider tiles halve A re-reads; narrower tiles quantise better on 148 SMs
-    const long m_tiles = (long)g.BB * ((g.T + BLOCK_M - 1) / BLOCK_M);
-    bool use256 = false;
-    if (g.N > 128) {
-        const long t256 = m_tiles * ((g.N + 255) / 256), t128 = m_tiles * ((g.N + 127) / 128);
-        const long w256 = (t256 + num_sms - 1) / num_sms * 2, w128 = (t128 + num_sms - 1) / num_sms;
-        use256 = false && (w256 <= w128 + w128 / 8);   // 128x256 with 2 stages is TMA-latency bound (profiles/r1a); 2-CTA 256x256 is the planned wide tile
-    }
-    return use256 ? launch_bn<256>(g, num_sms, s) : launch_bn<128>(g, num_sms, s);
+    // one tile shape here: 128 x 128 (a 128 x 256 1-CTA tile with two smem stages was TMA-latency bound, profiles/r1a;
+    // the wide tile is the 2-CTA kernel's)
+    return launch_bn<128>(g, num_sms, s);
 }
 
 }  // namespace st
