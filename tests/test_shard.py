@@ -98,3 +98,49 @@ def test_length_buckets_and_bucketed_solve():
     f = lambda mu_, mask_, c_, z_: (z_ + 2 * mu_) * mask_ + c_.mean(1)[:, None, None] * mask_
     out = shard.bucketed_solve(f, mu, mask, c, z, ls, n_buckets=3)
     assert torch.allclose(out, f(mu, mask, c, z))
+
+
+# ---- property tests of the host-side partition logic (hypothesis) ------------------------------------------
+from hypothesis import given, settings, strategies as hst   # noqa: E402
+
+_lengths = hst.lists(hst.integers(min_value=1, max_value=4000), min_size=0, max_size=64)
+
+
+@settings(max_examples=200, deadline=None)
+@given(n=hst.integers(min_value=0, max_value=5000), world=hst.integers(min_value=1, max_value=16))
+def test_split_counts_properties(n, world):
+    from stabletts_b200 import shard
+    c = shard.split_counts(n, world)
+    assert len(c) == world and sum(c) == n
+    assert max(c) - min(c) <= 1 and c == sorted(c, reverse=True)          # near-equal, larger slices first
+
+
+@settings(max_examples=200, deadline=None)
+@given(lengths=_lengths, world=hst.integers(min_value=1, max_value=8))
+def test_partition_by_cost_properties(lengths, world):
+    """every utterance lands in exactly one shard; shards are length-sorted; the greedy LPT bound holds:
+    max load <= mean load + the largest single cost"""
+    from stabletts_b200 import shard
+    shards = shard.partition_by_cost(lengths, world)
+    assert len(shards) == world
+    flat = sorted(i for s in shards for i in s)
+    assert flat == list(range(len(lengths)))
+    for s in shards:
+        assert [lengths[i] for i in s] == sorted(lengths[i] for i in s)
+    if lengths:
+        costs = [shard.utterance_cost(x) for x in lengths]
+        loads = [sum(costs[i] for i in s) for s in shards]
+        assert max(loads) <= sum(costs) / world + max(costs) + 1e-6 * sum(costs)
+
+
+@settings(max_examples=200, deadline=None)
+@given(lengths=_lengths, n_buckets=hst.integers(min_value=1, max_value=8))
+def test_length_buckets_properties(lengths, n_buckets):
+    """buckets partition the indices, are contiguous in sorted-length order, and there are at most n_buckets"""
+    from stabletts_b200 import shard
+    b = shard.length_buckets(lengths, n_buckets)
+    assert len(b) <= n_buckets
+    flat = [i for g in b for i in g]
+    assert sorted(flat) == list(range(len(lengths)))
+    assert [lengths[i] for i in flat] == sorted(lengths)
+    assert all(g for g in b)
