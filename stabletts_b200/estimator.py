@@ -116,8 +116,10 @@ class Decoder(NativeModule):
         mask = self._f32c("mask", mask, (B, 1, T))
         c = self._f32c("c", c, (B, self.gin_channels))
         t = torch.as_tensor(t, dtype=torch.float32, device=x.device).reshape(-1).contiguous()
-        if t.numel() not in (1, B):
+        if t.numel() not in (1, B) and B > 0:
             raise ValueError("t must be 0-dim or have shape (B,)")
+        if B == 0 or T == 0:                    # empty batch / zero frames: the reference returns an empty tensor
+            return torch.empty_like(x)
         lib, h, stream = self._prepare(x, B, T, 0)
         out = torch.empty_like(x)
         rc = lib.st_estimator_forward(h, t.data_ptr(), t.numel(), x.data_ptr(), mask.data_ptr(), mu.data_ptr(),

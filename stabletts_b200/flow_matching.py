@@ -72,6 +72,8 @@ class CFMDecoder(nn.Module):
         mu_ = est._f32c("mu", mu, (B, est.cond_channels, T))
         mask_ = est._f32c("mask", mask, (B, 1, T))
         c_ = est._f32c("c", c, (B, est.gin_channels))
+        if B == 0 or T == 0:                     # empty batch / zero frames: odeint on an empty state returns it
+            return z.to(mu.dtype)
         t_span = torch.linspace(0, 1, n_timesteps + 1, dtype=torch.float32)         # :46 (host copy of the grid)
         t_host = (C.c_float * (n_timesteps + 1))(*t_span.tolist())
         method = _method_id(solver)

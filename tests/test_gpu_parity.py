@@ -254,3 +254,23 @@ def test_long_and_wide_shapes_vs_oracle(dev):
         e = rel_errs(out, ref)
         assert max(e) < 1e-3, (n_mel, T, e)
         assert float((out.cpu() * (1 - inp["mask"])).abs().max()) == 0.0
+
+
+def test_empty_and_zero_length_inputs(dev):
+    """Edge cases: an empty batch and zero frames return empty tensors like the reference's modules do; an utterance
+    of length 0 inside a batch (all-zero mask row) yields exact zeros for that row and leaves the others untouched."""
+    m = model_for(80, "tcgen05", dev)
+    e = m.estimator(torch.tensor(0.3, device=dev), torch.zeros(0, 80, 16, device=dev), torch.zeros(0, 1, 16, device=dev),
+                    torch.zeros(0, 80, 16, device=dev), torch.zeros(0, 256, device=dev))
+    assert e.shape == (0, 80, 16)
+    s0 = m(torch.zeros(2, 80, 0, device=dev), torch.zeros(2, 1, 0, device=dev), 3, 1.0, torch.zeros(2, 256, device=dev), "euler")
+    assert s0.shape == (2, 80, 0)
+    st = weights.make_state(cases.WEIGHT_SEED, 80)
+    inp = weights.make_inputs(55, [70, 0, 33], 70)
+    assert float(inp["mask"][1].sum()) == 0.0
+    with torch.inference_mode():
+        ref = R.estimator_forward(st, inp["t"], inp["x"], inp["mask"], inp["mu"], inp["c"])
+    out = m.estimator(inp["t"].to(dev), inp["x"].to(dev), inp["mask"].to(dev), inp["mu"].to(dev), inp["c"].to(dev)).cpu()
+    assert torch.isfinite(out).all()
+    assert float(out[1].abs().max()) == 0.0
+    assert max(rel_errs(out, ref)) < 1e-3
