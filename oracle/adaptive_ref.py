@@ -6,8 +6,11 @@ reference's requirements.txt:14 and ABSENT here, so this file restates its publi
 (Dormand & Prince 1980 tableau with Shampine's embedded 4th-order weights and dense-output midpoint
 coefficients; Hairer's initial-step heuristic; I-controller with safety 0.9, ifactor 10, dfactor 0.2;
 RMS mixed error norm over ALL elements; evaluation at the requested times by a 4th-order interpolant).
-PARITY UNPINNED: nothing in the reference pins these semantics; the CUDA driver is tested against THIS
-restatement only.
+PARITY UNPINNED against torchdiffeq itself: nothing in the reference pins these semantics and the package is
+not installable here.  What IS pinned (tests/test_adaptive.py): the 5th-order tableau against scipy's RK45 (an
+independent implementation of the same published method), the solution of a nonlinear system against
+scipy's adaptive RK45 at equal tolerances, and a closed-form ODE.  The embedded error weights are Shampine's
+variant as published in torchdiffeq (last coefficient -1/60), which scipy does not share.
 """
 from __future__ import annotations
 

@@ -20,6 +20,40 @@ def test_oracle_on_closed_form_ode():
     assert stats["accepted"] >= 3 and stats["nfe"] == 2 + 6 * (stats["accepted"] + stats["rejected"])
 
 
+def test_tableau_matches_an_independent_implementation():
+    """The 5th-order Dormand–Prince tableau (nodes, stage matrix, solution weights) against scipy's RK45, an
+    independent implementation of the same published method that IS installed here.  (The embedded 4th-order
+    weights differ on purpose: torchdiffeq uses Shampine's variant, last error coefficient -1/60; scipy the
+    classic 1/40 — so step sequences are not comparable one to one, only the solutions are.)"""
+    import numpy as np
+    from scipy.integrate._ivp.rk import RK45
+    assert np.allclose(RK45.C[1:], AD.ALPHA[:5]) and AD.ALPHA[5] == 1.0
+    for i, row in enumerate(AD.BETA[:5]):
+        assert np.allclose(RK45.A[i + 1][:len(row)], row, rtol=0, atol=1e-15)
+    assert np.allclose(RK45.B, AD.C_SOL[:6], rtol=0, atol=1e-15) and AD.C_SOL[6] == 0
+    assert np.allclose(AD.BETA[5], AD.C_SOL[:6])                      # FSAL: last stage input = the solution
+    assert abs(sum(AD.C_ERROR)) < 1e-15                               # both weight sets sum to one
+
+
+def test_oracle_solution_agrees_with_scipy_rk45():
+    """Same nonlinear system, same tolerances: both adaptive solvers must land on the same solution to a few times
+    the tolerance, with step counts of the same order."""
+    import numpy as np
+    from scipy.integrate import solve_ivp
+
+    def rhs_np(t, y):
+        return np.array([y[1], -np.sin(y[0]) - 0.3 * y[1] + np.cos(2.0 * t), -0.5 * y[2] + y[0] * y[1]])
+
+    def rhs_t(t, y):
+        return torch.stack([y[1], -torch.sin(y[0]) - 0.3 * y[1] + torch.cos(2.0 * t), -0.5 * y[2] + y[0] * y[1]])
+
+    y0 = [1.0, 0.0, 0.5]
+    sol = solve_ivp(rhs_np, (0.0, 1.0), y0, method="RK45", rtol=1e-6, atol=1e-6)
+    out, stats = AD.odeint_dopri5(rhs_t, torch.tensor(y0, dtype=torch.float32), 1.0, 1e-6, 1e-6)
+    assert np.abs(out.numpy() - sol.y[:, -1]).max() < 2e-5
+    assert 0.5 * len(sol.t) <= stats["accepted"] + 1 <= 2.0 * len(sol.t)
+
+
 @pytest.mark.gpu
 def test_cuda_adaptive_vs_oracle():
     if not torch.cuda.is_available():
