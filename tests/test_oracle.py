@@ -112,3 +112,26 @@ def test_cfm_loss_restatement_vs_reference_golden(name, golden_dir):
     loss, y = R.cfm_loss(st, x1, inp["mask"], inp["mu"], inp["c"], u, z)
     assert abs(float(loss) - float(g["loss"])) <= 2e-5 * abs(float(g["loss"]))
     assert np.abs(y.numpy() - g["y"]).max() <= 1e-6
+
+
+def test_fixed_grid_solvers_have_their_published_order():
+    """torchdiffeq is absent, so the fixed-grid stepping of the oracle driver is pinned by what its tableaux must
+    deliver: on y' = -y + sin(3t) (closed form) halving the step divides the error by ~2^p with p = 1 (euler),
+    2 (midpoint), 4 (rk4, the 3/8 rule), 5 (dopri5 on a fixed grid); and the 3/8-rule weights are (1,3,3,1)/8."""
+    import math
+    f = lambda t, y: -y + torch.sin(3 * t)
+    exact = math.exp(-1) * 1.3 + (math.sin(3) - 3 * math.cos(3)) / 10
+    y0 = torch.ones(1, dtype=torch.float64)
+
+    def err(method, n):
+        ts = torch.linspace(0, 1, n + 1, dtype=torch.float64)
+        return abs(float(R.odeint_fixed(f, y0, ts, method)[0]) - exact)
+
+    for method, p, n in [("euler", 1, 64), ("midpoint", 2, 32), ("rk4", 4, 16), ("dopri5_fixed", 5, 16)]:   # asymptotic range
+        ratio = err(method, n) / err(method, 2 * n)
+        assert 0.8 * 2 ** p < ratio < 1.25 * 2 ** p, (method, ratio)
+    # one 3/8-rule step on y' = 1, y' = t, y' = t^2, y' = t^3 integrates exactly (a 4th-order quadrature)
+    for k in range(4):
+        g = lambda t, y, k=k: t ** k + 0 * y
+        out = R.odeint_fixed(g, torch.zeros(1, dtype=torch.float64), torch.tensor([0.0, 1.0], dtype=torch.float64), "rk4")
+        assert abs(float(out[0]) - 1.0 / (k + 1)) < 1e-12
