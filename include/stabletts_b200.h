@@ -111,8 +111,18 @@ int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float
                       const float* fake_content, const float* fake_speaker, float cfg_strength, double t_start,
                       double t_end, double rtol, double atol, int max_steps, int B, int T, void* stream, int64_t* stats);
 
+/* The other adaptive `solver` strings the reference's UI offers (webui.py:110) are further embedded tableaux on the
+ * same controller: Bogacki–Shampine 3(2) ("bosh3"), Fehlberg 2(1) ("fehlberg2"), Heun–Euler 2(1) ("adaptive_heun");
+ * stats: [accepted, rejected, NFE] with NFE = 2 + stages*(accepted+rejected).  "implicit_adams" (a multistep
+ * predictor-corrector with its own history) is NOT built: the Python surface raises for it. */
+enum { ST_ADAPT_DOPRI5 = 0, ST_ADAPT_BOSH3 = 1, ST_ADAPT_FEHLBERG2 = 2, ST_ADAPT_HEUN = 3 };
+int st_solve_adaptive_ex(st_handle* h, int method, float* z_inout, const float* mu, const float* mask, const float* c,
+                         const float* fake_content, const float* fake_speaker, float cfg_strength, double t_start,
+                         double t_end, double rtol, double atol, int max_steps, int B, int T, void* stream, int64_t* stats);
+
 /* Same as st_solve with HOST buffers: copies inputs host->device and the sample device->host on
- * `stream` and synchronises it before returning (the end-to-end form bench.py's `e2e` times). */
+ * `stream` and synchronises it before returning (the end-to-end form bench.py's `e2e` times).  Page-locked host
+ * buffers are copied from/to directly; pageable ones are staged through a pinned buffer the handle owns. */
 int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const float* mask_host,
                   const float* c_host, const float* fake_content_host, const float* fake_speaker_host,
                   float cfg_strength, const float* t_span_host, int n_steps, int method, int B, int T,

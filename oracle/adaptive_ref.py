@@ -1,4 +1,5 @@
-"""CPU oracle for the ADAPTIVE Dormand–Prince 5(4) solver (TEST INFRASTRUCTURE ONLY).
+"""CPU oracle for the ADAPTIVE embedded Runge–Kutta solvers: Dormand–Prince 5(4) (the reference's default) and the
+other adaptive strings of webui.py:110 — bosh3, fehlberg2, adaptive_heun (TEST INFRASTRUCTURE ONLY).
 
 The reference's default ``solver=None`` means ``torchdiffeq.odeint(..., method='dopri5', rtol=1e-5,
 atol=1e-5)`` (models/flow_matching.py:54).  torchdiffeq is a third-party package, unpinned in the
@@ -34,11 +35,35 @@ C_MID = [6025192743 / 30085553152 / 2, 0, 51252292925 / 65400821598 / 2, -269186
 SAFETY, IFACTOR, DFACTOR, ORDER = 0.9, 10.0, 0.2, 5
 
 
+class Tableau:
+    """One embedded Runge-Kutta pair as torchdiffeq's rk_common._ButcherTableau carries it (+ c_mid and the order)."""
+    def __init__(self, alpha, beta, c_sol, c_error, c_mid, order):
+        self.alpha, self.beta, self.c_sol, self.c_error, self.c_mid, self.order = alpha, beta, c_sol, c_error, c_mid, order
+        self.stages = len(alpha)                 # new derivative evaluations per step
+        # "this property (true for Dormand-Prince) lets us save a few FLOPs": the last stage input is the solution
+        self.sol_is_last_stage = c_sol[-1] == 0 and list(c_sol[:-1]) == list(beta[-1])
+
+
+TABLEAUS = {
+    # torchdiffeq dopri5.py (Dormand & Prince 1980, Shampine's embedded weights)
+    "dopri5": Tableau(ALPHA, BETA, C_SOL, C_ERROR, C_MID, 5),
+    # torchdiffeq bosh3.py (Bogacki & Shampine 1989)
+    "bosh3": Tableau([1 / 2, 3 / 4, 1.], [[1 / 2], [0., 3 / 4], [2 / 9, 1 / 3, 4 / 9]], [2 / 9, 1 / 3, 4 / 9, 0.],
+                     [2 / 9 - 7 / 24, 1 / 3 - 1 / 4, 4 / 9 - 1 / 3, -1 / 8], [0., 0.5, 0., 0.], 3),
+    # torchdiffeq fehlberg2.py (Fehlberg 2(1))
+    "fehlberg2": Tableau([1 / 2, 1.0], [[1 / 2], [1 / 256, 255 / 256]], [1 / 512, 255 / 256, 1 / 512],
+                         [-1 / 512, 0, 1 / 512], [0., 0.5, 0.], 2),
+    # torchdiffeq adaptive_heun.py (Heun-Euler 2(1))
+    "adaptive_heun": Tableau([1.], [[1.]], [0.5, 0.5], [0.5, -0.5], [0.5, 0.], 2),
+}
+
+
 def rms_norm(x: torch.Tensor) -> float:
     return float(x.double().pow(2).mean().sqrt())
 
 
-def select_initial_step(f, t0: float, y0, f0, rtol, atol) -> float:
+def select_initial_step(f, t0: float, y0, f0, rtol, atol, order: int = ORDER) -> float:
+    """torchdiffeq misc._select_initial_step, called with ``order - 1`` by the adaptive solvers: exponent 1/order."""
     scale = atol + y0.abs() * rtol
     d0, d1 = rms_norm(y0 / scale), rms_norm(f0 / scale)
     h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
@@ -48,16 +73,21 @@ def select_initial_step(f, t0: float, y0, f0, rtol, atol) -> float:
     if d1 <= 1e-15 and d2 <= 1e-15:
         h1 = max(1e-6, h0 * 1e-3)
     else:
-        h1 = (0.01 / max(d1, d2)) ** (1.0 / ORDER)
+        h1 = (0.01 / max(d1, d2)) ** (1.0 / order)
     return min(100 * h0, h1)
 
 
-def odeint_dopri5(f, y0: torch.Tensor, t_end: float = 1.0, rtol: float = 1e-5, atol: float = 1e-5, max_steps: int = 1000):
-    """Integrates dy/dt = f(t, y) from 0 and returns (y(t_end), stats).  Time is carried in float64 (as
-    torchdiffeq does), the state in float32; f receives t as a 0-dim float32 tensor."""
+def odeint_adaptive(f, y0: torch.Tensor, method: str = "dopri5", t_end: float = 1.0, rtol: float = 1e-5, atol: float = 1e-5,
+                    max_steps: int = 100000):
+    """Integrates dy/dt = f(t, y) from 0 and returns (y(t_end), stats) with the embedded pair ``method``.  Time is
+    carried in float64 (as torchdiffeq does), the state in float32; f receives t as a 0-dim float32 tensor.
+    Restates rk_common.RKAdaptiveStepsizeODESolver: _runge_kutta_step (stage k_{i+1} at t1 exactly when alpha_i == 1; the
+    LAST stage derivative becomes the next step's f0 for every tableau), _compute_error_ratio (RMS mixed norm),
+    _optimal_step_size (safety 0.9, ifactor 10, dfactor 0.2, exponent 1/order), _interp_fit / _interp_evaluate."""
+    tb = TABLEAUS[method]
     t0 = 0.0
     f0 = f(torch.tensor(t0, dtype=torch.float32), y0)
-    dt = select_initial_step(f, t0, y0, f0, rtol, atol)
+    dt = select_initial_step(f, t0, y0, f0, rtol, atol, tb.order)
     n_acc = n_rej = 0
     y = y0
     interp = None
@@ -66,16 +96,18 @@ def odeint_dopri5(f, y0: torch.Tensor, t_end: float = 1.0, rtol: float = 1e-5, a
             raise RuntimeError("max_steps exceeded")
         t1 = t0 + dt
         k = [f0]
-        for i in range(6):
+        for i in range(tb.stages):
             yi = y
-            for j, b in enumerate(BETA[i]):
+            for j, b in enumerate(tb.beta[i]):
                 if b != 0:
                     yi = yi + (dt * b) * k[j]
-            ti = t1 if ALPHA[i] == 1.0 else t0 + ALPHA[i] * dt
+            ti = t1 if tb.alpha[i] == 1.0 else t0 + tb.alpha[i] * dt
             k.append(f(torch.tensor(ti, dtype=torch.float32), yi))
-            if i == 5:
-                y1 = yi                                       # last stage input is the 5th-order solution (FSAL)
-        err = sum((dt * c) * kk for c, kk in zip(C_ERROR, k) if c != 0)
+        if tb.sol_is_last_stage:
+            y1 = yi                                           # last stage input is the solution
+        else:
+            y1 = y + sum((dt * c) * kk for c, kk in zip(tb.c_sol, k) if c != 0)
+        err = sum((dt * c) * kk for c, kk in zip(tb.c_error, k) if c != 0)
         tol = atol + rtol * torch.max(y.abs(), y1.abs())
         ratio = rms_norm(err / tol)
         accept = ratio <= 1.0
@@ -83,22 +115,26 @@ def odeint_dopri5(f, y0: torch.Tensor, t_end: float = 1.0, rtol: float = 1e-5, a
             factor = IFACTOR
         else:
             dfac = 1.0 if ratio < 1 else DFACTOR
-            factor = min(IFACTOR, max(SAFETY / ratio ** (1.0 / ORDER), dfac))
+            factor = min(IFACTOR, max(SAFETY / ratio ** (1.0 / tb.order), dfac))
         if accept:
             n_acc += 1
-            y_mid = y + sum((dt * c) * kk for c, kk in zip(C_MID, k) if c != 0)
-            interp = (y, y1, y_mid, k[0], k[6], dt, t0, t1)
-            y, f0, t0 = y1, k[6], t1
+            y_mid = y + sum((dt * c) * kk for c, kk in zip(tb.c_mid, k) if c != 0)
+            interp = (y, y1, y_mid, k[0], k[-1], dt, t0, t1)
+            y, f0, t0 = y1, k[-1], t1
         else:
             n_rej += 1
         dt = dt * factor
         if accept and t0 >= t_end:
             break
-    ya, yb, ym, fa, fb, h, ta, tb = interp
+    ya, yb, ym, fa, fb, h, ta, tb_ = interp
     a = 2 * h * (fb - fa) - 8 * (yb + ya) + 16 * ym
     b = h * (5 * fa - 3 * fb) + 18 * ya + 14 * yb - 32 * ym
     c = h * (fb - 4 * fa) - 11 * ya - 5 * yb + 16 * ym
     d = h * fa
-    x = (t_end - ta) / (tb - ta)
+    x = (t_end - ta) / (tb_ - ta)
     out = ya + x * (d + x * (c + x * (b + x * a)))
-    return out, dict(accepted=n_acc, rejected=n_rej, nfe=2 + 6 * (n_acc + n_rej))
+    return out, dict(accepted=n_acc, rejected=n_rej, nfe=2 + tb.stages * (n_acc + n_rej))
+
+
+def odeint_dopri5(f, y0: torch.Tensor, t_end: float = 1.0, rtol: float = 1e-5, atol: float = 1e-5, max_steps: int = 1000):
+    return odeint_adaptive(f, y0, "dopri5", t_end, rtol, atol, max_steps)

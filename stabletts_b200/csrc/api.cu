@@ -79,6 +79,7 @@ struct st_handle {
     std::vector<GraphEntry> graphs;
     std::vector<std::string> graph_seen;   // keys enqueued directly once (kernels loaded, attributes set) before capture
     double* pinned = nullptr;          // 16 B of pinned host memory: norm read-back of the adaptive controller
+    char* pin_buf = nullptr; size_t pin_bytes = 0;   // pinned staging of st_solve_host for callers with pageable buffers
     cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the caller's may be the legacy stream)
     int graph_mode = -1;               // -1: read STABLETTS_B200_GRAPH on first use; 0 off; 1 always; 2 auto (small problems)
     void drop_graphs() { for (auto& g : graphs) cudaGraphExecDestroy(g.exec); graphs.clear(); }
@@ -464,12 +465,21 @@ Tableau tableau_for(int method) {
     return t;
 }
 
+// Every entry point runs on the handle's device and RESTORES the caller's current device on return (a torch caller
+// whose current device is cuda:0 must not find it switched to cuda:1 because a module lives there).
+struct DevGuard {
+    int prev = -1, dev;
+    explicit DevGuard(int d) : dev(d) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != d) cudaSetDevice(d); }
+    ~DevGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+    DevGuard(const DevGuard&) = delete; DevGuard& operator=(const DevGuard&) = delete;
+};
+#define ST_ENTER(h) DevGuard dev_guard__((h)->device)
+
 int check_common(st_handle* h, int B, int T) {
     if (!h) return 1;
     if (!h->finalized) return fail(h, "weights not finalized (call st_finalize_weights)");
     if (B <= 0 || T <= 0) return fail(h, "B and T must be positive");
     if (B > 32767) return fail(h, "B too large");
-    ST_CUDA(cudaSetDevice(h->device));
     return 0;
 }
 
@@ -521,7 +531,8 @@ int st_create_text_encoder(const st_dims* dims, int n_vocab, int device, st_hand
 
 int st_destroy(st_handle* h) {
     if (!h) return 0;
-    cudaSetDevice(h->device);
+    {
+    ST_ENTER(h);
     cudaDeviceSynchronize();
     h->drop_graphs();
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -530,6 +541,8 @@ int st_destroy(st_handle* h) {
     for (void* p : h->owned) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->ws_ptr && h->ws_owned) cudaFree(h->ws_ptr);
+    if (h->pin_buf) cudaFreeHost(h->pin_buf);
+    }
     delete h;
     return 0;
 }
@@ -553,7 +566,7 @@ int st_profile_begin(st_handle* h) {
 int st_profile_end(st_handle* h, double* ms, double* flops, double* bytes, int64_t* launches) {
     if (!h) return 1;
     h->prof_on = false;
-    ST_CUDA(cudaSetDevice(h->device));
+    ST_ENTER(h);
     ST_CUDA(cudaDeviceSynchronize());
     for (int i = 0; i < ST_PROF_NCAT; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
     for (auto& r : h->prof) {
@@ -567,7 +580,7 @@ int st_profile_end(st_handle* h, double* ms, double* flops, double* bytes, int64
 
 int st_load_weight(st_handle* h, const char* name, const float* data, int64_t numel, void* stream) {
     if (!h || !name || !data || numel <= 0) return fail(h, "st_load_weight: bad argument");
-    ST_CUDA(cudaSetDevice(h->device));
+    ST_ENTER(h);
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, data) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
         cudaGetLastError();
@@ -575,7 +588,10 @@ int st_load_weight(st_handle* h, const char* name, const float* data, int64_t nu
     }
     float* p;
     ST_CUDA(cudaMalloc((void**)&p, sizeof(float) * numel));
-    ST_CUDA(cudaMemcpyAsync(p, data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    {
+        cudaError_t ce = cudaMemcpyAsync(p, data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        if (ce != cudaSuccess) { cudaFree(p); return fail(h, std::string("st_load_weight: copy of ") + name + " failed: " + cudaGetErrorString(ce)); }
+    }
     auto it = h->raw.find(name);
     if (it != h->raw.end()) { cudaFree(it->second.first); }
     h->raw[name] = {p, numel};
@@ -585,7 +601,7 @@ int st_load_weight(st_handle* h, const char* name, const float* data, int64_t nu
 
 int st_finalize_weights(st_handle* h, void* stream) {
     if (!h) return 1;
-    ST_CUDA(cudaSetDevice(h->device));
+    ST_ENTER(h);
     cudaStream_t s = (cudaStream_t)stream;
     const st_dims& d = h->d;
     const int H = d.hidden, F = d.filter, M = d.n_mel, k = d.kernel, L = d.n_layers;
@@ -647,7 +663,8 @@ size_t st_workspace_bytes(const st_handle* h, int B, int T, int cfg) {
 
 int st_attach_workspace(st_handle* h, void* dev_ptr, size_t bytes) {
     if (!h) return 1;
-    if (h->ws_ptr && h->ws_owned) { cudaSetDevice(h->device); cudaFree(h->ws_ptr); }
+    ST_ENTER(h);
+    if (h->ws_ptr && h->ws_owned) cudaFree(h->ws_ptr);
     h->drop_graphs();                  // cached graphs hold pointers into the old workspace
     h->ws_ptr = dev_ptr; h->ws_bytes = dev_ptr ? bytes : 0; h->ws_owned = false;
     return 0;
@@ -655,6 +672,8 @@ int st_attach_workspace(st_handle* h, void* dev_ptr, size_t bytes) {
 
 int st_estimator_forward(st_handle* h, const float* t, int t_count, const float* x, const float* mask, const float* mu,
                          const float* c, float* out, int B, int T, void* stream) {
+    if (!h) return 1;
+    ST_ENTER(h);
     if (check_common(h, B, T)) return 1;
     if (h->kind != 0) return fail(h, "handle is not a CFM estimator");
     if (!t || !x || !mask || !mu || !c || !out) return fail(h, "st_estimator_forward: null pointer");
@@ -677,6 +696,8 @@ int st_estimator_forward(st_handle* h, const float* t, int t_count, const float*
 // and z (:96): y = (1-(1-sigma)t) z + t x1 -> estimator(t, y, mask, mu, c) -> sum((v-u)^2) / (sum(mask) * n_mel).
 int st_cfm_loss(st_handle* h, const float* x1, const float* z, const float* t, const float* mask, const float* mu, const float* c,
                 float sigma_min, float* y_out, float* loss_out, int B, int T, void* stream) {
+    if (!h) return 1;
+    ST_ENTER(h);
     if (check_common(h, B, T)) return 1;
     if (h->kind != 0) return fail(h, "handle is not a CFM estimator");
     if (!x1 || !z || !t || !mask || !mu || !c || !y_out || !loss_out) return fail(h, "st_cfm_loss: null pointer");
@@ -752,6 +773,8 @@ static int solve_impl(st_handle* h, Workspace& w, float* z_inout, const float* m
 // models/text_encoder.py:34-44: emb(x)*sqrt(H) -> n_layers DiTConVBlocks(x, c, x_mask) -> proj(x)*x_mask
 int st_text_encoder_forward(st_handle* h, const int64_t* ids, const float* c, const int64_t* x_lengths, float* x_out,
                             float* mu_out, float* mask_out, int B, int T, void* stream) {
+    if (!h) return 1;
+    ST_ENTER(h);
     if (check_common(h, B, T)) return 1;
     if (h->kind != 1) return fail(h, "handle is not a text encoder");
     if (!ids || !c || !x_lengths || !x_out || !mu_out || !mask_out) return fail(h, "st_text_encoder_forward: null pointer");
@@ -787,6 +810,8 @@ int st_text_encoder_forward(st_handle* h, const int64_t* ids, const float* c, co
 int st_solve(st_handle* h, float* z_inout, const float* mu, const float* mask, const float* c, const float* fake_content,
              const float* fake_speaker, float cfg_strength, const float* t_span_host, int n_steps, int method, int B, int T,
              void* stream) {
+    if (!h) return 1;
+    ST_ENTER(h);
     if (check_common(h, B, T)) return 1;
     if (h->kind != 0) return fail(h, "handle is not a CFM estimator");
     if (!z_inout || !mu || !mask || !c || !t_span_host) return fail(h, "st_solve: null pointer");
@@ -866,18 +891,75 @@ int st_solve(st_handle* h, float* z_inout, const float* mu, const float* mask, c
     return 0;
 }
 
-// ---- adaptive Dormand–Prince 5(4): the reference's default solver (`solver=None` -> torchdiffeq dopri5,
-// models/flow_matching.py:54).  torchdiffeq is absent and unpinned, so this follows its PUBLISHED algorithm
-// (oracle/adaptive_ref.py restates the same and is what the tests compare against): FSAL 7-stage tableau,
-// Shampine's embedded error weights, RMS mixed error norm over all elements, I-controller (safety 0.9,
-// factor in [0.2, 10]), Hairer's initial step, evaluation at t_end through the 4th-order dense output.
-// Like torchdiffeq on a GPU, accept/reject needs ONE host-visible scalar per step (8 bytes, pinned).
-int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float* mask, const float* c,
-                      const float* fake_content, const float* fake_speaker, float cfg_strength, double t_start, double t_end,
-                      double rtol, double atol, int max_steps, int B, int T, void* stream, int64_t* stats) {
+// ---- adaptive embedded Runge–Kutta solvers: the reference's default `solver=None` -> torchdiffeq dopri5
+// (models/flow_matching.py:54) and the other adaptive strings webui.py:110 offers (bosh3, fehlberg2, adaptive_heun).
+// torchdiffeq is absent and unpinned, so this follows its PUBLISHED algorithm (oracle/adaptive_ref.py restates the same
+// and is what the tests compare against): one generic stepper over a Butcher tableau (alpha, beta, c_sol, c_error,
+// c_mid, order) — stage k_{i+1} = f(t_i, y + dt sum_j beta_ij k_j), t_i = t1 exactly when alpha_i = 1; the solution is
+// the last stage input when c_sol equals the last beta row (Dormand–Prince), else y + dt sum c_sol_j k_j; the LAST
+// stage derivative is carried over as the next step's f0 for every tableau (what torchdiffeq's rk_common does, also
+// for the tableaux that are not strictly FSAL) — RMS mixed error norm over all elements, I-controller (safety 0.9,
+// factor in [0.2, 10], exponent 1/order), Hairer's initial step, evaluation at t_end through the 4th-order Hermite
+// interpolant fitted to (y0, y1, y_mid, f0, f1).  Like torchdiffeq on a GPU, accept/reject needs ONE host-visible
+// scalar per step (8 bytes, pinned).
+namespace {
+struct AdTab { int S, order; double alpha[6], beta[6][6], csol[7], cerr[7], cmid[7]; bool sol_is_last_stage; };
+
+AdTab adaptive_tableau(int method) {
+    AdTab t{};
+    if (method == ST_ADAPT_BOSH3) {            // Bogacki–Shampine 3(2)
+        t.S = 3; t.order = 3;
+        const double al[3] = {1. / 2, 3. / 4, 1.};
+        const double be[3][3] = {{1. / 2}, {0., 3. / 4}, {2. / 9, 1. / 3, 4. / 9}};
+        const double cs[4] = {2. / 9, 1. / 3, 4. / 9, 0.};
+        const double ce[4] = {2. / 9 - 7. / 24, 1. / 3 - 1. / 4, 4. / 9 - 1. / 3, -1. / 8};
+        const double cm[4] = {0., 0.5, 0., 0.};
+        for (int i = 0; i < 3; ++i) { t.alpha[i] = al[i]; for (int j = 0; j < 3; ++j) t.beta[i][j] = be[i][j]; }
+        for (int i = 0; i < 4; ++i) { t.csol[i] = cs[i]; t.cerr[i] = ce[i]; t.cmid[i] = cm[i]; }
+        t.sol_is_last_stage = true;
+    } else if (method == ST_ADAPT_FEHLBERG2) { // Fehlberg 2(1)
+        t.S = 2; t.order = 2;
+        t.alpha[0] = 0.5; t.alpha[1] = 1.0;
+        t.beta[0][0] = 0.5; t.beta[1][0] = 1. / 256; t.beta[1][1] = 255. / 256;
+        t.csol[0] = 1. / 512; t.csol[1] = 255. / 256; t.csol[2] = 1. / 512;
+        t.cerr[0] = -1. / 512; t.cerr[1] = 0.; t.cerr[2] = 1. / 512;
+        t.cmid[0] = 0.; t.cmid[1] = 0.5; t.cmid[2] = 0.;
+        t.sol_is_last_stage = false;
+    } else if (method == ST_ADAPT_HEUN) {      // Heun–Euler 2(1)
+        t.S = 1; t.order = 2;
+        t.alpha[0] = 1.0; t.beta[0][0] = 1.0;
+        t.csol[0] = 0.5; t.csol[1] = 0.5;
+        t.cerr[0] = 0.5; t.cerr[1] = -0.5;
+        t.cmid[0] = 0.5; t.cmid[1] = 0.;
+        t.sol_is_last_stage = false;
+    } else {                                   // Dormand–Prince 5(4), Shampine's embedded weights
+        t.S = 6; t.order = 5;
+        const double al[6] = {1. / 5, 3. / 10, 4. / 5, 8. / 9, 1.0, 1.0};
+        const double be[6][6] = {{1. / 5}, {3. / 40, 9. / 40}, {44. / 45, -56. / 15, 32. / 9},
+                                 {19372. / 6561, -25360. / 2187, 64448. / 6561, -212. / 729},
+                                 {9017. / 3168, -355. / 33, 46732. / 5247, 49. / 176, -5103. / 18656},
+                                 {35. / 384, 0, 500. / 1113, 125. / 192, -2187. / 6784, 11. / 84}};
+        const double ce[7] = {35. / 384 - 1951. / 21600, 0, 500. / 1113 - 22642. / 50085, 125. / 192 - 451. / 720,
+                              -2187. / 6784 + 12231. / 42400, 11. / 84 - 649. / 6300, -1. / 60};
+        const double cm[7] = {6025192743. / 30085553152. / 2, 0, 51252292925. / 65400821598. / 2, -2691868925. / 45128329728. / 2,
+                              187940372067. / 1594534317056. / 2, -1776094331. / 19743644256. / 2, 11237099. / 235043384. / 2};
+        for (int i = 0; i < 6; ++i) { t.alpha[i] = al[i]; t.csol[i] = be[5][i]; for (int j = 0; j < 6; ++j) t.beta[i][j] = be[i][j]; }
+        for (int i = 0; i < 7; ++i) { t.cerr[i] = ce[i]; t.cmid[i] = cm[i]; }
+        t.sol_is_last_stage = true;
+    }
+    return t;
+}
+}  // namespace
+
+int st_solve_adaptive_ex(st_handle* h, int method, float* z_inout, const float* mu, const float* mask, const float* c,
+                         const float* fake_content, const float* fake_speaker, float cfg_strength, double t_start, double t_end,
+                         double rtol, double atol, int max_steps, int B, int T, void* stream, int64_t* stats) {
+    if (!h) return 1;
+    ST_ENTER(h);
     if (check_common(h, B, T)) return 1;
     if (h->kind != 0) return fail(h, "handle is not a CFM estimator");
     if (!z_inout || !mu || !mask || !c) return fail(h, "st_solve_adaptive: null pointer");
+    if (method < ST_ADAPT_DOPRI5 || method > ST_ADAPT_HEUN) return fail(h, "st_solve_adaptive: unknown adaptive method");
     if (!(t_end > t_start) || rtol <= 0 || atol <= 0 || max_steps <= 0) return fail(h, "st_solve_adaptive: bad tolerances / interval");
     const int cfg = (fake_content && fake_speaker) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
@@ -886,20 +968,12 @@ int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float
     if (!h->pinned) ST_CUDA(cudaMallocHost((void**)&h->pinned, 16));
     const st_dims& d = h->d;
     const long numel = (long)B * T * d.n_mel;
-    const long film_row = (long)d.n_layers * 2 * d.hidden;
-    static const double ALPHA[6] = {1. / 5, 3. / 10, 4. / 5, 8. / 9, 1.0, 1.0};
-    static const double BETA[6][6] = {{1. / 5}, {3. / 40, 9. / 40}, {44. / 45, -56. / 15, 32. / 9},
-                                      {19372. / 6561, -25360. / 2187, 64448. / 6561, -212. / 729},
-                                      {9017. / 3168, -355. / 33, 46732. / 5247, 49. / 176, -5103. / 18656},
-                                      {35. / 384, 0, 500. / 1113, 125. / 192, -2187. / 6784, 11. / 84}};
-    static const double CERR[7] = {35. / 384 - 1951. / 21600, 0, 500. / 1113 - 22642. / 50085, 125. / 192 - 451. / 720,
-                                   -2187. / 6784 + 12231. / 42400, 11. / 84 - 649. / 6300, -1. / 60};
-    static const double CMID[7] = {6025192743. / 30085553152. / 2, 0, 51252292925. / 65400821598. / 2, -2691868925. / 45128329728. / 2,
-                                   187940372067. / 1594534317056. / 2, -1776094331. / 19743644256. / 2, 11237099. / 235043384. / 2};
+    const AdTab tb = adaptive_tableau(method);
+    const int S = tb.S;
     int64_t nfe = 0, n_acc = 0, n_rej = 0;
 
     if (precompute_cond(h, w, mu, mask, c, fake_content, fake_speaker, s)) return 1;
-    // state buffers (token-major): y, y1 and 7 stage derivatives rotate through Kst[]
+    // state buffers (token-major): y, y1 and S+1 stage derivatives rotate through Kst[]
     float* y = w.xt.f32; float* y1 = w.Kst[7]; float* ymid = w.Kst[8]; float* ysave = w.Kst[9];
     float* k[7]; for (int i = 0; i < 7; ++i) k[i] = w.Kst[i];
     ST_LAUNCH(launch_bct_to_btc(z_inout, y, nullptr, nullptr, B, d.n_mel, T, nullptr, s));
@@ -919,7 +993,6 @@ int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float
         if (estimator_eval(h, w, xin, mask, w.film, 0, s)) return 1;
         if (launch_cfg_combine(w.V.f32, kout, B, (long)T * d.n_mel, cfg, cfg_strength, s) != cudaSuccess) return fail(h, "cfg combine failed");
         h->launches++; ++nfe;
-        (void)film_row;
         return 0;
     };
     auto norm = [&](const float* const* K, const float* coef, int n, const float* u, const float* v, double* out) -> int {
@@ -930,11 +1003,19 @@ int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float
         *out = std::sqrt(h->pinned[0] / (double)numel);
         return 0;
     };
+    // dst = base + dt * sum_j w[j] k[j] over the non-zero weights (j < n)
+    auto combine = [&](float* dst, const float* base, const double* wts, int n, double dt) -> int {
+        float coef[7]; const float* Ks[7]; int m = 0;
+        for (int j = 0; j < n; ++j) if (wts[j] != 0.0) { coef[m] = (float)(dt * wts[j]); Ks[m] = k[j]; ++m; }
+        if (m > 6) return fail(h, "internal: too many terms in a stage combination");
+        ST_LAUNCH(launch_lincomb(dst, base, Ks, coef, m, numel, s));
+        return 0;
+    };
 
     double t0 = t_start;
     if (feval(t0, y, k[0])) return 1;
     double dt;
-    {   // Hairer's initial step (order 5 -> exponent 1/5)
+    {   // Hairer's initial step; torchdiffeq passes order - 1, so the exponent is 1 / order
         double d0, d1, d2;
         const float one = 1.f; const float* Ky[1] = {y}; const float* Kf[1] = {k[0]};
         if (norm(Ky, &one, 1, y, y, &d0) || norm(Kf, &one, 1, y, y, &d1)) return 1;
@@ -945,42 +1026,38 @@ int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float
         const float pm[2] = {1.f, -1.f}; const float* Kd[2] = {k[1], k[0]};
         if (norm(Kd, pm, 2, y, y, &d2)) return 1;
         d2 /= h0;
-        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? std::max(1e-6, h0 * 1e-3) : std::pow(0.01 / std::max(d1, d2), 1.0 / 5.0);
+        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? std::max(1e-6, h0 * 1e-3) : std::pow(0.01 / std::max(d1, d2), 1.0 / tb.order);
         dt = std::min(100 * h0, h1);
     }
     double ia_t0 = t0, ia_t1 = t0, ia_dt = 0;      // interval of the last accepted step (dense output)
     while (true) {
         if (n_acc + n_rej >= max_steps) return fail(h, "st_solve_adaptive: max_steps exceeded");
         const double t1 = t0 + dt;
-        for (int i = 0; i < 6; ++i) {
-            float coef[6]; const float* Ks[6]; int n = 0;
-            for (int j = 0; j <= i; ++j) if (BETA[i][j] != 0.0) { coef[n] = (float)(dt * BETA[i][j]); Ks[n] = k[j]; ++n; }
-            float* dst = (i == 5) ? y1 : w.ytmp.f32;          // the last stage input IS the 5th-order solution (FSAL)
-            ST_LAUNCH(launch_lincomb(dst, y, Ks, coef, n, numel, s));
-            if (feval(ALPHA[i] == 1.0 ? t1 : t0 + ALPHA[i] * dt, dst, k[i + 1])) return 1;
+        for (int i = 0; i < S; ++i) {
+            // the last stage input IS the solution when c_sol equals the last beta row (Dormand–Prince, Bogacki–Shampine)
+            float* dst = (i == S - 1 && tb.sol_is_last_stage) ? y1 : w.ytmp.f32;
+            if (combine(dst, y, tb.beta[i], i + 1, dt)) return 1;
+            if (feval(tb.alpha[i] == 1.0 ? t1 : t0 + tb.alpha[i] * dt, dst, k[i + 1])) return 1;
         }
+        if (!tb.sol_is_last_stage && combine(y1, y, tb.csol, S + 1, dt)) return 1;
         double ratio;
         {
             float coef[7]; const float* Ks[7]; int n = 0;
-            for (int j = 0; j < 7; ++j) if (CERR[j] != 0.0) { coef[n] = (float)(dt * CERR[j]); Ks[n] = k[j]; ++n; }
+            for (int j = 0; j <= S; ++j) if (tb.cerr[j] != 0.0) { coef[n] = (float)(dt * tb.cerr[j]); Ks[n] = k[j]; ++n; }
             if (norm(Ks, coef, n, y, y1, &ratio)) return 1;
         }
         const bool accept = ratio <= 1.0;
         double factor;
         if (ratio == 0.0) factor = 10.0;
-        else factor = std::min(10.0, std::max(0.9 / std::pow(ratio, 1.0 / 5.0), ratio < 1.0 ? 1.0 : 0.2));
+        else factor = std::min(10.0, std::max(0.9 / std::pow(ratio, 1.0 / tb.order), ratio < 1.0 ? 1.0 : 0.2));
         if (accept) {
             ++n_acc;
-            {   // y_mid for the dense output
-                float coef[6]; const float* Ks[6]; int n = 0;
-                for (int j = 0; j < 7; ++j) if (CMID[j] != 0.0) { coef[n] = (float)(dt * CMID[j]); Ks[n] = k[j]; ++n; }
-                ST_LAUNCH(launch_lincomb(ymid, y, Ks, coef, n, numel, s));
-            }
-            // keep (y_a = y, y_b = y1, f_a = k0, f_b = k6) alive for the interpolant; advance by pointer rotation
+            if (combine(ymid, y, tb.cmid, S + 1, dt)) return 1;      // y_mid for the dense output
+            // keep (y_a = y, y_b = y1, f_a = k0, f_b = k_S) alive for the interpolant; advance by pointer rotation
             ia_t0 = t0; ia_t1 = t1; ia_dt = dt;
             std::swap(y, ysave);        // ysave now holds y_a ... (y pointer will be replaced below)
             std::swap(y, y1);           // y = y_b (new state); y1 = old ysave buffer (free)
-            std::swap(k[0], k[6]);      // f0 <- f(t1, y1) (FSAL); k[6] now holds f_a
+            std::swap(k[0], k[S]);      // f0 <- last stage derivative; k[S] now holds f_a
             t0 = t1;
         } else {
             ++n_rej;
@@ -988,7 +1065,7 @@ int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float
         dt *= factor;
         if (accept && t0 >= t_end) break;
     }
-    {   // 4th-order dense output at t_end on the last accepted interval (y_a = ysave, y_b = y, f_a = k[6], f_b = k[0])
+    {   // 4th-order dense output at t_end on the last accepted interval (y_a = ysave, y_b = y, f_a = k[S], f_b = k[0])
         const double hh = ia_dt, x = (t_end - ia_t0) / (ia_t1 - ia_t0);
         const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
         // out = ya + x d + x^2 c + x^3 b + x^4 a with a,b,c,d linear in (ya, yb, ym, fa, fb)
@@ -998,7 +1075,7 @@ int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float
         const double cfa = hh * (x - 4 * x2 + 5 * x3 - 2 * x4);
         const double cfb = hh * (x2 - 3 * x3 + 2 * x4);
         float coef[5] = {(float)(cya - 1.0), (float)cyb, (float)cym, (float)cfa, (float)cfb};
-        const float* Ks[5] = {ysave, y, ymid, k[6], k[0]};
+        const float* Ks[5] = {ysave, y, ymid, k[S], k[0]};
         ST_LAUNCH(launch_lincomb(w.ytmp.f32, ysave, Ks, coef, 5, numel, s));
     }
     ST_LAUNCH(launch_btc_to_bct(w.ytmp.f32, z_inout, B, d.n_mel, T, s));
@@ -1006,9 +1083,18 @@ int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float
     return 0;
 }
 
+int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float* mask, const float* c,
+                      const float* fake_content, const float* fake_speaker, float cfg_strength, double t_start, double t_end,
+                      double rtol, double atol, int max_steps, int B, int T, void* stream, int64_t* stats) {
+    return st_solve_adaptive_ex(h, ST_ADAPT_DOPRI5, z_inout, mu, mask, c, fake_content, fake_speaker, cfg_strength, t_start, t_end,
+                                rtol, atol, max_steps, B, T, stream, stats);
+}
+
 int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const float* mask_host, const float* c_host,
                   const float* fake_content_host, const float* fake_speaker_host, float cfg_strength,
                   const float* t_span_host, int n_steps, int method, int B, int T, void* stream) {
+    if (!h) return 1;
+    ST_ENTER(h);
     if (check_common(h, B, T)) return 1;
     if (!z_inout_host || !mu_host || !mask_host || !c_host) return fail(h, "st_solve_host: null pointer");
     const int cfg = (fake_content_host && fake_speaker_host) ? 1 : 0;
@@ -1017,19 +1103,46 @@ int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const
     if (ensure_ws(h, w, B, T, cfg)) return 1;
     const st_dims& d = h->d;
     const size_t n = (size_t)B * T * d.n_mel;
-    ST_CUDA(cudaMemcpyAsync(w.h_z, z_inout_host, n * 4, cudaMemcpyHostToDevice, s));
-    ST_CUDA(cudaMemcpyAsync(w.h_mu, mu_host, n * 4, cudaMemcpyHostToDevice, s));
-    ST_CUDA(cudaMemcpyAsync(w.h_mask, mask_host, (size_t)B * T * 4, cudaMemcpyHostToDevice, s));
-    ST_CUDA(cudaMemcpyAsync(w.h_c, c_host, (size_t)B * d.gin * 4, cudaMemcpyHostToDevice, s));
-    if (cfg) {
-        ST_CUDA(cudaMemcpyAsync(w.h_fc, fake_content_host, (size_t)d.n_mel * 4, cudaMemcpyHostToDevice, s));
-        ST_CUDA(cudaMemcpyAsync(w.h_fs, fake_speaker_host, (size_t)d.gin * 4, cudaMemcpyHostToDevice, s));
+    // Host buffers that are not page-locked are staged through a pinned buffer the handle owns (a pageable
+    // cudaMemcpyAsync is staged by the driver in small chunks and serialises with the stream); pinned callers
+    // (cudaHostAlloc / torch pin_memory) are copied from directly.
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const size_t sizes[6] = {n * 4, n * 4, (size_t)B * T * 4, (size_t)B * d.gin * 4, (size_t)d.n_mel * 4, (size_t)d.gin * 4};
+    const void* src[6] = {z_inout_host, mu_host, mask_host, c_host, cfg ? fake_content_host : nullptr, cfg ? fake_speaker_host : nullptr};
+    void* dst[6] = {w.h_z, w.h_mu, w.h_mask, w.h_c, w.h_fc, w.h_fs};
+    size_t need = 0;
+    bool pinned_in[6];
+    for (int i = 0; i < 6; ++i) { pinned_in[i] = !src[i] || is_pinned(src[i]); if (!pinned_in[i]) need += (sizes[i] + 255) & ~size_t(255); }
+    const bool z_pinned = pinned_in[0];
+    if (!z_pinned && need < ((n * 4 + 255) & ~size_t(255))) need = (n * 4 + 255) & ~size_t(255);
+    if (need > h->pin_bytes) {
+        if (h->pin_buf) { ST_CUDA(cudaStreamSynchronize(s)); cudaFreeHost(h->pin_buf); h->pin_buf = nullptr; h->pin_bytes = 0; }
+        ST_CUDA(cudaMallocHost((void**)&h->pin_buf, need));
+        h->pin_bytes = need;
+    }
+    size_t off = 0;
+    char* z_stage = nullptr;
+    for (int i = 0; i < 6; ++i) {
+        if (!src[i]) continue;
+        const void* from = src[i];
+        if (!pinned_in[i]) {
+            memcpy(h->pin_buf + off, src[i], sizes[i]);
+            from = h->pin_buf + off;
+            if (i == 0) z_stage = h->pin_buf + off;
+            off += (sizes[i] + 255) & ~size_t(255);
+        }
+        ST_CUDA(cudaMemcpyAsync(dst[i], from, sizes[i], cudaMemcpyHostToDevice, s));
     }
     if (st_solve(h, w.h_z, w.h_mu, w.h_mask, w.h_c, cfg ? w.h_fc : nullptr, cfg ? w.h_fs : nullptr, cfg_strength, t_span_host,
                  n_steps, method, B, T, stream))
         return 1;
-    ST_CUDA(cudaMemcpyAsync(z_inout_host, w.h_z, n * 4, cudaMemcpyDeviceToHost, s));
+    ST_CUDA(cudaMemcpyAsync(z_pinned ? (void*)z_inout_host : (void*)z_stage, w.h_z, n * 4, cudaMemcpyDeviceToHost, s));
     ST_CUDA(cudaStreamSynchronize(s));
+    if (!z_pinned) memcpy(z_inout_host, z_stage, n * 4);
     return 0;
 }
 
@@ -1055,7 +1168,7 @@ int st_align_expand(const float* mu_x, const float* x_mask, const float* cum, co
 int st_test_conv(st_handle* h, const float* x, const float* wgt, const float* bias, float* out, int B, int Cin, int Cout,
                  int T, int k, void* stream) {
     if (!h) return 1;
-    ST_CUDA(cudaSetDevice(h->device));
+    ST_ENTER(h);
     cudaStream_t s = (cudaStream_t)stream;
     const bool tc = h->engine == ST_ENGINE_TCGEN05;
     const size_t nx = (size_t)B * T * Cin, nw = (size_t)k * Cout * Cin, no = (size_t)B * T * Cout;
@@ -1086,7 +1199,7 @@ int st_test_conv(st_handle* h, const float* x, const float* wgt, const float* bi
 int st_test_gemm(st_handle* h, const float* A, const float* W, const float* bias, float* out, int R, int K, int N, int silu,
                  void* stream) {
     if (!h) return 1;
-    ST_CUDA(cudaSetDevice(h->device));
+    ST_ENTER(h);
     cudaStream_t s = (cudaStream_t)stream;
     const bool tc = h->engine == ST_ENGINE_TCGEN05;
     const size_t na = (size_t)R * K, nw = (size_t)N * K;
@@ -1124,7 +1237,7 @@ __global__ void fill_pattern_kernel(float* p, long n, uint32_t seed) {
 // when epi != 0 (bias, mask, gate, residual, fp32 + split outputs) or bias-only split output otherwise.
 int st_bench_conv(st_handle* h, int B, int Cin, int Cout, int T, int k, int epi, int reps, float* ms_out) {
     if (!h || !ms_out) return 1;
-    ST_CUDA(cudaSetDevice(h->device));
+    ST_ENTER(h);
     cudaStream_t s = 0;
     const bool tc = h->engine == ST_ENGINE_TCGEN05;
     const size_t nx = (size_t)B * T * Cin, nw = (size_t)k * Cout * Cin, no = (size_t)B * T * Cout;
@@ -1172,7 +1285,7 @@ int st_test_attention_trace(long long* host_out) { return st::attention_tc_read_
 
 int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* out, int B, int T, void* stream) {
     if (!h) return 1;
-    ST_CUDA(cudaSetDevice(h->device));
+    ST_ENTER(h);
     cudaStream_t s = (cudaStream_t)stream;
     const bool tc = h->engine == ST_ENGINE_TCGEN05;
     int *kvlen, *prefix; float* cs;

@@ -705,7 +705,7 @@ attention_tc5_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
 
 std::mutex g_att_mu;
 long long* g_att_trace = nullptr;
-bool g_att_attr = false;
+std::atomic<uint64_t> g_att_attr4{0}, g_att_attr5{0};   // one bit per device
 std::string g_att_err;
 
 }  // namespace
@@ -752,16 +752,10 @@ cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t s) {
     }
     static int use_v4 = -1;
     if (use_v4 < 0) { const char* e = getenv("STABLETTS_B200_ATT_V4"); use_v4 = (e && !strcmp(e, "1")) ? 1 : 0; }
-    if (!g_att_attr) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT5_SMEM);
+    {
+        cudaError_t e = ensure_dyn_smem(attention_tc4_kernel, ATT4_SMEM, g_att_attr4);
+        if (e == cudaSuccess) e = ensure_dyn_smem(attention_tc5_kernel, ATT5_SMEM, g_att_attr5);
         if (e != cudaSuccess) { g_att_err = "cudaFuncSetAttribute failed for the attention kernels"; return e; }
-        if (getenv("STABLETTS_B200_DEBUG")) {
-            int occ = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attention_tc5_kernel, A_THREADS, ATT5_SMEM);
-            fprintf(stderr, "[stabletts_b200] attention CTAs/SM: %d\n", occ);
-        }
-        g_att_attr = true;
     }
     dim3 grid((a.T + AQ - 1) / AQ, a.n_heads, a.BB);
     if (use_v4)        // A/B only: Q tile in shared memory, O_A / O_B (v4)

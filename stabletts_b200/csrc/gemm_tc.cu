@@ -197,7 +197,6 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 std::string g_err = "";
 std::mutex g_mu;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
-bool g_attr_set = false;
 
 struct MapKey {
     const void* ptr; uint64_t d0, d1, d2; uint32_t b0, b1; int rank;
@@ -268,10 +267,10 @@ cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t s) {
     p.m_tiles_per_b = (g.T + BLOCK_M - 1) / BLOCK_M;
     p.n_tiles = (g.N + BN - 1) / BN;
     p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
-    if (!g_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    {
+        static std::atomic<uint64_t> attr_done{0};  // one bit per device (per template instance)
+        cudaError_t e = ensure_dyn_smem(gemm_tc_kernel<BN>, C::SMEM_BYTES, attr_done);
         if (e != cudaSuccess) { g_err = "cudaFuncSetAttribute(max dynamic smem) failed"; return e; }
-        g_attr_set = true;
     }
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     return launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, s, maps, p);

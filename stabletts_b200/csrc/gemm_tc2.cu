@@ -215,13 +215,12 @@ static int pick_bn2(const GemmArgs& g, int pairs) {
 
 template <int BN2>
 static cudaError_t launch_tc2_bn(const Maps2& maps, Params2& p, const GemmArgs& g, int pairs, cudaStream_t s) {
-    static bool attr = false;
+    static std::atomic<uint64_t> attr_done{0};      // one bit per device
     p.n_tiles = (g.N + BN2 - 1) / BN2;
     p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN2>::SMEM_BYTES);
+    {
+        cudaError_t e = ensure_dyn_smem(gemm_tc2_kernel<BN2>, Cfg2<BN2>::SMEM_BYTES, attr_done);
         if (e != cudaSuccess) { g_err2 = "cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc2_kernel"; return e; }
-        attr = true;
     }
     const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
     return launch_k(gemm_tc2_kernel<BN2>, dim3(2 * clusters), dim3(THREADS), (size_t)Cfg2<BN2>::SMEM_BYTES, s, maps, p);

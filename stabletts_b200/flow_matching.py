@@ -5,14 +5,16 @@ cfg_kwargs=None)`` and ``cfg_wrapper``; ``.estimator`` is the drop-in ``Decoder`
 solve (every estimator evaluation, CFG as a doubled batch, the Runge–Kutta updates) is ONE call
 into the CUDA library, device-resident with no host synchronisation between steps.
 
-Solver strings: the fixed-grid ones (``'euler'``, ``'midpoint'``, ``'rk4'``) follow torchdiffeq's
+Solver strings (webui.py:110): the fixed-grid ones (``'euler'``, ``'midpoint'``, ``'rk4'``) follow torchdiffeq's
 published tableaux and run device-resident without any host synchronisation.  The reference's default
 ``solver=None`` (= ``'dopri5'``) is torchdiffeq's ADAPTIVE Dormand–Prince with ``rtol = atol = 1e-5``
 (models/flow_matching.py:54): here it runs ``st_solve_adaptive`` — same published algorithm (FSAL
 tableau, RMS mixed error norm, I-controller, dense output at t = 1), one 8-byte host read per step for
 accept/reject exactly like torchdiffeq on a GPU.  torchdiffeq itself is absent and unpinned, so that
-solver's parity is pinned only against ``oracle/adaptive_ref.py``.  ``'dopri5_fixed'`` steps the same
-tableau on the caller's grid without error control (BASELINE.json cfg2's "dopri5-equiv").
+solver's parity is pinned only against ``oracle/adaptive_ref.py``; ``'bosh3'``, ``'fehlberg2'`` and
+``'adaptive_heun'`` are further embedded tableaux on the same controller.  ``'dopri5_fixed'`` steps the
+Dormand-Prince tableau on the caller's grid without error control (BASELINE.json cfg2's "dopri5-equiv").
+``'implicit_adams'`` / ``'explicit_adams'`` raise ``ValueError`` (multistep methods are not built).
 """
 from __future__ import annotations
 
@@ -27,8 +29,11 @@ from .estimator import Decoder
 
 _METHODS = {"euler": _lib.ST_EULER, "midpoint": _lib.ST_MIDPOINT, "rk4": _lib.ST_RK4,
             "dopri5_fixed": _lib.ST_DOPRI5_FIXED}
-_ADAPTIVE = (None, "dopri5")
-ST_ADAPTIVE = -1
+# adaptive embedded Runge-Kutta tableaux of st_solve_adaptive_ex (webui.py:110 lists these strings)
+_ADAPTIVE = {None: _lib.ST_ADAPT_DOPRI5, "dopri5": _lib.ST_ADAPT_DOPRI5, "bosh3": _lib.ST_ADAPT_BOSH3,
+             "fehlberg2": _lib.ST_ADAPT_FEHLBERG2, "adaptive_heun": _lib.ST_ADAPT_HEUN}
+_STAGES = {_lib.ST_ADAPT_DOPRI5: 6, _lib.ST_ADAPT_BOSH3: 3, _lib.ST_ADAPT_FEHLBERG2: 2, _lib.ST_ADAPT_HEUN: 1}
+ST_ADAPTIVE = -1            # _method_id's answer for every adaptive solver; _ADAPTIVE picks the tableau
 
 
 def _method_id(solver):
@@ -36,7 +41,12 @@ def _method_id(solver):
         return ST_ADAPTIVE
     if solver in _METHODS:
         return _METHODS[solver]
-    raise ValueError(f"solver {solver!r} is not supported; use one of {sorted(_METHODS)} or None/'dopri5' (adaptive)")
+    if solver in ("implicit_adams", "explicit_adams"):
+        raise ValueError(f"solver {solver!r} (torchdiffeq's fixed-grid Adams-Bashforth(-Moulton) multistep method) is not built "
+                         f"in stabletts_b200; use one of {sorted(_METHODS)} (fixed grid) or "
+                         f"{sorted(k for k in _ADAPTIVE if k)} / None (adaptive)")
+    raise ValueError(f"solver {solver!r} is not supported; use one of {sorted(_METHODS)} (fixed grid) or "
+                     f"{sorted(k for k in _ADAPTIVE if k)} / None (adaptive)")
 
 
 class CFMDecoder(nn.Module):
@@ -86,11 +96,15 @@ class CFMDecoder(nn.Module):
         lib, h, stream = est._prepare(mu_, B, T, 0 if fc is None else 1)
         if method == ST_ADAPTIVE:                                                    # rtol = atol = 1e-5, :54
             stats = (C.c_int64 * 3)()
-            rc = lib.st_solve_adaptive(h, z.data_ptr(), mu_.data_ptr(), mask_.data_ptr(), c_.data_ptr(),
-                                       None if fc is None else fc.data_ptr(), None if fs is None else fs.data_ptr(),
-                                       strength, float(t_span[0]), float(t_span[-1]), 1e-5, 1e-5, 100000, B, T, stream, stats)
-            _lib.check(lib, h, rc, "st_solve_adaptive")
-            self.last_solver_stats = dict(accepted=int(stats[0]), rejected=int(stats[1]), nfe=int(stats[2]))
+            tableau = _ADAPTIVE[solver]
+            rc = lib.st_solve_adaptive_ex(h, tableau, z.data_ptr(), mu_.data_ptr(), mask_.data_ptr(), c_.data_ptr(),
+                                          None if fc is None else fc.data_ptr(), None if fs is None else fs.data_ptr(),
+                                          strength, float(t_span[0]), float(t_span[-1]), 1e-5, 1e-5, 100000, B, T, stream, stats)
+            _lib.check(lib, h, rc, "st_solve_adaptive_ex")
+            # torchdiffeq is absent/unpinned: this solver follows its published algorithm; parity with the package itself
+            # is UNPINNED (oracle/adaptive_ref.py) -- the stats say so for callers that log them
+            self.last_solver_stats = dict(solver=solver or "dopri5", accepted=int(stats[0]), rejected=int(stats[1]),
+                                          nfe=int(stats[2]), stages_per_step=_STAGES[tableau], parity="unpinned (torchdiffeq absent)")
             return z.to(mu.dtype)
         rc = lib.st_solve(h, z.data_ptr(), mu_.data_ptr(), mask_.data_ptr(), c_.data_ptr(),
                           None if fc is None else fc.data_ptr(), None if fs is None else fs.data_ptr(),

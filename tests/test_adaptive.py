@@ -54,6 +54,64 @@ def test_oracle_solution_agrees_with_scipy_rk45():
     assert 0.5 * len(sol.t) <= stats["accepted"] + 1 <= 2.0 * len(sol.t)
 
 
+def _order_conditions(tb, weights, p):
+    """Residuals of the Runge-Kutta order conditions up to order p (<= 3) for solution weights ``weights`` over the
+    S+1 stage derivatives (stage 0 at c = 0, stage i+1 at c = alpha[i] with row beta[i])."""
+    n = tb.stages + 1
+    c = [0.0] + list(tb.alpha)
+    A = [[0.0] * n for _ in range(n)]
+    for i, row in enumerate(tb.beta):
+        for j, v in enumerate(row):
+            A[i + 1][j] = v
+    res = [abs(sum(weights) - 1.0)]
+    if p >= 2:
+        res.append(abs(sum(w * ci for w, ci in zip(weights, c)) - 0.5))
+    if p >= 3:
+        res.append(abs(sum(w * ci * ci for w, ci in zip(weights, c)) - 1 / 3))
+        res.append(abs(sum(weights[i] * A[i][j] * c[j] for i in range(n) for j in range(n)) - 1 / 6))
+    return max(res)
+
+
+@pytest.mark.parametrize("method,p_sol,p_emb", [("bosh3", 3, 2), ("fehlberg2", 2, 1), ("adaptive_heun", 2, 1), ("dopri5", 3, 3)])
+def test_embedded_pairs_satisfy_their_order_conditions(method, p_sol, p_emb):
+    """The restated tableaux (torchdiffeq bosh3.py / fehlberg2.py / adaptive_heun.py, from the published pairs) are
+    consistent Runge-Kutta pairs: the solution weights meet the order conditions of the stated order, the embedded
+    weights (c_sol - c_error) those of one order less, every row of beta sums to its node."""
+    tb = AD.TABLEAUS[method]
+    assert _order_conditions(tb, list(tb.c_sol), p_sol) < 1e-14
+    emb = [a - b for a, b in zip(tb.c_sol, tb.c_error)]
+    assert _order_conditions(tb, emb, p_emb) < 1e-14
+    for al, row in zip(tb.alpha, tb.beta):
+        assert abs(sum(row) - al) < 1e-15
+    assert abs(sum(tb.c_error)) < 1e-15 and len(tb.c_mid) == tb.stages + 1
+    assert tb.sol_is_last_stage == (method in ("dopri5", "bosh3"))
+
+
+@pytest.mark.parametrize("method,tol", [("bosh3", 2e-5), ("fehlberg2", 2e-4), ("adaptive_heun", 2e-5)])
+def test_other_adaptive_tableaux_on_closed_form_ode(method, tol):
+    f = lambda t, y: -y + torch.sin(3 * t)
+    out, stats = AD.odeint_adaptive(f, torch.ones(3), method, 1.0, 1e-6, 1e-6)
+    exact = math.exp(-1) * 1.3 + (math.sin(3) - 3 * math.cos(3)) / 10
+    assert abs(float(out[0]) - exact) < tol, (method, float(out[0]) - exact, stats)
+    assert stats["nfe"] == 2 + AD.TABLEAUS[method].stages * (stats["accepted"] + stats["rejected"])
+
+
+def test_method_strings_of_the_reference_ui():
+    """webui.py:110 offers dopri5, euler, midpoint, rk4, implicit_adams, bosh3, fehlberg2, adaptive_heun: all but the
+    multistep Adams method map to a built solver; that one raises a ValueError naming the alternatives."""
+    from stabletts_b200.flow_matching import _method_id, _ADAPTIVE, ST_ADAPTIVE
+    from stabletts_b200 import _lib
+    for name in ("dopri5", "bosh3", "fehlberg2", "adaptive_heun", None):
+        assert _method_id(name) == ST_ADAPTIVE and name in _ADAPTIVE
+    assert _ADAPTIVE["bosh3"] == _lib.ST_ADAPT_BOSH3 and _ADAPTIVE["adaptive_heun"] == _lib.ST_ADAPT_HEUN
+    for name in ("euler", "midpoint", "rk4"):
+        assert _method_id(name) >= 0
+    with pytest.raises(ValueError, match="not built"):
+        _method_id("implicit_adams")
+    with pytest.raises(ValueError):
+        _method_id("no_such_solver")
+
+
 @pytest.mark.gpu
 def test_cuda_adaptive_vs_oracle():
     if not torch.cuda.is_available():
@@ -85,3 +143,35 @@ def test_cuda_adaptive_vs_oracle():
     assert max(e) < 1e-3, (e, stats, got)
     assert abs(got["accepted"] - stats["accepted"]) <= max(2, stats["accepted"] // 10), (stats, got)
     assert got["nfe"] == 2 + 6 * (got["accepted"] + got["rejected"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,stages", [("bosh3", 3), ("fehlberg2", 2), ("adaptive_heun", 1)])
+def test_cuda_other_adaptive_solvers_vs_oracle(method, stages):
+    """bosh3 / fehlberg2 / adaptive_heun through CFMDecoder.forward(solver=...) against the oracle restatement on the
+    estimator's (damped) vector field.  Low-order pairs at rtol = atol = 1e-5 take many steps: a short utterance."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as ge
+    ge.build()
+    from stabletts_b200 import CFMDecoder
+    dev = torch.device("cuda:0")
+    n_mel = 80
+    st = weights.make_state(cases.WEIGHT_SEED, n_mel)
+    for k in list(st):
+        if k.startswith("final_proj"):
+            st[k] = st[k] * 0.02
+    m = CFMDecoder(n_mel, n_mel, 256, n_mel, 1024, 4, 6, 3, 0.1, 256).eval()
+    m.estimator.load_state_dict(st, strict=True)
+    m = m.to(dev)
+    inp = weights.make_inputs(62, [24, 17], 24, n_mel)
+    z = inp["x"]
+    g = lambda t, y: R.estimator_forward(st, t, y, inp["mask"], inp["mu"], inp["c"])
+    with torch.inference_mode():
+        ref, stats = AD.odeint_adaptive(g, z, method)
+    out = m(inp["mu"].to(dev), inp["mask"].to(dev), 10, 1.0, inp["c"].to(dev), method, None, z=z.to(dev))
+    got = m.last_solver_stats
+    e = rel_errs(out, ref)
+    assert max(e) < 1e-3, (method, e, stats, got)
+    assert abs(got["accepted"] - stats["accepted"]) <= max(2, stats["accepted"] // 10), (stats, got)
+    assert got["nfe"] == 2 + stages * (got["accepted"] + got["rejected"]) and got["solver"] == method

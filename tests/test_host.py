@@ -87,8 +87,9 @@ def test_solver_names():
     assert _method_id("euler") == _lib.ST_EULER and _method_id("midpoint") == _lib.ST_MIDPOINT
     assert _method_id("rk4") == _lib.ST_RK4 and _method_id("dopri5_fixed") == _lib.ST_DOPRI5_FIXED
     assert _method_id(None) == ST_ADAPTIVE and _method_id("dopri5") == ST_ADAPTIVE     # the reference's default
+    assert _method_id("bosh3") == ST_ADAPTIVE                # further adaptive tableaux (webui.py:110)
     with pytest.raises(ValueError):
-        _method_id("bosh3")
+        _method_id("implicit_adams")
 
 
 def test_product_never_imports_oracle():
