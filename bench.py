@@ -6,15 +6,19 @@
 A "step" is one complete ``CFMDecoder.forward`` ODE solve over one batch of synthetic inputs
 (SURVEY.md §8d): weights = reference-style init under manual_seed(0) with the adaLN gates re-drawn
 N(0, 0.3²); inputs under manual_seed(1); z unmasked; CFG strength 3.
-  value  : frames/s with inputs already resident in HBM (device timed, max over ranks)
-  e2e    : the same metric through the public module call with PINNED HOST inputs — H2D copies of
-           (mu, mask, c, z) and the D2H read of the mel are inside the timed region
+  value  : frames/s with every rank's batch slice already resident in its HBM (device timed, max over ranks)
+  e2e    : the same metric through ``CFMDecoder.solve_host`` = ``st_solve_host`` of the C ABI with PINNED HOST
+           buffers — the H2D copies of (mu, mask, c, z), the solve, the D2H read of the mel and the stream
+           synchronisation are inside the call and inside the timed region, per rank
   roofline: the tcgen05 conv-GEMM class (dominant kernel): algorithmic FLOPs / CUDA-event time of
            every launch in one instrumented solve, against MEASURED_PEAKS.json's sustained bf16 peak
-  cpu_baseline / --impl reference: the oracle port of the reference's PyTorch path on host cores
-           (bounded sample), the only place this file executes anything under oracle/.
-Multi-GPU (torchrun, one rank per GPU): weak scaling, the per-GPU batch is fixed; rank 0 owns the
-global batch, scatters (mu, mask, c, z) and gathers the mel over NCCL inside the timed region.
+  cpu_baseline / --impl reference: the reference's own CPU path — the genuine modules staged under
+           baseline/_ref (kind "reference"; oracle port if nothing is staged) — on host cores, bounded sample
+  parity : utterances {first, second, middle, last} of the measured batch re-solved on the CPU (checker only)
+Multi-GPU (torchrun, one rank per GPU): weak scaling, the per-GPU batch is fixed, every rank owns its slice
+(value / e2e); the rank-0-owns-everything NCCL scatter/gather variant is timed beside it (root_scatter_gather,
+with the scatter+gather alone reported separately); at N = 8 BASELINE cfg4 as written (1024 = 128 per GPU)
+rides along under the key "cfg4".
 """
 from __future__ import annotations
 
@@ -158,28 +162,91 @@ def cpu_threads() -> int:
     return usable_cpus()
 
 
-def cpu_reference_solve(state, inp, cfgd, B, budget_s=25.0):
-    """The oracle port (the reference's own PyTorch CPU path restated) on a BOUNDED sample: the first B
-    utterances; if a probe evaluation predicts the full-NFE solve would exceed ``budget_s`` the number
-    of ODE steps is cut (same grid spacing semantics, fewer steps) and the throughput is scaled to the
-    full NFE.  Returns (output or None if truncated, seconds-equivalent for the FULL solve, note)."""
-    from oracle import estimator_ref as R
-    sl = slice(0, B)
+class CpuArm:
+    """The reference's CPU path for this workload: the GENUINE ``models.flow_matching.CFMDecoder`` /
+    ``models.estimator.Decoder`` staged unmodified under baseline/_ref (oracle/stage_reference.py; ``kind`` =
+    "reference") with the fixed-grid stepping of the absent torchdiffeq restated, or — when nothing is staged — the
+    oracle port (``kind`` = "port").  One of the two places bench.py executes anything under oracle/ (the other is the
+    parity check)."""
+
+    def __init__(self, state):
+        from oracle import stage_reference as SR
+        self.state = state
+        self.kind = "port"
+        self.model = None
+        if SR.available():
+            try:
+                _, RefCFM = SR.load_reference()
+                m = RefCFM(N_MEL, N_MEL, 256, N_MEL, 1024, 4, 6, 3, 0.1, 256).eval()
+                m.estimator.load_state_dict(state, strict=True)
+                self.model, self.kind = m, "reference"
+            except Exception as e:                     # noqa: BLE001 — fall back to the port, say why
+                self.note = f"staged reference failed to import ({e}); oracle port used"
+
+    def estimator_call(self, inp):
+        from oracle import estimator_ref as R
+        with torch.inference_mode():
+            if self.model is not None:
+                return self.model.estimator(torch.tensor(0.5), inp["z"], inp["mask"], inp["mu"], inp["c"])
+            return R.estimator_forward(self.state, torch.tensor(0.5), inp["z"], inp["mask"], inp["mu"], inp["c"])
+
+    def solve(self, inp, steps, method, kw):
+        """CFMDecoder.forward semantics with the noise injected (the reference draws randn_like(mu) from the global RNG:
+        the draw is replaced by the workload's z through a one-shot patch of torch.randn_like)."""
+        from oracle import estimator_ref as R
+        if self.model is None:
+            return R.cfm_forward(self.state, inp["mu"], inp["mask"], steps, inp["z"], inp["c"], method, kw)
+        orig = torch.randn_like
+        torch.randn_like = lambda *_a, **_k: inp["z"].clone()
+        try:
+            with torch.inference_mode():
+                return self.model(inp["mu"], inp["mask"], steps, 1.0, inp["c"], method, kw)
+        finally:
+            torch.randn_like = orig
+
+
+def take_rows(inp, rows):
+    idx = torch.as_tensor(rows)
+    out = {k: inp[k][idx].contiguous() for k in ("mu", "mask", "c", "z")}
+    out["lens"] = inp["lens"][idx]
+    Tm = int(out["lens"].max())
+    Tc = min(inp["T"], Tm + 4)                  # >= 4 pad frames: crop-invariant with and without CFG
+    for k in ("mu", "mask", "z"):
+        out[k] = out[k][:, :, :Tc].contiguous()
+    out["T"] = Tc
+    return out
+
+
+def cpu_reference_solve(arm, inp, cfgd, rows, budget_s=25.0):
+    """The CPU arm on a BOUNDED sample: the utterances ``rows`` of the workload; if a probe evaluation predicts that
+    the full-NFE solve exceeds ``budget_s`` first the row set is halved (keeping first and last), then the number of ODE
+    steps is cut and the throughput scaled to the full NFE.  Returns (rows used, output or None if truncated,
+    seconds-equivalent for the FULL solve of those rows, note)."""
     kw = None if cfgd["cfg"] is None else dict(fake_speaker=inp["fs"], fake_content=inp["fc"], cfg_strength=cfgd["cfg"])
     per_step = NFE_PER_STEP[cfgd["method"]] * (2 if kw else 1)
-    with torch.inference_mode():
+    rows = list(rows)
+    while True:
+        sub = take_rows(inp, rows)
         t0 = time.perf_counter()
-        R.estimator_forward(state, torch.tensor(0.5), inp["z"][sl], inp["mask"][sl], inp["mu"][sl], inp["c"][sl])
+        arm.estimator_call(sub)
         probe = time.perf_counter() - t0
+        if probe * per_step * cfgd["n_steps"] <= budget_s or len(rows) <= 2:
+            break
+        rows = [rows[0], rows[-1]]
     steps = cfgd["n_steps"]
     if probe * per_step * steps > budget_s:
         steps = max(1, int(budget_s / (probe * per_step)))
     t0 = time.perf_counter()
-    out = R.cfm_forward(state, inp["mu"][sl], inp["mask"][sl], steps, inp["z"][sl], inp["c"][sl], cfgd["method"], kw)
+    out = arm.solve(sub, steps, cfgd["method"], kw)
     dt = time.perf_counter() - t0
     if steps == cfgd["n_steps"]:
-        return out, dt, f"full NFE={per_step * steps}"
-    return None, dt * cfgd["n_steps"] / steps, f"{steps} of {cfgd['n_steps']} ODE steps timed ({dt:.1f} s), scaled to the full NFE"
+        return rows, out, dt, f"full NFE={per_step * steps}"
+    return rows, None, dt * cfgd["n_steps"] / steps, f"{steps} of {cfgd['n_steps']} ODE steps timed ({dt:.1f} s), scaled to the full NFE"
+
+
+def sample_rows(B):
+    """first, second, middle and last utterance of a batch (a batch-offset bug in the later rows must show)."""
+    return sorted(set([0, min(1, B - 1), B // 2, B - 1]))
 
 
 def run_reference(args, cfgd, rank):
@@ -189,26 +256,228 @@ def run_reference(args, cfgd, rank):
     torch.set_num_threads(threads)
     model = make_model(None)
     state = {k: v.detach().clone() for k, v in model.estimator.state_dict().items()}
-    Bs = 1
-    inp = make_inputs(cfgd, max(Bs, 2))
-    frames = int(inp["lens"][:Bs].sum())
-    budget = max(5.0, 150.0 / max(args.steps + 1, 1))          # whole run within a few minutes
+    arm = CpuArm(state)
+    inp = make_inputs(cfgd, cfgd["B"])
+    set_cfg_params(inp, cfgd)
+    rows = sample_rows(cfgd["B"])
+    budget = max(5.0, 150.0 / max(args.steps + max(args.warmup, 0) / 4 + 1, 1))          # whole run within a few minutes
     if args.warmup > 0:
-        cpu_reference_solve(state, inp, cfgd, Bs, budget_s=budget / 4)
-    t, note = 0.0, ""
+        cpu_reference_solve(arm, inp, cfgd, rows, budget_s=budget / 4)
+    t, note, used, frames = 0.0, "", rows, 0
     for _ in range(args.steps):
-        _, dt, note = cpu_reference_solve(state, inp, cfgd, Bs, budget_s=budget)
+        used, _, dt, note = cpu_reference_solve(arm, inp, cfgd, rows, budget_s=budget)
         t += dt
-    val = frames * args.steps / t
-    sample = f"B={Bs} utterance of the workload at T={inp['T']} per step; {note}; {threads} torch threads"
+        frames += int(inp["lens"][torch.as_tensor(used)].sum())
+    val = frames / t
+    sample = (f"utterances {used} of the workload (B={len(used)}, BASELINE.md §4) per step; {note}; {threads} torch threads; "
+              f"{'genuine reference modules from baseline/_ref' if arm.kind == 'reference' else 'oracle port'}")
     line = {"impl": "reference", "metric": "mel-frames/sec through CFM DiT estimator (ODE solve, all evaluations)",
             "value": val, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}: {cfgd['desc']} (CPU sample: {sample})"},
-            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": arm.kind, "sample": sample},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def set_cfg_params(inp, cfgd):
+    """fake_* are model parameters (models/model.py:43-44): replicated like the weights, same on every rank."""
+    if cfgd["cfg"] is not None:
+        g = torch.Generator().manual_seed(2)
+        inp["fs"], inp["fc"] = torch.randn(1, 256, generator=g), torch.randn(1, N_MEL, 1, generator=g)
+
+
+def run_config(args, name, model, dev, rank, world, steps, warmup, flush, *, full=True):
+    """Measures one BASELINE config on this process group.  Every rank generates the same seeded GLOBAL batch on the
+    host and keeps its own contiguous slice (pinned): a one-process-per-GPU server owns its requests' buffers.
+      value  : every rank's slice resident in its HBM, no collective in the timed region ("per_rank_inputs")
+      e2e    : every rank uploads its own pinned slice and downloads its own mel through CFMDecoder.solve_host
+               (= st_solve_host of the C ABI: H2D + solve + D2H + stream sync inside the call)
+      root_scatter_gather (N > 1): rank 0 owns the global batch in HBM, NCCL scatter -> solve -> gather inside the timed
+               region; the scatter+gather alone is timed separately."""
+    import torch.distributed as dist
+    from stabletts_b200 import _lib, shard
+    cfgd = CONFIGS[name]
+    Bper = cfgd["B"]
+    Bglob = Bper * world
+    inp = make_inputs(cfgd, Bglob)
+    set_cfg_params(inp, cfgd)
+    T = inp["T"]
+    sl = slice(rank * Bper, (rank + 1) * Bper)
+    kw = kw_host = None
+    if cfgd["cfg"] is not None:
+        kw_host = dict(fake_speaker=inp["fs"], fake_content=inp["fc"], cfg_strength=cfgd["cfg"])
+        kw = dict(fake_speaker=inp["fs"].to(dev), fake_content=inp["fc"].to(dev), cfg_strength=cfgd["cfg"])
+    pinned = {k: inp[k][sl].contiguous().pin_memory() for k in ("mu", "mask", "c", "z")}
+    local = {k: pinned[k].to(dev) for k in pinned}
+    lens_local = [int(v) for v in inp["lens"][sl]]
+    out_pinned = torch.empty(Bper, N_MEL, T, dtype=torch.float32).pin_memory()
+    frames_global = int(inp["lens"].sum())
+    bucketed = cfgd["lengths"] is not None
+
+    def solve_one(mu, mask, c, z):
+        return model(mu, mask, cfgd["n_steps"], 1.0, c, cfgd["method"], kw, z=z)
+
+    def solve(mu, mask, c, z, lens=None):
+        if not bucketed:
+            return solve_one(mu, mask, c, z)
+        lens = lens if lens is not None else mask.sum(dim=(1, 2)).long().tolist()    # host-visible lengths (bucketing is host logic)
+        return shard.bucketed_solve(solve_one, mu, mask, c, z, lens, n_buckets=4)
+
+    def step_device():
+        return solve(local["mu"], local["mask"], local["c"], local["z"], lens_local)
+
+    def step_e2e():
+        if not bucketed:
+            return model.solve_host(pinned["mu"], pinned["mask"], cfgd["n_steps"], 1.0, pinned["c"], cfgd["method"], kw_host,
+                                    z=pinned["z"], out=out_pinned)
+        out_pinned.zero_()
+        for idx in shard.length_buckets(lens_local, 4):              # host tensors are cropped per bucket on the host
+            Tb = min(T, max(lens_local[i] for i in idx) + 4)
+            sel = torch.as_tensor(idx)
+            o = model.solve_host(pinned["mu"][sel][:, :, :Tb].contiguous(), pinned["mask"][sel][:, :, :Tb].contiguous(),
+                                 cfgd["n_steps"], 1.0, pinned["c"][sel].contiguous(), cfgd["method"], kw_host,
+                                 z=pinned["z"][sel][:, :, :Tb].contiguous())
+            out_pinned[sel, :, :Tb] = o
+        return out_pinned
+
+    glob = None
+    if world > 1 and rank == 0:
+        glob = {k: inp[k].to(dev) for k in ("mu", "mask", "c", "z")}
+
+    def step_sg(fn=None):
+        a = (glob["mu"], glob["mask"], glob["c"], glob["z"]) if rank == 0 else (None,) * 4
+        return shard.sharded_solve(fn or solve, *a, device=dev, batch=Bglob, n_mel=N_MEL, T=T, gin=256)
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        ev[0].record()
+        out = None
+        for i in range(n):
+            flush.zero_()
+            out = fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev[0].elapsed_time(ev[n])], device=dev)
+        per = [round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(n)]    # diagnostics (this rank)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out, per
+
+    remeasured = []
+
+    def timed_checked(fn, n, tag):
+        """K timed steps; if one step is an outlier (> 1.5x the median: a host stall or a driver hiccup starves the GPU
+        for tens of ms about once in a dozen runs) the whole K-step region is measured ONCE more and the repeat is kept;
+        the JSON line says so.  The decision is rank 0's, broadcast, so every rank repeats or none does."""
+        ms, out, per = timed(fn, n)
+        med = sorted(per)[len(per) // 2]
+        again = torch.tensor([1 if (n >= 3 and max(per) > 1.5 * med) else 0], device=dev)
+        if world > 1:
+            dist.broadcast(again, 0)
+        if int(again.item()) and not args.ncu_mode:
+            remeasured.append({"region": tag, "first_attempt_step_ms": per[:32]})
+            ms, out, per = timed(fn, n)
+        return ms, out, per
+
+    # warm-up: at least W untimed steps AND ~2 s of load (under the 1 kW cap the SM clock needs about a second to
+    # settle); the extra count is decided on rank 0 and broadcast so every rank does the same.
+    tw0 = time.perf_counter()
+    for _ in range(warmup):
+        flush.zero_()                   # same ops as a timed step: torch lazy-loads its fill kernel's module on first use
+        step_device()
+    torch.cuda.synchronize()
+    el = time.perf_counter() - tw0
+    extra = 0 if args.ncu_mode else int(max(0.0, 2.0 - el) / max(el / max(warmup, 1), 1e-4)) + 1
+    if world > 1:
+        ex_t = torch.tensor([extra], device=dev)
+        dist.broadcast(ex_t, 0)
+        extra = int(ex_t.item())
+    for _ in range(extra):
+        flush.zero_()
+        step_device()
+    timed(step_device, 1)               # one untimed pass through the timing harness itself (events, all_reduce)
+    n_warm = warmup + extra + 1
+    torch.cuda.synchronize()
+    th0 = time.perf_counter()
+    step_device()                       # host-side enqueue time of one step (no sync): launch-bound check
+    host_ms = (time.perf_counter() - th0) * 1e3
+    torch.cuda.synchronize()
+    l0 = model.estimator.launch_count()
+    ms_dev, out_dev, per_dev = timed_checked(step_device, steps, "value")
+    launches = (model.estimator.launch_count() - l0) // (2 if any(r["region"] == "value" for r in remeasured) else 1)
+    res = {"name": name, "cfgd": cfgd, "Bglob": Bglob, "T": T, "frames": frames_global, "ms_dev": ms_dev, "per_dev": per_dev,
+           "launches": int(launches), "host_ms": host_ms, "n_warm": n_warm, "remeasured": remeasured, "inp": inp}
+    if args.ncu_mode:
+        return res
+    step_e2e()
+    ms_e2e, _, per_e2e = timed_checked(step_e2e, steps, "e2e")
+    res.update(ms_e2e=ms_e2e, per_e2e=per_e2e, h2d=sum(pinned[k].numel() * 4 for k in pinned) * world,
+               d2h=Bglob * N_MEL * T * 4)
+    out_global = None
+    if world > 1:
+        n_sg = min(steps, 3)
+        step_sg()
+        ms_sg, out_global, per_sg = timed_checked(step_sg, n_sg, "root_scatter_gather")
+        ident = lambda mu, mask, c, z: z                 # scatter + gather alone (no solve)
+        step_sg(ident)
+        ms_only, _, _ = timed(lambda: step_sg(ident), n_sg)
+        res["sg"] = {"ms_per_step": ms_sg / n_sg, "value": frames_global * n_sg / (ms_sg * 1e-3), "steps": n_sg,
+                     "scatter_gather_only_ms": ms_only / n_sg, "step_ms": per_sg,
+                     "what": "rank 0 owns the global batch in HBM; NCCL P2P scatter of (mu, mask, c, z), solve, gather of the mel, all inside the timed region"}
+
+    # parity: first / second / middle / last utterance re-solved by the CPU arm (the checker) — on the gathered global
+    # batch when N > 1 (rank 0), so a wrong slice offset on ANY rank would show
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = cpu_threads()
+        torch.set_num_threads(threads)
+        state = {k: v.detach().cpu().clone() for k, v in model.estimator.state_dict().items()}
+        arm = CpuArm(state)
+        got = out_global if out_global is not None else out_dev
+        nb = Bglob if out_global is not None else Bper
+        rows, ref, dt, note = cpu_reference_solve(arm, inp, cfgd, sample_rows(nb), budget_s=args.cpu_budget)
+        fr = int(inp["lens"][torch.as_tensor(rows)].sum())
+        if world == 1 and full:
+            res["cpu_baseline"] = {"value": fr / dt, "unit": "frames/s", "cores": threads, "kind": arm.kind,
+                                   "sample": f"utterances {rows} of the batch (T={T}); {note}; os.cpu_count()={os.cpu_count()}"}
+        if ref is not None:
+            Tc = ref.shape[-1]
+            d = got[torch.as_tensor(rows, device=got.device)][:, :, :Tc].cpu().double() - ref.double()
+            res["parity"] = {"max_rel": float(d.abs().max() / ref.abs().max()), "l2_rel": float(d.norm() / ref.double().norm()),
+                             "rows": rows, "vs": f"CPU {arm.kind} on the same inputs, full solve, utterances {rows} of the "
+                                                 f"{'gathered global' if out_global is not None else 'measured'} batch"}
+        else:
+            res["parity"] = {"max_rel": None, "note": f"full-NFE CPU solve exceeds --cpu-budget ({note})"}
+
+    # instrumented solve: per-class CUDA-event timing of every launch (roofline) — rank 0's slice, no collectives
+    if full and rank == 0:
+        lib, h = _lib.load_library(), model.estimator._handle
+        lib.st_profile_begin(h)
+        step_device()
+        n = _lib.ST_PROF_NCAT
+        ms_a, fl_a, by_a, ln_a = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+        lib.st_profile_end(h, ms_a, fl_a, by_a, ln_a)
+        prof = {nm: dict(ms=ms_a[i], flops=fl_a[i], bytes=by_a[i], launches=int(ln_a[i])) for i, nm in enumerate(_lib.ST_PROF_NAMES)}
+        prof["gemm"] = {k: sum(v[k] for n_, v in prof.items() if n_.startswith("gemm_")) for k in ("ms", "flops", "bytes", "launches")}
+        res["prof"] = prof
+    if world > 1:
+        dist.barrier()
+    del local, glob
+    torch.cuda.empty_cache()
+    return res
+
+
+def work_flops(cfgd, lens):
+    nfe = cfgd["n_steps"] * NFE_PER_STEP[cfgd["method"]] * (2 if cfgd["cfg"] is not None else 1)
+    lens = lens.double()
+    hoisted = float(((nfe * (32.948e6 - COND_FLOPS) + COND_FLOPS) * lens + nfe * 6144.0 * lens * lens).sum())
+    faithful = float((nfe * (32.948e6 * lens + 6144.0 * lens * lens)).sum())
+    return nfe, hoisted, faithful
 
 
 def main():
@@ -220,6 +489,8 @@ def main():
     ap.add_argument("--config", default="cfg1", choices=list(CONFIGS))
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=30.0, help="seconds of CPU work for the cpu_baseline / parity leg")
+    ap.add_argument("--no-cfg4", action="store_true", help="at N=8 skip the additional BASELINE cfg4 block (128/GPU = 1024 global)")
     ap.add_argument("--ncu-mode", action="store_true",
                     help="for `ncu` launch lists only: honours --warmup < 3, skips e2e / instrumented / CPU legs (numbers printed under a profiler are never bench values)")
     args = ap.parse_args()
@@ -239,164 +510,26 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    from stabletts_b200 import _lib, shard
 
     model = make_model(dev)
     model.estimator.set_engine(args.engine)
-    Bper = cfgd["B"]
-    Bglob = Bper * world
-    inp = make_inputs(cfgd, Bglob) if rank == 0 else None
-    T = cfgd["T"] if cfgd["lengths"] is None else None
-    if world > 1:
-        hdr = torch.tensor([inp["T"] if rank == 0 else 0], device=dev)
-        dist.broadcast(hdr, 0)
-        T = int(hdr.item())
-    else:
-        T = inp["T"]
-    kw = None
-    fs_d, fc_d = None, None
-    if cfgd["cfg"] is not None:
-        # fake_* are model parameters (models/model.py:43-44): replicated like the weights
-        torch.manual_seed(2)
-        fs_d, fc_d = torch.randn(1, 256).to(dev), torch.randn(1, N_MEL, 1).to(dev)
-        if rank == 0:
-            inp["fs"], inp["fc"] = fs_d.cpu(), fc_d.cpu()
-        kw = dict(fake_speaker=fs_d, fake_content=fc_d, cfg_strength=cfgd["cfg"])
-
-    def solve_one(mu, mask, c, z):
-        return model(mu, mask, cfgd["n_steps"], 1.0, c, cfgd["method"], kw, z=z)
-
-    def solve(mu, mask, c, z):
-        if cfgd["lengths"] is None:
-            return solve_one(mu, mask, c, z)
-        lens_local = mask.sum(dim=(1, 2)).long().tolist()       # host-visible lengths (bucketing is host logic)
-        return shard.bucketed_solve(solve_one, mu, mask, c, z, lens_local, n_buckets=4)
-
-    # device-resident global inputs on rank 0
-    if rank == 0:
-        g = {k: inp[k].to(dev) for k in ("mu", "mask", "c", "z")}
-        pinned = {k: inp[k].pin_memory() for k in ("mu", "mask", "c", "z")}
-        frames_global = int(inp["lens"].sum())
-    else:
-        g, pinned, frames_global = None, None, 0
-
-    def step_device():
-        if world == 1:
-            return solve(g["mu"], g["mask"], g["c"], g["z"])
-        return shard.sharded_solve(solve, *((g["mu"], g["mask"], g["c"], g["z"]) if rank == 0 else (None,) * 4), device=dev,
-                                   batch=Bglob, n_mel=N_MEL, T=T, gin=256)
-
-    def step_e2e():
-        if rank == 0:
-            d = {k: pinned[k].to(dev, non_blocking=True) for k in pinned}
-        if world == 1:
-            out = solve(d["mu"], d["mask"], d["c"], d["z"])
-        else:
-            out = shard.sharded_solve(solve, *((d["mu"], d["mask"], d["c"], d["z"]) if rank == 0 else (None,) * 4), device=dev,
-                                      batch=Bglob, n_mel=N_MEL, T=T, gin=256)
-        return out.cpu() if rank == 0 else None
-
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-
-    def timed(fn, steps):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-        ev[0].record()
-        out = None
-        for i in range(steps):
-            flush.zero_()
-            out = fn()
-            ev[i + 1].record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([ev[0].elapsed_time(ev[steps])], device=dev)
-        timed.per_step = [round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(steps)]    # diagnostics (this rank)
-        if world > 1:
-            dist.barrier()
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), out
-
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                 # started BEFORE warm-up: nvidia-smi start-up stalls the driver for ~100 ms
-    # at least W untimed steps AND ~2 s of load: under the 1 kW cap the SM clock needs about a second to settle
-    # (the first few hundred ms run at 1965 MHz, then the power controller pulls back and briefly overshoots).
-    # The extra count is decided on rank 0 and broadcast so every rank issues the same number of collectives.
-    tw0 = time.perf_counter()
-    for _ in range(args.warmup):
-        flush.zero_()                   # same ops as a timed step: torch lazy-loads its fill kernel's module on first use
-        step_device()                   # (hundreds of ms on a cold box) and that must not land in the timed region
-    torch.cuda.synchronize()
-    el = time.perf_counter() - tw0
-    extra = 0 if args.ncu_mode else int(max(0.0, 2.0 - el) / max(el / max(args.warmup, 1), 1e-4)) + 1
-    if world > 1:
-        ex_t = torch.tensor([extra], device=dev)
-        dist.broadcast(ex_t, 0)
-        extra = int(ex_t.item())
-    for _ in range(extra):
-        flush.zero_()
-        step_device()
-    timed(step_device, 1)               # one untimed pass through the timing harness itself (events, all_reduce)
-    n_warm = args.warmup + extra + 1
-    torch.cuda.synchronize()
-    th0 = time.perf_counter()
-    step_device()                       # host-side enqueue time of one step (no sync): launch-bound check
-    host_ms = (time.perf_counter() - th0) * 1e3
-    torch.cuda.synchronize()
-    l0 = model.estimator.launch_count()
-    remeasured = []
-
-    def timed_checked(fn, steps, tag):
-        """K timed steps; if one step is an outlier (> 1.5x the median: a host stall or a driver hiccup starves the GPU
-        for tens of ms about once in a dozen runs) the whole K-step region is measured ONCE more and the repeat is kept;
-        the JSON line says so.  The decision is rank 0's, broadcast, so every rank repeats or none does."""
-        ms, out = timed(fn, steps)
-        per = list(timed.per_step)
-        med = sorted(per)[len(per) // 2]
-        again = torch.tensor([1 if (steps >= 3 and max(per) > 1.5 * med) else 0], device=dev)
-        if world > 1:
-            dist.broadcast(again, 0)
-        if int(again.item()) and not args.ncu_mode:
-            remeasured.append({"region": tag, "first_attempt_step_ms": per[:32]})
-            ms, out = timed(fn, steps)
-            per = list(timed.per_step)
-        return ms, out, per
-
-    ms_dev, out_dev, per_step_dev = timed_checked(step_device, args.steps, "value")
-    launches = (model.estimator.launch_count() - l0) // (2 if any(r["region"] == "value" for r in remeasured) else 1)
+    r = run_config(args, args.config, model, dev, rank, world, args.steps, args.warmup, flush, full=True)
     if args.ncu_mode:
         if rank == 0:
             sampler.stop()
-            print(json.dumps({"ncu_mode": True, "ms_per_step_under_profiler": ms_dev / args.steps, "gpu_launches": int(launches)}))
+            print(json.dumps({"ncu_mode": True, "ms_per_step_under_profiler": r["ms_dev"] / args.steps, "gpu_launches": r["launches"]}))
         if world > 1:
             dist.destroy_process_group()
         return
-    for _ in range(1):
-        step_e2e()
-    ms_e2e, _, per_step_e2e = timed_checked(step_e2e, args.steps, "e2e")
     clocks = sampler.stop() if rank == 0 else None
-
-    # instrumented solve: per-class CUDA-event timing of every launch (roofline)
-    lib, h = _lib.load_library(), model.estimator._handle
-    prof = None
-    if rank == 0 or world == 1:
-        lib.st_profile_begin(h)
-        if world == 1:
-            step_device()
-        else:
-            sl = slice(0, Bper)
-            solve(g["mu"][sl].contiguous(), g["mask"][sl].contiguous(), g["c"][sl].contiguous(), g["z"][sl].contiguous())
-        n = _lib.ST_PROF_NCAT
-        ms_a, fl_a, by_a, ln_a = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
-        lib.st_profile_end(h, ms_a, fl_a, by_a, ln_a)
-        prof = {name: dict(ms=ms_a[i], flops=fl_a[i], bytes=by_a[i], launches=int(ln_a[i]))
-                for i, name in enumerate(_lib.ST_PROF_NAMES)}
-        prof["gemm"] = {k: sum(v[k] for n_, v in prof.items() if n_.startswith("gemm_")) for k in ("ms", "flops", "bytes", "launches")}
-    if world > 1:
-        # non-root ranks must take part in nothing here; keep ranks aligned
-        dist.barrier()
-
+    # BASELINE cfg4 AS WRITTEN (batch 1024 over 8 GPUs = 128 per GPU) rides along in the N = 8 run of the default config
+    r4 = None
+    if world == 8 and args.config == "cfg1" and not args.no_cfg4:
+        r4 = run_config(args, "cfg4", model, dev, rank, world, min(args.steps, 3), 3, flush, full=False)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -414,51 +547,43 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))["dram_bytes_per_launch_avg"]
     except Exception:
         pass
+    prof = r["prof"]
     gm = prof["gemm"]
     ach_tf = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
-    nfe = cfgd["n_steps"] * NFE_PER_STEP[cfgd["method"]] * (2 if cfgd["cfg"] is not None else 1)
-    lens = inp["lens"].double()
-    hoisted = float(((nfe * (32.948e6 - COND_FLOPS) + COND_FLOPS) * lens + nfe * 6144.0 * lens * lens).sum())
-    faithful = float((nfe * (32.948e6 * lens + 6144.0 * lens * lens)).sum())
-    sec_step = ms_dev * 1e-3 / args.steps
-    value = frames_global * args.steps / (ms_dev * 1e-3)
-    e2e_val = frames_global * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(pinned[k].numel() * 4 for k in pinned)
-    d2h = Bglob * N_MEL * T * 4
+    nfe, hoisted, faithful = work_flops(cfgd, r["inp"]["lens"])
+    sec_step = r["ms_dev"] * 1e-3 / args.steps
+    value = r["frames"] * args.steps / (r["ms_dev"] * 1e-3)
+    e2e_val = r["frames"] * args.steps / (r["ms_e2e"] * 1e-3)
 
-    cpu_baseline = None
-    parity = None
-    if not args.no_cpu_baseline and world == 1:
-        threads = cpu_threads()
-        torch.set_num_threads(threads)
-        state = {k: v.detach().cpu().clone() for k, v in model.estimator.state_dict().items()}
-        Bs = 1
-        ref, dt, note = cpu_reference_solve(state, inp, cfgd, Bs, budget_s=25.0)
-        fr = int(inp["lens"][:Bs].sum())
-        cpu_baseline = {"value": fr / dt, "unit": "frames/s", "cores": threads, "kind": "port",
-                        "sample": f"first utterance of the batch at T={T}; {note}; os.cpu_count()={os.cpu_count()}"}
-        if ref is not None:
-            d = (out_dev[:Bs].cpu().double() - ref.double())
-            parity = {"max_rel": float(d.abs().max() / ref.abs().max()), "l2_rel": float(d.norm() / ref.double().norm()),
-                      "vs": "oracle port on the same inputs, first utterance, full solve"}
+    def block(rr, n_steps):
+        b = {"workload": f"{rr['name']}: {rr['cfgd']['desc']}", "global_batch": rr["Bglob"], "T": rr["T"], "frames_per_step": rr["frames"],
+             "steps": n_steps, "value": rr["frames"] * n_steps / (rr["ms_dev"] * 1e-3), "ms_per_step": rr["ms_dev"] / n_steps,
+             "e2e": {"value": rr["frames"] * n_steps / (rr["ms_e2e"] * 1e-3), "ms_per_step": rr["ms_e2e"] / n_steps,
+                     "h2d_bytes_per_step": rr["h2d"], "d2h_bytes_per_step": rr["d2h"]},
+             "root_scatter_gather": rr.get("sg"), "parity": rr.get("parity"), "step_ms": rr["per_dev"], "unit": "frames/s"}
+        return b
 
     line = {
         "metric": "mel-frames/sec through CFM DiT estimator (ODE solve, all evaluations)",
-        "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "warmup_steps_run": n_warm,
+        "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "warmup_steps_run": r["n_warm"],
         "ms_per_step": 1e3 * sec_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (split-bf16x3 tensor-core operands, fp32 accumulate)" if args.engine == "tcgen05" else "f32",
         "data": "synthetic",
-        "config": {"workload": f"{args.config}: {cfgd['desc']}", "global_batch": Bglob, "T": T, "nfe": nfe,
-                   "frames_per_step": frames_global, "parallelism": f"batch-shard x{world}",
+        "config": {"workload": f"{args.config}: {cfgd['desc']}", "global_batch": r["Bglob"], "T": r["T"], "nfe": nfe,
+                   "frames_per_step": r["frames"], "parallelism": f"batch-shard x{world}",
+                   "inputs": "every rank owns its contiguous batch slice (value: resident in its HBM; e2e: its own pinned host buffers); "
+                             "the rank-0 NCCL scatter/gather variant is reported under root_scatter_gather",
                    "l2": "256 MiB flush between steps; per-eval working set (~1.5 GB) exceeds the 126 MB L2",
                    "engine": args.engine},
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                    "samples": clocks["samples"], "power_w_max": clocks.get("power_w_max")},
-        "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 2),
-        "step_ms": {"value": per_step_dev[:32], "e2e": per_step_e2e[:32]}, "remeasured": remeasured,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 split-bf16 conv-GEMM, all launches of one solve)",
+        "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                "ms_per_step": r["ms_e2e"] / args.steps,
+                "api": "CFMDecoder.solve_host -> st_solve_host (C ABI): pinned host buffers, H2D + solve + D2H + stream sync inside the call, per rank"},
+        "root_scatter_gather": r.get("sg"),
+        "gpu_launches": r["launches"], "host_enqueue_ms_per_step": round(r["host_ms"], 2),
+        "step_ms": {"value": r["per_dev"][:32], "e2e": r["per_e2e"][:32]}, "remeasured": r["remeasured"],
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 split-bf16 conv-GEMM, all launches of one solve)",
                      "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
                      "traffic_note": "dram__bytes_read+write per launch, mean over the ncu --set full capture in profiles/gemm_traffic.json",
                      "achieved_per_launch_gflop": gm["flops"] / max(gm["launches"], 1) / 1e9,
@@ -467,10 +592,13 @@ def main():
         "breakdown_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
         "breakdown_tflops": {k: round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1) for k, v in prof.items() if v["flops"] > 0},
         "attention": {"tflops": prof["attention"]["flops"] / max(prof["attention"]["ms"], 1e-9) / 1e9},
+        "ln": {"gbs": prof["ln"]["bytes"] / max(prof["ln"]["ms"], 1e-9) / 1e6, "hbm_peak_gbs": peaks.get("hbm_gbs")},
         "work": {"hoisted_tflop_per_step": hoisted / 1e12, "faithful_tflop_per_step": faithful / 1e12,
                  "whole_solve_tflops_hoisted": hoisted / 1e12 / sec_step / max(world, 1) * 1.0},
-        "cpu_baseline": cpu_baseline, "parity": parity,
+        "cpu_baseline": r.get("cpu_baseline"), "parity": r.get("parity"),
     }
+    if r4 is not None:
+        line["cfg4"] = block(r4, min(args.steps, 3))
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -70,7 +70,24 @@ class NativeModule(nn.Module):
             _lib.check(lib, h, lib.st_set_engine(h, self._engine), "st_set_engine")
         return lib, self._handle
 
-    def _sync_weights(self, lib, h, stream: int) -> None:
+    def _refuse_training_graph(self, what: str) -> None:
+        """The CUDA path is inference-only (no dropout, no autograd graph): in ``train()`` mode with grad enabled the
+        reference would return a differentiable, dropout-perturbed output; returning the detached eval output instead
+        would silently train nothing, so raise (``compute_loss`` does the same)."""
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(f"{what} in train() mode with autograd enabled needs dropout + backward kernels, "
+                                      "which the inference-only B200 path does not build; call .eval() / torch.no_grad(), "
+                                      "or train with the reference module and load the checkpoint here")
+
+    def invalidate_weights(self) -> None:
+        """Force a re-pack of every parameter on the next call.  Needed after in-place updates made THROUGH ``p.data``
+        (``p.data.copy_()``, EMA loops, legacy loaders): those do not bump ``p._version``, which is what the automatic
+        freshness check keys on together with the storage pointer."""
+        self._synced.clear()
+
+    def _sync_weights(self, lib, h, stream: int, force: bool = False) -> None:
+        if force:
+            self._synced.clear()
         dirty = False
         for name in self._shapes:
             p = self._param(name)
@@ -100,6 +117,27 @@ class NativeModule(nn.Module):
         self._sync_weights(lib, h, stream)
         self._ensure_workspace(lib, h, B, T, cfg, ref.device)
         return lib, h, stream
+
+    # -- copying / pickling: the library state (ctypes handle, workspace, sync tags) is per-process and per-device;
+    #    copies and unpickled modules re-create theirs lazily on first use ---------------------------------------
+    _NATIVE_STATE = ("_handle", "_handle_device", "_synced", "_workspace")
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_handle"], state["_handle_device"], state["_synced"], state["_workspace"] = None, None, {}, None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in self._NATIVE_STATE:
+                continue
+            setattr(new, k, copy.deepcopy(v, memo))
+        new._handle, new._handle_device, new._synced, new._workspace = None, None, {}, None
+        return new
 
     def release(self) -> None:
         if self._handle is not None:

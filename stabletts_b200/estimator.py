@@ -106,8 +106,12 @@ class Decoder(NativeModule):
 
 
     # -- the reference's forward ------------------------------------------------------------------
-    @torch.no_grad()
     def forward(self, t, x, mask, mu, c):
+        self._refuse_training_graph("Decoder.forward")      # checked BEFORE autograd is switched off below
+        with torch.no_grad():
+            return self._forward_impl(t, x, mask, mu, c)
+
+    def _forward_impl(self, t, x, mask, mu, c):
         """models/estimator.py:103-137.  t: 0-dim or (B,); x, mu: (B, n_mel, T); mask: (B, 1, T)
         float {0,1}; c: (B, gin).  Returns (B, n_mel, T), exactly 0 at masked frames."""
         B, M, T = x.shape

@@ -113,6 +113,52 @@ class CFMDecoder(nn.Module):
         return z.to(mu.dtype)                                                        # trajectory[-1], :55
 
     @torch.inference_mode()
+    def solve_host(self, mu, mask, n_timesteps, temperature=1.0, c=None, solver="euler", cfg_kwargs=None, *, z=None, out=None):
+        """``forward`` for HOST tensors (the serving form: requests arrive in host memory): one ``st_solve_host`` call
+        copies ``(z, mu, mask, c)`` host->device on the current stream of the module's device, runs the device-resident
+        solve, copies the mel back and synchronises that stream.  Page-locked inputs (``tensor.pin_memory()``) are copied
+        from directly, pageable ones are staged through a pinned buffer inside the library.  Fixed-grid solvers only.
+        ``out``: optional (pinned) CPU tensor to receive the mel; by default a new pinned tensor is returned."""
+        est = self.estimator
+        dev = next(est.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("stabletts_b200 runs on CUDA (B200) only: move the module with .to('cuda') (no CPU fallback)")
+        if any(t is not None and t.device.type != "cpu" for t in (mu, mask, c, z)):
+            raise RuntimeError("solve_host takes host tensors; use forward() for device tensors")
+        method = _method_id(solver)
+        if method == ST_ADAPTIVE:
+            raise ValueError("solve_host runs the fixed-grid solvers (euler, midpoint, rk4, dopri5_fixed)")
+        B, M, T = mu.shape
+        if c is None:
+            raise ValueError("c (speaker embedding, (B, gin_channels)) is required")
+        if z is None:
+            z = torch.randn_like(mu) * temperature                                   # :45
+        if out is None:
+            out = torch.empty((B, M, T), dtype=torch.float32).pin_memory() if B * T > 0 else torch.empty((B, M, T))
+        if tuple(out.shape) != (B, M, T) or out.dtype != torch.float32 or not out.is_contiguous() or out.device.type != "cpu":
+            raise ValueError("out must be a contiguous fp32 CPU tensor of shape (B, n_mel, T)")
+        out.copy_(z.to(torch.float32).reshape(B, M, T))
+        if B == 0 or T == 0:
+            return out
+        f32 = lambda t, shape: t.detach().to(torch.float32).reshape(shape).contiguous()
+        mu_, mask_, c_ = f32(mu, (B, M, T)), f32(mask, (B, T)), f32(c, (B, est.gin_channels))
+        t_span = torch.linspace(0, 1, n_timesteps + 1, dtype=torch.float32)         # :46
+        t_host = (C.c_float * (n_timesteps + 1))(*t_span.tolist())
+        fc = fs = None
+        strength = 1.0
+        if cfg_kwargs is not None:
+            fs = f32(cfg_kwargs["fake_speaker"].cpu(), (est.gin_channels,))
+            fc = f32(cfg_kwargs["fake_content"].cpu(), (est.cond_channels,))
+            strength = float(cfg_kwargs["cfg_strength"])
+        with torch.cuda.device(dev):
+            lib, h, stream = est._prepare(torch.empty(0, device=dev), B, T, 0 if fc is None else 1)
+            rc = lib.st_solve_host(h, out.data_ptr(), mu_.data_ptr(), mask_.data_ptr(), c_.data_ptr(),
+                                   None if fc is None else fc.data_ptr(), None if fs is None else fs.data_ptr(),
+                                   strength, t_host, n_timesteps, method, B, T, stream)
+        _lib.check(lib, h, rc, "st_solve_host")
+        return out
+
+    @torch.inference_mode()
     def cfg_wrapper(self, t, x, mask, mu, c, cfg_kwargs):
         """models/flow_matching.py:58-67 (kept for API parity; ``forward`` fuses the two branches into
         one doubled batch inside the library instead of calling this)."""

@@ -59,12 +59,17 @@ def length_buckets(lengths: Sequence[int], n_buckets: int) -> List[List[int]]:
 
 
 def bucketed_solve(solve: Callable[..., torch.Tensor], mu, mask, c, z, lengths: Sequence[int], n_buckets: int = 4,
-                   min_pad: int = 3) -> torch.Tensor:
+                   min_pad: int = 4) -> torch.Tensor:
     """Run ``solve`` per length bucket with each bucket cropped to (its max length + ``min_pad``) frames
     (capped at T), and scatter the results back into a (B, M, T) tensor.  Padded frames stay zero
-    (the estimator's output is exactly 0 there).  ``min_pad`` >= 3 keeps the reference's padded-edge
-    behaviour: an utterance followed by >= 3 pad frames is insensitive to further padding
-    (SURVEY.md fact 4)."""
+    (the estimator's output is exactly 0 there).
+
+    ``min_pad``: how many pad frames an utterance needs behind it to be insensitive to further padding.  Without
+    CFG 3 is exact (cond_proj's three k=3 convs see zeros, the unmasked in_proj / long-skip convs
+    reach one frame further).  With CFG the unconditional branch broadcasts a NON-ZERO ``fake_content`` over the pad
+    frames too, so the last valid frame sees cond_proj at frame L, which depends on ``mu[L+3]`` — a crop to L+3
+    frames replaces that by the conv's zero padding (3e-5 max-rel on valid frames, measured with the oracle); 4 pad
+    frames are exact for both.  The default is therefore 4."""
     B, M, T = mu.shape
     out = torch.zeros_like(z)
     for idx in length_buckets(lengths, n_buckets):

@@ -84,8 +84,12 @@ class TextEncoder(NativeModule):
                 else:
                     p.uniform_(-1.0 / math.sqrt(fan_in), 1.0 / math.sqrt(fan_in))
 
-    @torch.no_grad()
     def forward(self, x: torch.Tensor, c: torch.Tensor, x_lengths: torch.Tensor):
+        self._refuse_training_graph("TextEncoder.forward")      # checked BEFORE autograd is switched off below
+        with torch.no_grad():
+            return self._forward_impl(x, c, x_lengths)
+
+    def _forward_impl(self, x: torch.Tensor, c: torch.Tensor, x_lengths: torch.Tensor):
         """x: (B, T) int64 token ids; c: (B, gin); x_lengths: (B,).  Returns x (B, hidden, T), mu_x (B, out, T),
         x_mask (B, 1, T) — models/text_encoder.py:34-44."""
         if x.device.type != "cuda":
@@ -94,10 +98,16 @@ class TextEncoder(NativeModule):
         ids = x.detach().to(torch.int64).contiguous()
         lens = x_lengths.detach().to(device=x.device, dtype=torch.int64).contiguous()
         c_ = self._f32c("c", c, (B, self.gin_channels))
-        lib, h, stream = self._prepare(c_, B, T, 0)
         xo = torch.empty(B, self.hidden_channels, T, device=x.device, dtype=torch.float32)
         mu = torch.empty(B, self.out_channels, T, device=x.device, dtype=torch.float32)
         mask = torch.empty(B, 1, T, device=x.device, dtype=torch.float32)
+        if B == 0 or T == 0:                    # empty batch / zero tokens: empty tensors, like Decoder / CFMDecoder
+            return xo, mu, mask
+        # nn.Embedding raises on ids outside [0, n_vocab) (models/text_encoder.py:22,35); a silently clamped id would
+        # turn a tokenizer/vocabulary mismatch into plausible-looking output, so validate (one host read per call)
+        if bool(((ids < 0) | (ids >= self.n_vocab)).any()):
+            raise IndexError(f"token id out of range [0, {self.n_vocab}) in TextEncoder input")
+        lib, h, stream = self._prepare(c_, B, T, 0)
         rc = lib.st_text_encoder_forward(h, ids.data_ptr(), c_.data_ptr(), lens.data_ptr(), xo.data_ptr(), mu.data_ptr(),
                                          mask.data_ptr(), B, T, stream)
         _lib.check(lib, h, rc, "st_text_encoder_forward")

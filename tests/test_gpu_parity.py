@@ -274,3 +274,115 @@ def test_empty_and_zero_length_inputs(dev):
     assert torch.isfinite(out).all()
     assert float(out[1].abs().max()) == 0.0
     assert max(rel_errs(out, ref)) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2..4] at (or near) their full per-utterance sizes — VERDICT r1 "configs without a parity record"
+# ---------------------------------------------------------------------------------------------------------------------
+def _oracle_solve_rows(st, inp, rows, steps, method, kw):
+    """Per-utterance oracle solves (utterances are independent on this path)."""
+    outs = []
+    for i in rows:
+        sl = slice(i, i + 1)
+        outs.append(R.cfm_forward(st, inp["mu"][sl], inp["mask"][sl], steps, inp["x"][sl], inp["c"][sl], method, kw))
+    return torch.cat(outs, dim=0)
+
+
+def test_cfg2_25_step_dormand_prince_T500(dev):
+    """BASELINE cfg2's solver at its full depth: 25 fixed Dormand-Prince steps = 150 estimator evaluations at T = 500
+    (B = 4, one ragged row) against the oracle — error accumulation over 150 evaluations is where a 1e-5-per-call path
+    could drift; the bar stays 1e-3."""
+    st = weights.make_state(cases.WEIGHT_SEED, 80)
+    m = model_for(80, "tcgen05", dev)
+    inp = weights.make_inputs(201, [500, 500, 387, 500], 500)
+    with torch.inference_mode():
+        ref = R.cfm_forward(st, inp["mu"], inp["mask"], 25, inp["x"], inp["c"], "dopri5_fixed", None)
+    out = m(inp["mu"].to(dev), inp["mask"].to(dev), 25, 1.0, inp["c"].to(dev), "dopri5_fixed", None, z=inp["x"].to(dev))
+    e = rel_errs(out, ref)
+    assert max(e) < 1e-3, e
+    assert torch.isfinite(out).all()
+
+
+def test_cfg3_bucketed_solve_vs_per_utterance_oracle(dev):
+    """BASELINE cfg3's plumbing: a seeded U{200..2000} batch solved through shard.bucketed_solve (sorted, cut into cost
+    buckets, each cropped to its own maximum + 4 pad frames) against PER-UTTERANCE oracle solves at each utterance's own
+    padded length — with CFG (the case ADVICE r1 flagged: the unconditional branch makes pad >= 4 necessary) and without."""
+    from stabletts_b200 import shard
+    st = weights.make_state(cases.WEIGHT_SEED, 80)
+    m = model_for(80, "tcgen05", dev)
+    g = torch.Generator().manual_seed(303)
+    lens = sorted(int(v) for v in torch.randint(200, 2001, (10,), generator=g))
+    T = max(lens)
+    inp = weights.make_inputs(304, lens, T)
+    fs, fc = weights.make_cfg_params(cases.CFG_SEED)
+    for kw_cpu in (None, dict(fake_speaker=fs, fake_content=fc, cfg_strength=3.0)):
+        kw = None if kw_cpu is None else dict(fake_speaker=fs.to(dev), fake_content=fc.to(dev), cfg_strength=3.0)
+        solve_one = lambda mu, mask, c, z: m(mu, mask, 3, 1.0, c, "euler", kw, z=z)
+        out = shard.bucketed_solve(solve_one, inp["mu"].to(dev), inp["mask"].to(dev), inp["c"].to(dev), inp["x"].to(dev),
+                                   lens, n_buckets=3).cpu()
+        assert float((out * (1 - inp["mask"])).abs().max()) == 0.0
+        for i in (0, 4, 9):                                     # shortest, middle, longest: alone, padded to the batch T
+            sl = slice(i, i + 1)
+            with torch.inference_mode():
+                ref = R.cfm_forward(st, inp["mu"][sl], inp["mask"][sl], 3, inp["x"][sl], inp["c"][sl], "euler", kw_cpu)
+            L = lens[i]
+            e = rel_errs(out[sl, :, :L], ref[:, :, :L])
+            assert max(e) < 1e-3, (kw_cpu is not None, i, L, e)
+
+
+def test_cfg4_doubled_batch_256_spot_check(dev):
+    """BASELINE cfg4's per-GPU shape: B = 128 at T = 1000 with CFG = a doubled batch of 256 rows inside the library
+    (row b and row 128+b share a sample).  Two Euler steps on the device, utterances {0, 63, 127} re-solved by the
+    oracle: a tile-index or batch-offset error in the later rows of the big batch would show here."""
+    st = weights.make_state(cases.WEIGHT_SEED, 80)
+    m = model_for(80, "tcgen05", dev)
+    B, T = 128, 1000
+    lens = [T] * B
+    lens[63], lens[127] = 811, 977
+    inp = weights.make_inputs(405, lens, T)
+    fs, fc = weights.make_cfg_params(cases.CFG_SEED)
+    kw = dict(fake_speaker=fs.to(dev), fake_content=fc.to(dev), cfg_strength=3.0)
+    out = m(inp["mu"].to(dev), inp["mask"].to(dev), 2, 1.0, inp["c"].to(dev), "euler", kw, z=inp["x"].to(dev)).cpu()
+    assert torch.isfinite(out).all()
+    with torch.inference_mode():
+        ref = _oracle_solve_rows(st, inp, (0, 63, 127), 2, "euler", dict(fake_speaker=fs, fake_content=fc, cfg_strength=3.0))
+    e = rel_errs(out[[0, 63, 127]], ref)
+    assert max(e) < 1e-3, e
+    del out
+    torch.cuda.empty_cache()
+
+
+def test_two_devices_in_one_process():
+    """Per-device kernel attributes (cudaFuncAttributeMaxDynamicSharedMemorySize is per device): a second module on
+    cuda:1 in the same process must launch the >48 KB-smem kernels too, and calling it must not change the caller's
+    current device.  Needs >= 2 GPUs (skipped on a 1-GPU box; run with `gpurun --gpus 2`)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import __graft_entry__ as g
+    g.build()
+    from stabletts_b200 import CFMDecoder
+    st = weights.make_state(cases.WEIGHT_SEED, 80)
+    inp = weights.make_inputs(11, [300, 251], 300)
+    outs = []
+    for idx in (0, 1):
+        d = torch.device("cuda", idx)
+        m = CFMDecoder(80, 80, 256, 80, 1024, 4, 6, 3, 0.1, 256).eval()
+        m.estimator.load_state_dict(st, strict=True)
+        m = m.to(d)
+        torch.cuda.set_device(0)
+        outs.append(m.estimator(inp["t"].to(d), inp["x"].to(d), inp["mask"].to(d), inp["mu"].to(d), inp["c"].to(d)).cpu())
+        assert torch.cuda.current_device() == 0          # the library restored the caller's device
+    with torch.inference_mode():
+        ref = R.estimator_forward(st, inp["t"], inp["x"], inp["mask"], inp["mu"], inp["c"])
+    assert max(rel_errs(outs[0], ref)) < 1e-3 and max(rel_errs(outs[1], ref)) < 1e-3
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_text_encoder_rejects_out_of_range_ids_and_empty_inputs(dev):
+    from stabletts_b200.text_encoder import TextEncoder
+    enc = TextEncoder(50, 80, 256, 1024, 4, 3, 3, 0.1, 256).eval().to(dev)
+    c = torch.zeros(1, 256, device=dev)
+    with pytest.raises(IndexError):
+        enc(torch.tensor([[1, 2, 50]], device=dev), c, torch.tensor([3], device=dev))
+    x, mu, mask = enc(torch.zeros(0, 5, dtype=torch.long, device=dev), torch.zeros(0, 256, device=dev), torch.zeros(0, dtype=torch.long, device=dev))
+    assert x.shape == (0, 256, 5) and mu.shape == (0, 80, 5) and mask.shape == (0, 1, 5)

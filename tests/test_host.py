@@ -157,3 +157,27 @@ def test_pure_c_consumer_on_gpu(built):
         pytest.skip("no CUDA device")
     r = subprocess.run([_build_c_smoke()], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_modules_can_be_deep_copied_and_pickled_and_refuse_training_graphs():
+    """the ctypes handle / workspace / sync tags are per-process library state; copies and pickles drop them
+    and re-create lazily.  In train() mode with autograd on, forward raises instead of returning a detached eval output."""
+    import copy
+    import pickle
+    from stabletts_b200 import CFMDecoder
+    m = CFMDecoder(80, 80, 256, 80, 1024, 4, 2, 3, 0.1, 256)
+    m.estimator._synced["x"] = (1, 2)                 # pretend the module has been used
+    m2 = copy.deepcopy(m)
+    assert m2.estimator._handle is None and m2.estimator._synced == {} and m2.estimator._workspace is None
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    assert m2.estimator.final_proj.weight.data_ptr() != m.estimator.final_proj.weight.data_ptr()
+    m3 = pickle.loads(pickle.dumps(m))
+    assert m3.estimator._handle is None and list(m3.state_dict()) == list(m.state_dict())
+    m.estimator.invalidate_weights()
+    assert m.estimator._synced == {}
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m.estimator(torch.tensor(0.1), torch.zeros(1, 80, 4), torch.ones(1, 1, 4), torch.zeros(1, 80, 4), torch.zeros(1, 256))
+    m.eval()
+    with pytest.raises(RuntimeError, match="CUDA"):       # eval: gets as far as the no-CPU-fallback check
+        m.estimator(torch.tensor(0.1), torch.zeros(1, 80, 4), torch.ones(1, 1, 4), torch.zeros(1, 80, 4), torch.zeros(1, 256))

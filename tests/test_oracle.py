@@ -135,3 +135,32 @@ def test_fixed_grid_solvers_have_their_published_order():
         g = lambda t, y, k=k: t ** k + 0 * y
         out = R.odeint_fixed(g, torch.zeros(1, dtype=torch.float64), torch.tensor([0.0, 1.0], dtype=torch.float64), "rk4")
         assert abs(float(out[0]) - 1.0 / (k + 1)) < 1e-12
+
+
+def test_cfg_needs_four_pad_frames_for_crop_invariance():
+    """ADVICE r1 / shard.bucketed_solve's default min_pad: without CFG an utterance followed by >= 3 pad frames is
+    insensitive to further padding; WITH CFG the unconditional branch broadcasts a non-zero fake_content over the pad
+    frames, the last valid frame sees cond_proj at frame L which reaches mu[L+3], so a crop needs >= 4 pad frames."""
+    from oracle import weights as W
+    st = W.make_state(0, 80)
+    L = 20
+    inp = W.make_inputs(5, [L], L + 12)
+    x = inp["x"].clone(); x[:, :, L:] = 0
+    fs, fc = W.make_cfg_params(7)
+    t = torch.tensor(0.4)
+
+    def run(pad, cfg):
+        Tp = L + pad
+        a = (x[:, :, :Tp], inp["mask"][:, :, :Tp], inp["mu"][:, :, :Tp], inp["c"])
+        with torch.inference_mode():
+            o = R.cfg_estimator(st, t, *a, fs, fc, 3.0) if cfg else R.estimator_forward(st, t, *a)
+        return o[:, :, :L]
+
+    for cfg in (False, True):
+        full = run(12, cfg)
+        err = {p: float((run(p, cfg) - full).abs().max() / full.abs().max()) for p in (2, 3, 4, 6)}
+        assert err[4] < 5e-6 and err[6] < 5e-6, (cfg, err)
+        if cfg:
+            assert err[3] > 5e-6, err                 # three pad frames are NOT enough under CFG
+        else:
+            assert err[3] < 5e-6 and err[2] > 5e-6, err

@@ -35,8 +35,10 @@ def test_drop_in_inventory():
         from models.text_encoder import TextEncoder as Ref
         assert list(Ref(401, 80, 256, 1024, 4, 3, 3, 0.1, 256).state_dict().keys()) == list(m.state_dict().keys())
     ids, c, lens = T.make_inputs(1, [4], 4)
-    with pytest.raises(RuntimeError, match="CUDA"):
+    with pytest.raises(NotImplementedError):                   # train() mode + autograd: no silent detached output
         m(ids, c, lens)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.eval()(ids, c, lens)
 
 
 @pytest.mark.gpu
