@@ -332,7 +332,7 @@ def run_config(args, name, model, dev, rank, world, steps, warmup, flush, *, ful
         if not bucketed:
             return model.solve_host(pinned["mu"], pinned["mask"], cfgd["n_steps"], 1.0, pinned["c"], cfgd["method"], kw_host,
                                     z=pinned["z"], out=out_pinned)
-        out_pinned.zero_()
+        out_pinned.copy_(pinned["z"])                                # padded frames keep the initial noise (reference semantics)
         for idx in shard.length_buckets(lens_local, 4):              # host tensors are cropped per bucket on the host
             Tb = min(T, max(lens_local[i] for i in idx) + 4)
             sel = torch.as_tensor(idx)

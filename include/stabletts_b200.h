@@ -149,6 +149,21 @@ int st_create_text_encoder(const st_dims* dims, int n_vocab, int device, st_hand
 int st_text_encoder_forward(st_handle* h, const int64_t* ids, const float* c, const int64_t* x_lengths, float* x_out,
                             float* mu_out, float* mask_out, int B, int T, void* stream);
 
+/* ---- the vocoder hand-off, api.py:76 `self.vocoder_model(mel_output)` --------------------------
+ * Replaces Vocos.__init__ / forward (vocoders/vocos/models/model.py:11-20: VocosBackbone backbone.py:21-56, ConvNeXtBlock
+ * module.py:15-46, ISTFTHead / ISTFT with "same" padding head.py:21-117).  dims = VocosConfig + MelConfig
+ * (vocoders/vocos/config.py): input_channels, dim, intermediate_dim, num_layers, n_fft, hop_length.
+ * Weights are loaded with st_load_weight under the reference's state_dict keys ("backbone.embed.weight",
+ * "backbone.norm.*", "backbone.convnext.{i}.{gamma,dwconv.*,norm.*,pwconv1.*,pwconv2.*}", "backbone.final_layer_norm.*",
+ * "head.out.*", "head.istft.window"), then st_finalize_weights.  The handle owns its workspace. */
+typedef struct st_vocos_dims {
+    int32_t n_mel, dim, intermediate, n_layers, n_fft, hop;
+} st_vocos_dims;
+int st_create_vocos(const st_vocos_dims* dims, int device, st_handle** out);
+/* mel (B, n_mel, T) device fp32 -> audio (B, T * hop) device fp32; enqueued on `stream`, no host synchronisation
+ * (except when the internal workspace has to grow). */
+int st_vocos_forward(st_handle* h, const float* mel, float* audio, int B, int T, void* stream);
+
 /* Number of kernels this library launched since the handle was created (bench.py gpu_launches). */
 int64_t st_launch_count(const st_handle* h);
 

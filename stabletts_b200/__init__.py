@@ -9,7 +9,8 @@ modules without the built library or without a CUDA device raises.
 from .estimator import Decoder                      # noqa: F401
 from .flow_matching import CFMDecoder               # noqa: F401
 from .text_encoder import TextEncoder               # noqa: F401
+from .vocos import Vocos                            # noqa: F401
 from .align import expand_by_durations              # noqa: F401
 from ._lib import library_path, load_library        # noqa: F401
 
-__all__ = ["Decoder", "CFMDecoder", "TextEncoder", "expand_by_durations", "library_path", "load_library"]
+__all__ = ["Decoder", "CFMDecoder", "TextEncoder", "Vocos", "expand_by_durations", "library_path", "load_library"]

@@ -17,12 +17,16 @@ ST_PROF_NCAT = len(ST_PROF_NAMES)
 EXPORTS = [
     "st_create", "st_destroy", "st_last_error", "st_version", "st_load_weight", "st_finalize_weights",
     "st_set_engine", "st_workspace_bytes", "st_attach_workspace", "st_estimator_forward", "st_cfm_loss", "st_solve",
-    "st_solve_host", "st_solve_adaptive", "st_solve_adaptive_ex", "st_align_lengths", "st_align_expand", "st_create_text_encoder", "st_text_encoder_forward", "st_launch_count", "st_profile_begin", "st_profile_end", "st_test_gemm", "st_test_conv", "st_test_attention", "st_test_attention_trace", "st_bench_conv",
+    "st_solve_host", "st_solve_adaptive", "st_solve_adaptive_ex", "st_align_lengths", "st_align_expand", "st_create_text_encoder", "st_text_encoder_forward", "st_create_vocos", "st_vocos_forward", "st_launch_count", "st_profile_begin", "st_profile_end", "st_test_gemm", "st_test_conv", "st_test_attention", "st_test_attention_trace", "st_bench_conv",
 ]
 
 
 class StDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_mel", "hidden", "filter", "n_heads", "n_layers", "kernel", "gin")]
+
+
+class StVocosDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_mel", "dim", "intermediate", "n_layers", "n_fft", "hop")]
 
 
 def library_path() -> str:
@@ -63,6 +67,8 @@ def load_library() -> C.CDLL:
     lib.st_align_expand.argtypes = [f32p, f32p, f32p, vp, i32, i32, i32, i32, f32p, f32p, f32p, vp]
     lib.st_create_text_encoder.argtypes = [C.POINTER(StDims), i32, i32, C.POINTER(vp)]
     lib.st_text_encoder_forward.argtypes = [vp, vp, f32p, vp, f32p, f32p, f32p, i32, i32, vp]
+    lib.st_create_vocos.argtypes = [C.POINTER(StVocosDims), i32, C.POINTER(vp)]
+    lib.st_vocos_forward.argtypes = [vp, f32p, f32p, i32, i32, vp]
     lib.st_launch_count.argtypes = [vp]
     lib.st_launch_count.restype = i64
     lib.st_profile_begin.argtypes = [vp]

@@ -9,9 +9,7 @@
 //                 -> final_proj.  With CFG the cond and uncond branches are ONE doubled batch.
 //   ODE driver  : explicit Runge–Kutta on the caller's grid, all device-resident: stage times are
 //                 baked into kernel arguments, nothing is copied or synchronised between steps.
-#include "common.cuh"
-#include <cstdio>
-#include <cstring>
+#include "handle.cuh"
 #include <cmath>
 #include <mutex>
 
@@ -21,26 +19,6 @@ namespace {
 
 std::string g_create_error;
 std::mutex g_mutex;
-
-struct GemmW {           // one packed conv/linear weight
-    float* f32 = nullptr; bf16* hi = nullptr; bf16* lo = nullptr; float* bias = nullptr;
-    int taps = 1, N = 0, K = 0;
-};
-
-struct Act {             // an activation buffer: fp32 and/or split-bf16 planes, (batch, T, C)
-    float* f32 = nullptr; bf16* hi = nullptr; bf16* lo = nullptr; int C = 0;
-};
-
-struct Bump {
-    char* base; size_t off = 0, cap;
-    Bump(void* p, size_t c) : base((char*)p), cap(c) {}
-    template <class T> T* take(size_t n) {
-        off = (off + 255) & ~size_t(255);
-        T* r = base ? (T*)(base + off) : nullptr;
-        off += n * sizeof(T);
-        return r;
-    }
-};
 
 constexpr int MAX_EVAL_TABLE = 1024;
 
@@ -59,70 +37,12 @@ struct Workspace {
 
 }  // namespace
 
-struct st_handle {
-    st_dims d;
-    int kind = 0;                      // 0 = CFM estimator (Decoder), 1 = TextEncoder
-    int n_vocab = 0; float* emb = nullptr;
-    int device = 0, engine = ST_ENGINE_TCGEN05, num_sms = 148;
-    std::string err;
-    std::map<std::string, std::pair<float*, int64_t>> raw;   // name -> (device copy, numel)
-    bool finalized = false;
-    GemmW cond0, cond2, cond4, inmu, inx, fin;
-    std::vector<GemmW> qkv, wo, c1, c2, lsc;
-    std::vector<float*> film_w, film_b, ada_w, ada_b;
-    float *tm0_w = nullptr, *tm0_b = nullptr, *tm2_w = nullptr, *tm2_b = nullptr;
-    std::vector<void*> owned;
-    void* ws_ptr = nullptr; size_t ws_bytes = 0; bool ws_owned = false;
-    int64_t launches = 0;
-    // CUDA-graph cache for launch-bound (small) solves: key -> instantiated graph + its launch count
-    struct GraphEntry { std::string key; cudaGraphExec_t exec; int64_t launches; };
-    std::vector<GraphEntry> graphs;
-    std::vector<std::string> graph_seen;   // keys enqueued directly once (kernels loaded, attributes set) before capture
-    double* pinned = nullptr;          // 16 B of pinned host memory: norm read-back of the adaptive controller
-    char* pin_buf = nullptr; size_t pin_bytes = 0;   // pinned staging of st_solve_host for callers with pageable buffers
-    cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the caller's may be the legacy stream)
-    int graph_mode = -1;               // -1: read STABLETTS_B200_GRAPH on first use; 0 off; 1 always; 2 auto (small problems)
-    void drop_graphs() { for (auto& g : graphs) cudaGraphExecDestroy(g.exec); graphs.clear(); }
-    // optional per-launch CUDA-event profiling (bench.py roofline): category, flops, bytes, event pair
-    bool prof_on = false;
-    struct ProfRec { int cat; double flops, bytes; cudaEvent_t e0, e1; };
-    std::vector<ProfRec> prof;
-    std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
-    cudaEvent_t take_event() {
-        if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
-        return ev_pool[ev_used++];
-    }
-};
-
-namespace {
-
-int fail(st_handle* h, const std::string& msg) {
+int st::fail(st_handle* h, const std::string& msg) {
     if (h) h->err = msg; else g_create_error = msg;
     return 1;
 }
 
-#define ST_CUDA(call)                                                                         \
-    do {                                                                                      \
-        cudaError_t e__ = (call);                                                             \
-        if (e__ != cudaSuccess) {                                                             \
-            char buf__[512];                                                                  \
-            snprintf(buf__, sizeof buf__, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
-                     cudaGetErrorString(e__));                                                \
-            return fail(h, buf__);                                                            \
-        }                                                                                     \
-    } while (0)
-
-#define ST_LAUNCH(call) do { h->launches++; ST_CUDA(call); } while (0)
-
-// profiled launch: brackets `call` with events on the launching stream when profiling is enabled
-#define ST_LAUNCH_P(cat, flops_, bytes_, s_, call)                                             \
-    do {                                                                                      \
-        st_handle::ProfRec pr__{cat, (double)(flops_), (double)(bytes_), nullptr, nullptr};   \
-        if (h->prof_on) { pr__.e0 = h->take_event(); pr__.e1 = h->take_event(); cudaEventRecord(pr__.e0, s_); } \
-        h->launches++;                                                                        \
-        ST_CUDA(call);                                                                        \
-        if (h->prof_on) { cudaEventRecord(pr__.e1, s_); h->prof.push_back(pr__); }            \
-    } while (0)
+namespace {
 
 // ----- weight packing ---------------------------------------------------------------------------
 // in: (Nsrc, Csrc, k) reference Conv1d / Linear layout -> out[tap][n_off + n][c] for c in [c_off, c_off+Cc)
@@ -153,13 +73,17 @@ __global__ void time_embed_val_kernel(TArr t, int n_t, int H, float* __restrict_
     out[(long)r * H + half + j] = cosf(e);
 }
 
-template <class T> int dev_alloc(st_handle* h, T** p, size_t n) {
-    ST_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
-    h->owned.push_back(*p);
-    return 0;
+}  // namespace
+
+cudaError_t st::launch_pack_conv(const float* in, float* out, int Nsrc, int Csrc, int k, int Ntot, int n_off, int c_off, int Cc,
+                                 cudaStream_t s) {
+    const long total = (long)k * Nsrc * Cc;
+    if (total == 0) return cudaSuccess;
+    pack_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, Nsrc, Csrc, k, Ntot, n_off, c_off, Cc);
+    return cudaGetLastError();
 }
 
-int get_raw(st_handle* h, const std::string& name, int64_t expect, float** out) {
+int st::get_raw(st_handle* h, const std::string& name, int64_t expect, float** out) {
     auto it = h->raw.find(name);
     if (it == h->raw.end()) return fail(h, "missing weight: " + name);
     if (it->second.second != expect) {
@@ -173,8 +97,8 @@ int get_raw(st_handle* h, const std::string& name, int64_t expect, float** out) 
 }
 
 // Packs `parts` reference tensors (each (N_i, Csrc, k)) stacked along N, taking channels [c_off, c_off+Cc).
-int pack_gemm(st_handle* h, GemmW* w, const std::vector<std::string>& names, int N_each, int Csrc, int k, int c_off,
-              int Cc, bool with_bias, cudaStream_t s) {
+int st::pack_gemm(st_handle* h, GemmW* w, const std::vector<std::string>& names, int N_each, int Csrc, int k, int c_off,
+                  int Cc, bool with_bias, cudaStream_t s) {
     int parts = (int)names.size();
     w->taps = k; w->N = N_each * parts; w->K = Cc;
     size_t n = (size_t)k * w->N * Cc;
@@ -198,6 +122,8 @@ int pack_gemm(st_handle* h, GemmW* w, const std::vector<std::string>& names, int
     ST_CUDA(launch_split(w->f32, w->hi, w->lo, (long)n, s));
     return 0;
 }
+
+namespace {
 
 // ----- workspace ----------------------------------------------------------------------------------
 void layout_ws(const st_handle* h, Workspace& w, void* base, size_t cap, int B, int T, int cfg) {
@@ -262,9 +188,11 @@ int ensure_ws(st_handle* h, Workspace& w, int B, int T, int cfg) {
     return 0;
 }
 
+}  // namespace
+
 // ----- GEMM dispatch -------------------------------------------------------------------------------
-int run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const Act* a1, const Act& out, cudaStream_t s,
-             int prof_cat = ST_PROF_GEMM) {
+int st::run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const Act* a1, const Act& out, cudaStream_t s,
+                 int prof_cat) {
     const bool tc = h->engine == ST_ENGINE_TCGEN05;
     g.n_src = a1 ? 2 : 1;
     const Act* as[2] = {a0, a1};
@@ -294,6 +222,8 @@ int run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const Act
     if (h->prof_on) { cudaEventRecord(pr.e1, s); h->prof.push_back(pr); }
     return 0;
 }
+
+namespace {
 
 // ----- per-solve precompute -------------------------------------------------------------------------
 // cond features (models/estimator.py:118) for B real rows + (cfg) the broadcast fake_content row;
@@ -465,16 +395,6 @@ Tableau tableau_for(int method) {
     return t;
 }
 
-// Every entry point runs on the handle's device and RESTORES the caller's current device on return (a torch caller
-// whose current device is cuda:0 must not find it switched to cuda:1 because a module lives there).
-struct DevGuard {
-    int prev = -1, dev;
-    explicit DevGuard(int d) : dev(d) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != d) cudaSetDevice(d); }
-    ~DevGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
-    DevGuard(const DevGuard&) = delete; DevGuard& operator=(const DevGuard&) = delete;
-};
-#define ST_ENTER(h) DevGuard dev_guard__((h)->device)
-
 int check_common(st_handle* h, int B, int T) {
     if (!h) return 1;
     if (!h->finalized) return fail(h, "weights not finalized (call st_finalize_weights)");
@@ -540,6 +460,7 @@ int st_destroy(st_handle* h) {
     for (auto& kv : h->raw) cudaFree(kv.second.first);
     for (void* p : h->owned) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->kind == 2) vocos_free(h);
     if (h->ws_ptr && h->ws_owned) cudaFree(h->ws_ptr);
     if (h->pin_buf) cudaFreeHost(h->pin_buf);
     }
@@ -608,6 +529,11 @@ int st_finalize_weights(st_handle* h, void* stream) {
     h->drop_graphs();                  // cached graphs hold pointers into the old packed weights
     for (void* p : h->owned) cudaFree(p);
     h->owned.clear();
+    if (h->kind == 2) {                // Vocos vocoder (vocoders/vocos/models/*.py): packed in vocos_api.cu
+        if (vocos_finalize(h, s)) return 1;
+        h->finalized = true;
+        return 0;
+    }
     h->qkv.assign(L, GemmW()); h->wo.assign(L, GemmW()); h->c1.assign(L, GemmW()); h->c2.assign(L, GemmW());
     h->lsc.assign(L / 2, GemmW());
     h->film_w.assign(L, nullptr); h->film_b.assign(L, nullptr); h->ada_w.assign(L, nullptr); h->ada_b.assign(L, nullptr);

@@ -32,6 +32,7 @@ enum : int {
     EPI_GATE  = 1 << 4,   // v *= gate[min(bb, c_clamp), n]
     EPI_RESID = 1 << 5,   // v += resid[min(bb, resid_clamp), t, n]
     EPI_ROPE  = 1 << 6,   // partial RoPE on q/k column blocks (QKV projection only; TC engine)
+    EPI_GELU  = 1 << 7,   // v = 0.5 v (1 + erf(v / sqrt 2)): nn.GELU() exact form (Vocos ConvNeXt block, module.py:26)
 };
 
 struct GemmArgs {
@@ -181,6 +182,7 @@ inline cudaError_t ensure_dyn_smem(K kernel, int bytes, std::atomic<uint64_t>& d
 }
 
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 
 // two floats -> packed (hi0,hi1) and (lo0,lo1) bf16x2 words: one cvt.rn.bf16x2 per plane
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {

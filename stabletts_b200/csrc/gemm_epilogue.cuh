@@ -150,6 +150,9 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, int bb, int t0,
                 if (p.flags & EPI_SILU) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
+                } else if (p.flags & EPI_GELU) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) x[e] = gelu_f(x[e]);
                 }
                 if (!plain) {                  // bias / SiLU only (cond_proj) skips the neutral FiLM·mask·gate+resid chain
                     const float m = mrow[it];

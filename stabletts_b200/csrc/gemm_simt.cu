@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
             float v = acc[i][j];
             if (g.flags & EPI_BIAS) v += g.bias[n];
             if (g.flags & EPI_SILU) v = silu_f(v);
+            else if (g.flags & EPI_GELU) v = gelu_f(v);
             if (g.flags & EPI_FILM) v = film[n] * v + film[g.film_H + n];
             if (g.flags & EPI_MASK) v *= m;
             if (g.flags & EPI_GATE) v *= gate[n];

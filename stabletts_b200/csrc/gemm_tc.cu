@@ -304,7 +304,7 @@ static int tc2_mode() {
 
 cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s) {
     if (g.BB == 0 || g.T == 0) return cudaSuccess;
-    if ((g.flags & EPI_ROPE) && (g.flags & (EPI_SILU | EPI_FILM | EPI_MASK | EPI_GATE | EPI_RESID))) {
+    if ((g.flags & EPI_ROPE) && (g.flags & (EPI_SILU | EPI_GELU | EPI_FILM | EPI_MASK | EPI_GATE | EPI_RESID))) {
         std::lock_guard<std::mutex> lk(g_mu);
         g_err = "EPI_ROPE combines with EPI_BIAS only (the QKV epilogue variant)";
         return cudaErrorInvalidValue;

@@ -61,8 +61,9 @@ def length_buckets(lengths: Sequence[int], n_buckets: int) -> List[List[int]]:
 def bucketed_solve(solve: Callable[..., torch.Tensor], mu, mask, c, z, lengths: Sequence[int], n_buckets: int = 4,
                    min_pad: int = 4) -> torch.Tensor:
     """Run ``solve`` per length bucket with each bucket cropped to (its max length + ``min_pad``) frames
-    (capped at T), and scatter the results back into a (B, M, T) tensor.  Padded frames stay zero
-    (the estimator's output is exactly 0 there).
+    (capped at T), and scatter the results back into a (B, M, T) tensor.  Padded frames keep the initial noise ``z``
+    exactly as in the reference (``z`` is unmasked, models/flow_matching.py:45, and the vector field is exactly 0 at
+    masked frames, so the ODE state never moves there) — inside and beyond the crop alike.
 
     ``min_pad``: how many pad frames an utterance needs behind it to be insensitive to further padding.  Without
     CFG 3 is exact (cond_proj's three k=3 convs see zeros, the unmasked in_proj / long-skip convs
@@ -71,7 +72,7 @@ def bucketed_solve(solve: Callable[..., torch.Tensor], mu, mask, c, z, lengths: 
     frames replaces that by the conv's zero padding (3e-5 max-rel on valid frames, measured with the oracle); 4 pad
     frames are exact for both.  The default is therefore 4."""
     B, M, T = mu.shape
-    out = torch.zeros_like(z)
+    out = z.clone()
     for idx in length_buckets(lengths, n_buckets):
         Tb = min(T, max(int(lengths[i]) for i in idx) + min_pad)
         sel = torch.as_tensor(idx, device=mu.device)
