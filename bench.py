@@ -412,6 +412,7 @@ def run_config(args, name, model, dev, rank, world, steps, warmup, flush, *, ful
     ms_dev, out_dev, per_dev = timed_checked(step_device, steps, "value")
     launches = (model.estimator.launch_count() - l0) // (2 if any(r["region"] == "value" for r in remeasured) else 1)
     res = {"name": name, "cfgd": cfgd, "Bglob": Bglob, "T": T, "frames": frames_global, "ms_dev": ms_dev, "per_dev": per_dev,
+           "out_dev": out_dev if (full and not bucketed) else None,
            "launches": int(launches), "host_ms": host_ms, "n_warm": n_warm, "remeasured": remeasured, "inp": inp}
     if args.ncu_mode:
         return res
@@ -472,6 +473,44 @@ def run_config(args, name, model, dev, rank, world, steps, warmup, flush, *, ful
     return res
 
 
+def run_vocoder(args, dev, mel, flush, steps=5):
+    """the vocoder hand-off (api.py:76) on the mel the solve just produced — Vocos at the reference's
+    VocosConfig / MelConfig sizes (dim 768, 12 ConvNeXt blocks, n_fft 2048, hop 512, 44.1 kHz) with input width n_mel = 80,
+    seeded synthetic weights.  Reports vocoder frames/s and audio-seconds/s, and the parity of two utterances vs the oracle."""
+    from stabletts_b200 import Vocos
+    from oracle import vocoder_ref as V
+    st = V.make_state(input_channels=N_MEL)
+    d = dict(V.DIMS); d["input_channels"] = N_MEL
+    voc = Vocos(**d).eval()
+    voc.load_state_dict(st, strict=True)
+    voc = voc.to(dev)
+    voc.set_engine(args.engine)
+    B, _, T = mel.shape
+    for _ in range(3):
+        audio = voc(mel)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        flush.zero_()
+        audio = voc(mel)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[steps]) / steps
+    out = {"workload": f"Vocos (dim 768, 12 blocks, n_fft 2048, hop 512) on the solve's mel: B={B}, n_mel={N_MEL}, T={T}",
+           "ms_per_step": ms, "frames_per_s": B * T / (ms * 1e-3), "audio_seconds_per_s": B * T * 512 / 44100.0 / (ms * 1e-3),
+           "sample_rate": 44100, "gflop_per_frame": 0.088, "tflops": B * T * 88.0e6 / (ms * 1e-3) / 1e12,
+           "gpu_launches_per_step": None}
+    if not args.no_cpu_baseline:
+        rows = [0, B - 1]
+        with torch.inference_mode():
+            ref = V.vocos_forward(st, mel[rows].cpu())
+        dlt = audio[rows].cpu().double() - ref.double()
+        out["parity"] = {"max_rel": float(dlt.abs().max() / ref.abs().max()), "l2_rel": float(dlt.norm() / ref.double().norm()),
+                         "vs": f"oracle/vocoder_ref.py (pinned against the unmodified reference Vocos) on utterances {rows}"}
+    return out
+
+
 def work_flops(cfgd, lens):
     nfe = cfgd["n_steps"] * NFE_PER_STEP[cfgd["method"]] * (2 if cfgd["cfg"] is not None else 1)
     lens = lens.double()
@@ -491,6 +530,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=30.0, help="seconds of CPU work for the cpu_baseline / parity leg")
     ap.add_argument("--no-cfg4", action="store_true", help="at N=8 skip the additional BASELINE cfg4 block (128/GPU = 1024 global)")
+    ap.add_argument("--no-vocoder", action="store_true", help="skip the vocoder hand-off block (row f4)")
     ap.add_argument("--ncu-mode", action="store_true",
                     help="for `ncu` launch lists only: honours --warmup < 3, skips e2e / instrumented / CPU legs (numbers printed under a profiler are never bench values)")
     args = ap.parse_args()
@@ -526,6 +566,12 @@ def main():
             dist.destroy_process_group()
         return
     clocks = sampler.stop() if rank == 0 else None
+    vocoder = None
+    if rank == 0 and world == 1 and not args.no_vocoder and r.get("out_dev") is not None:
+        try:
+            vocoder = run_vocoder(args, dev, r["out_dev"], flush)
+        except Exception as e:                              # noqa: BLE001 — the headline must not die with the extra block
+            vocoder = {"error": repr(e)[:300]}
     # BASELINE cfg4 AS WRITTEN (batch 1024 over 8 GPUs = 128 per GPU) rides along in the N = 8 run of the default config
     r4 = None
     if world == 8 and args.config == "cfg1" and not args.no_cfg4:
@@ -599,6 +645,8 @@ def main():
     }
     if r4 is not None:
         line["cfg4"] = block(r4, min(args.steps, 3))
+    if vocoder is not None:
+        line["vocoder"] = vocoder
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
