@@ -18,7 +18,7 @@ namespace st {
 struct TcParams {
     int n_src, Cs0, Cs1, taps, N, a_bmod, BB, T;
     int m_tiles_per_b, n_tiles, total_tiles;
-    int flags, B, film_H, c_clamp, resid_clamp, rope_H, tap_outer;
+    int flags, B, film_H, c_clamp, resid_clamp, rope_H, tap_outer, dbg;
     long film_bstride, gate_bstride;
     const float *bias, *mask, *film, *gate, *resid, *rope_cs;
     float* out_f32; bf16* out_hi; bf16* out_lo;
@@ -33,6 +33,9 @@ inline void fill_tc_params(TcParams& p, const GemmArgs& g) {
     static int tap_outer = -1;
     if (tap_outer < 0) { const char* e = getenv("STABLETTS_B200_TAP_OUTER"); tap_outer = (e && e[0] == '1') ? 1 : 0; }
     p.tap_outer = tap_outer;
+    static int dbg = -1;            // TEMPORARY timing experiments (results are wrong when set): 1 = no global stores, 2 = no stores, no math
+    if (dbg < 0) { const char* e = getenv("STABLETTS_B200_EPI_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
 }
 
 // softmax scale folded into q: 1/sqrt(64) * log2(e) (attention runs in the exp2 domain)
@@ -134,6 +137,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, int bb, int t0,
             const int rl = it * 4 + rs;
             const int t = t0 + rl;
             const float4 sv = stg[rl * 8 + (c4 ^ (rl & 7))];
+            if (p.dbg == 2) { if (sv.x == 1.2345e30f) stg[0].x = 1.f; continue; }     // TEMPORARY: phase A only
             float x[4] = {sv.x + b4.x, sv.y + b4.y, sv.z + b4.z, sv.w + b4.w};
             if constexpr (ROPE) {
                 if (rope) {                    // warp-uniform branch
@@ -162,7 +166,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, int bb, int t0,
                     x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[it].w;
                 }
             }
-            if (t < p.T && col_ok) {
+            if (t < p.T && col_ok && (p.dbg == 0 || x[0] == 1.2345e30f)) {
                 const long o = obase + (long)t * p.N + n;
                 if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
                 if (p.out_hi) {
