@@ -263,22 +263,43 @@ int precompute_film(st_handle* h, Workspace& w, int n_t, cudaStream_t s) {
     return 0;
 }
 
-// One adaLN-Zero DiT block on the residual stream X[xb] (models/diffusion_transformer.py:98-117) after the
-// caller prepared `ln` for the first LayerNorm (plain, or FiLM·mask fused): LN1+modulate -> QKV (+RoPE)
+// The LayerNorm + adaLN modulate that FOLLOWS a GEMM whose tile owns whole 256-channel rows rides in that GEMM's epilogue
+// (gemm_epilogue.cuh, EM_LN): O -> LN2, conv_2 / in_proj -> the next block's [FiLM·mask +] LN1, long-skip conv -> LN1.
+// Small problems (fewer pair tiles than TPCs run on the 1-CTA 128 x 128 kernel) and the SIMT engine keep the separate kernel.
+bool ln_fusion_on(const st_handle* h, const Workspace& w) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("STABLETTS_B200_FUSE_LN"); env = (e && !strcmp(e, "0")) ? 0 : 1; }
+    if (!env || h->engine != ST_ENGINE_TCGEN05) return false;
+    GemmArgs g;
+    g.BB = w.BB; g.T = w.T; g.N = h->d.hidden; g.Ktot = h->d.hidden; g.Cs[0] = h->d.hidden; g.n_src = 1;
+    g.A_hi[0] = w.U.hi; g.W_hi = w.U.hi;           // non-null placeholders: only shapes matter here
+    return gemm_tc_ln_fusable(g, h->num_sms);
+}
+
+struct NextLn {                 // the LayerNorm that directly follows this block's conv_2 (nullptr: none / not fused)
+    const float* film2; long film2_bs; float* x2_out;   // the next block's FiLM (estimator blocks < L/2), else nullptr
+    const float* shift; const float* scale;
+};
+
+// One adaLN-Zero DiT block on the residual stream X[xb] (models/diffusion_transformer.py:98-117): LN1+modulate -> QKV (+RoPE)
 // -> masked attention -> O·gate + residual -> LN2+modulate·mask -> conv_1+SiLU·mask -> conv_2·mask·gate + residual.
+// `ln` describes LN1 for the separate kernel (plain, or FiLM·mask fused); with `ln1_done` the previous GEMM's epilogue has
+// already written U.  `fuse`: LN2 rides in O's epilogue, and `next` (if any) in conv_2's.
 int dit_block_core(st_handle* h, Workspace& w, int l, LnArgs ln, const float* ada_l, long ada_bs, int xb, const float* mask,
-                   cudaStream_t s) {
+                   cudaStream_t s, bool fuse = false, bool ln1_done = false, const NextLn* next = nullptr) {
     const st_dims& d = h->d;
     const int H = d.hidden;
     auto base = [&](int flags) {
         GemmArgs g;
         g.BB = w.BB; g.T = w.T; g.a_bmod = w.BB; g.B = w.B; g.mask = mask; g.flags = flags;
         g.c_clamp = w.B; g.resid_clamp = w.BB - 1; g.film_H = H; g.rope_cs = w.rope_cs;
+        g.ada_bstride = ada_bs; g.u_hi = w.U.hi; g.u_lo = w.U.lo;
         return g;
     };
     ln.shift = ada_l; ln.scale = ada_l + H;
     ln.u_f32 = w.U.f32; ln.u_hi = w.U.hi; ln.u_lo = w.U.lo;
-    ST_LAUNCH_P(ST_PROF_LN, 0, (double)w.BB * w.T * H * (4 + (ln.has_film ? 4 : 0) + 4), s, launch_film_ln_mod(ln, s));
+    if (!ln1_done)
+        ST_LAUNCH_P(ST_PROF_LN, 0, (double)w.BB * w.T * H * (4 + (ln.has_film ? 4 : 0) + 4), s, launch_film_ln_mod(ln, s));
     {   // q,k,v projections as one N=3H GEMM (models/diffusion_transformer.py:59-61)
         // tcgen05 engine: partial RoPE + softmax scale fused in the epilogue, split-bf16 output
         GemmArgs g = base(h->engine == ST_ENGINE_TCGEN05 ? (EPI_BIAS | EPI_ROPE) : EPI_BIAS);
@@ -297,13 +318,14 @@ int dit_block_core(st_handle* h, Workspace& w, int l, LnArgs ln, const float* ad
             ST_LAUNCH_P(ST_PROF_ATTN, 4.0 * w.BB * (double)w.T * w.T * H, (double)w.BB * w.T * H * 16, s, launch_attention_simt(a, s));
         }
     }
-    {   // x += gate_msa * conv_o(attn) * mask   (:65, :111)
+    {   // x += gate_msa * conv_o(attn) * mask   (:65, :111)  [+ LN2 + modulate, FFN input mask (:112, :26) in the epilogue]
         GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
         g.gate = ada_l + 2 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
+        if (fuse) { g.ln = 1; g.ln_mask_out = 1; g.ln_shift = ada_l + 3 * H; g.ln_scale = ada_l + 4 * H; }
         Act out = w.X[xb]; out.hi = nullptr; out.lo = nullptr;
         if (run_gemm(h, g, h->wo[l], &w.AO, nullptr, out, s, ST_PROF_GEMM_O)) return 1;
     }
-    {   // LN2 + modulate, FFN input mask (:112, :26)
+    if (!fuse) {   // LN2 + modulate, FFN input mask (:112, :26)
         LnArgs l2 = ln;
         l2.xin = w.X[xb].f32; l2.xout = nullptr; l2.has_film = 0; l2.mask_out = 1;
         l2.shift = ada_l + 3 * H; l2.scale = ada_l + 4 * H;
@@ -313,9 +335,13 @@ int dit_block_core(st_handle* h, Workspace& w, int l, LnArgs ln, const float* ad
         GemmArgs g = base(EPI_BIAS | EPI_SILU | EPI_MASK);
         if (run_gemm(h, g, h->c1[l], &w.U, nullptr, w.Hid, s, ST_PROF_GEMM_C1)) return 1;
     }
-    {   // x += gate_mlp * (conv_2(h) * mask)   (:29-30, :112)
+    {   // x += gate_mlp * (conv_2(h) * mask)   (:29-30, :112)  [+ the next block's (FiLM·mask,) LN1 + modulate in the epilogue]
         GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
         g.gate = ada_l + 5 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
+        if (fuse && next) {
+            g.ln = 1; g.ln_mask_out = 0; g.ln_shift = next->shift; g.ln_scale = next->scale;
+            g.film2 = next->film2; g.film2_bstride = next->film2_bs; g.out2_f32 = next->x2_out;
+        }
         if (run_gemm(h, g, h->c2[l], &w.Hid, nullptr, w.X[xb], s, ST_PROF_GEMM_C2)) return 1;
     }
     return 0;
@@ -335,10 +361,17 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
         g.c_clamp = w.B; g.resid_clamp = w.BB - 1; g.film_H = H; g.rope_cs = w.rope_cs;
         return g;
     };
-    // in_proj: x-half GEMM + hoisted P (cond rows P[b], uncond rows P[B])
+    const bool fuse = ln_fusion_on(h, w);
+    auto set_u = [&](GemmArgs& g) { g.ada_bstride = ada_bs; g.u_hi = w.U.hi; g.u_lo = w.U.lo; };
+    // in_proj: x-half GEMM + hoisted P (cond rows P[b], uncond rows P[B])  [+ block 0's FiLM·mask and LN1 in the epilogue]
     {
         GemmArgs g = base(EPI_RESID);
         g.a_bmod = w.B; g.resid = w.P.f32; g.resid_clamp = w.B;
+        if (fuse) {
+            set_u(g);
+            g.ln = 1; g.ln_shift = w.ada; g.ln_scale = w.ada + H;
+            g.film2 = film; g.film2_bstride = film_bstride; g.out2_f32 = w.X[1].f32;
+        }
         if (run_gemm(h, g, h->inx, &xin, nullptr, w.X[0], s)) return 1;
     }
     // buffer plan (skips are block INPUTS, models/estimator.py:128-131):
@@ -355,15 +388,24 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
             ln.xin = w.X[cur].f32; ln.xout = w.X[xb].f32; ln.has_film = 1; ln.film = film_l; ln.film_bstride = film_bstride;
         } else {
             // long skip: x = Conv1d(k=3)(cat(x, skip)) UNMASKED (models/estimator.py:131-132), FiLM·mask fused in the epilogue
+            // [+ LN1 + modulate]
             const int sk = L - 1 - l;      // pop order: block-(L-1-l) input
             xb = (cur == n_lsc) ? n_lsc + 1 : n_lsc;
             GemmArgs g = base(EPI_BIAS | EPI_FILM | EPI_MASK);
             g.film = film_l; g.film_bstride = film_bstride;
+            if (fuse) { set_u(g); g.ln = 1; g.ln_shift = ada_l; g.ln_scale = ada_l + H; }
             Act out = w.X[xb]; out.hi = nullptr; out.lo = nullptr;     // consumed by LN only
             if (run_gemm(h, g, h->lsc[l - n_lsc], &w.X[cur], &w.X[sk], out, s, ST_PROF_GEMM_LSC)) return 1;
             ln.xin = w.X[xb].f32; ln.has_film = 0;
         }
-        if (dit_block_core(h, w, l, ln, ada_l, ada_bs, xb, mask, s)) return 1;
+        // the LN1 of block l+1 follows this block's conv_2 directly when that block has no long-skip conv in between
+        NextLn nx;
+        const bool has_next = fuse && (l + 1 < n_lsc);
+        if (has_next) {
+            nx.film2 = film + (size_t)(l + 1) * 2 * H; nx.film2_bs = film_bstride; nx.x2_out = w.X[xb + 1].f32;
+            nx.shift = w.ada + (size_t)(l + 1) * 6 * H; nx.scale = nx.shift + H;
+        }
+        if (dit_block_core(h, w, l, ln, ada_l, ada_bs, xb, mask, s, fuse, fuse, has_next ? &nx : nullptr)) return 1;
         cur = xb;
     }
     {   // final_proj(x * mask) * mask (:136-137); x is already masked at this point
@@ -716,11 +758,16 @@ int st_text_encoder_forward(st_handle* h, const int64_t* ids, const float* c, co
     ST_LAUNCH(launch_rope_table(w.rope_cs, T, 32, s));
     for (int l = 0; l < L; ++l)        // adaLN(c) for every layer: (B, L, 6H)
         ST_LAUNCH(launch_gemv(c, h->ada_w[l], h->ada_b[l], w.ada + (size_t)l * 6 * H, ada_bs, B, d.gin, 6 * H, 1, 0, s));
+    const bool fuse = ln_fusion_on(h, w);
     for (int l = 0; l < L; ++l) {
         LnArgs ln;
         ln.BB = w.BB; ln.T = w.T; ln.H = H; ln.mask = mask_out; ln.B = w.B; ln.c_clamp = w.B; ln.ada_bstride = ada_bs;
         ln.xin = w.X[0].f32; ln.has_film = 0;
-        if (dit_block_core(h, w, l, ln, w.ada + (size_t)l * 6 * H, ada_bs, 0, mask_out, s)) return 1;
+        NextLn nx;                     // block l+1's LN1 rides in this block's conv_2 epilogue (no FiLM in the text encoder)
+        nx.film2 = nullptr; nx.film2_bs = 0; nx.x2_out = nullptr;
+        nx.shift = w.ada + (size_t)(l + 1) * 6 * H; nx.scale = nx.shift + H;
+        if (dit_block_core(h, w, l, ln, w.ada + (size_t)l * 6 * H, ada_bs, 0, mask_out, s, fuse, fuse && l > 0,
+                           (fuse && l + 1 < L) ? &nx : nullptr)) return 1;
     }
     {   // mu_x = proj(x) * x_mask (:42)
         GemmArgs g;

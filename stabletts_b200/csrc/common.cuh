@@ -60,6 +60,14 @@ struct GemmArgs {
     float* out_f32 = nullptr;
     bf16*  out_hi = nullptr;
     bf16*  out_lo = nullptr;
+    // fused LayerNorm(C = N, no affine, eps 1e-5) + adaLN modulate of the finished output row (tcgen05 engine, tiles that span
+    // all N = 256 channels: gemm_tc_ln_fusable): u = ((x - mean) rstd (1 + scale) + shift) [* mask] -> u_hi / u_lo.
+    // film2 (optional): x2 = (gamma2 x + beta2) * mask first — the NEXT block's time fusion (models/estimator.py:16) —
+    // written to out2_f32, and the LayerNorm runs over x2.
+    int ln = 0, ln_mask_out = 0;
+    const float* ln_shift = nullptr; const float* ln_scale = nullptr; long ada_bstride = 0;
+    bf16* u_hi = nullptr; bf16* u_lo = nullptr;
+    const float* film2 = nullptr; long film2_bstride = 0; float* out2_f32 = nullptr;
 };
 
 // engines
@@ -67,6 +75,8 @@ cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t s);
 // returns cudaErrorNotSupported if the tensor-map driver entry point is unavailable
 cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s);
 const char* gemm_tc_last_error();
+// true when launch_gemm_tc would run this problem on full-row (256-channel) 2-CTA tiles, i.e. GemmArgs::ln may be set
+bool gemm_tc_ln_fusable(const GemmArgs& g, int num_sms);
 
 // ----------------------------------------------------------------------------------------------
 // elementwise / reduction kernels (elementwise.cu)

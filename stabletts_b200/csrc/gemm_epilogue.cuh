@@ -1,13 +1,21 @@
 // Fused conv-GEMM epilogue shared by the 1-CTA (gemm_tc.cu) and 2-CTA (gemm_tc2.cu) tcgen05 kernels.
 //
-// One call drains this warp's share of a finished accumulator tile (its TMEM lane quarter = 32 frames,
-// every second 32-column chunk):
-//   Phase A: tcgen05.ld (thread = frame, 32 columns) -> XOR-swizzled shared-memory staging, no math.
-//   Phase B: lane = (4 frames x 8 float4 column groups): every global access is a coalesced 128-byte
-//            row segment (residual read, fp32 / split-bf16 writes); per-column vectors (bias, gate,
-//            FiLM) sit in registers for the whole chunk, the per-frame mask for the whole tile.
-//   v = acc + bias; [SiLU]; [partial RoPE on q/k head chunks, q pre-scaled for the exp2 softmax];
-//   v = (gamma*v + beta) * mask * gate + resid  -> fp32 and/or split-bf16 planes.
+// Four epilogue warps per CTA, one per TMEM lane quarter; THREAD = FRAME: `tcgen05.ld.32x32b.x32` hands every thread 32
+// consecutive output channels of its own frame, so
+//   * all math runs on registers — bias / SiLU / GELU / FiLM / mask / gate / residual, the partial RoPE of the QKV
+//     projection (the rotation partners j, j+16 of a head live in the same thread) — with per-column vectors read through
+//     warp-uniform 16-byte loads and the per-frame mask / RoPE row held in registers for the whole tile;
+//   * results leave through shared memory and the TMA unit: each chunk is written once into a swizzled staging tile
+//     (explicit `st.shared.v4`, conflict-free) and one elected lane issues `cp.async.bulk.tensor` stores (fp32 tile and /
+//     or the split-bf16 hi / lo tiles); rows beyond T and columns beyond N are clipped by the TMA unit.  No per-lane
+//     global stores, no transposition pass, no generic-address shared accesses (the previous epilogue spent its time there:
+//     profiles/r2c_qkv_o_stalls.md);
+//   * a thread owns its frame's WHOLE row when the tile spans all N channels, so the LayerNorm + adaLN-modulate that follows
+//     O / conv_2 / the long-skip conv / in_proj in the reference (models/diffusion_transformer.py:111-112,119-121) is fused:
+//     pass 1 writes x back into the accumulator's own TMEM columns (`tcgen05.st`) while accumulating shifted sums, pass 2
+//     re-reads it, normalises, modulates and emits the split-bf16 operand of the next GEMM — the separate LayerNorm
+//     kernel and its 2 KB / frame HBM round trip disappear.
+// One code instance per mode (plain / SiLU / GELU / RoPE / LayerNorm-fused); a launch executes exactly one of them.
 #pragma once
 #include "common.cuh"
 #include <cstdlib>
@@ -15,169 +23,300 @@
 
 namespace st {
 
+enum : int { EM_PLAIN = 0, EM_SILU = 1, EM_GELU = 2, EM_ROPE = 3, EM_LN = 4 };
+
+struct EpiMaps { CUtensorMap o_f32, o_hi, o_lo, o2_f32, u_hi, u_lo; };     // TMA STORE maps: (N, T, BB), box 32 x 32 x 1
+
 struct TcParams {
     int n_src, Cs0, Cs1, taps, N, a_bmod, BB, T;
     int m_tiles_per_b, n_tiles, total_tiles;
-    int flags, B, film_H, c_clamp, resid_clamp, rope_H, tap_outer, dbg;
+    int flags, B, film_H, c_clamp, resid_clamp, rope_H, tap_outer;
     long film_bstride, gate_bstride;
     const float *bias, *mask, *film, *gate, *resid, *rope_cs;
-    float* out_f32; bf16* out_hi; bf16* out_lo;
+    int mode;                         // EM_* (kernel-uniform)
+    int has_f32, has_split;           // which forms of the output exist (o_f32 / o_hi + o_lo)
+    // EM_LN: u = ((x - mean) * rstd * (1 + scale) + shift) [* mask] over the finished row -> u_hi / u_lo;
+    // film2: x2 = (gamma2 * x + beta2) * mask first (the NEXT block's time fusion, models/estimator.py:16) -> o2_f32, LN over x2
+    int ln_mask_out, has_film2;
+    const float *ln_shift, *ln_scale, *film2;
+    long ada_bstride, film2_bstride;
 };
+
+inline int epilogue_mode(const GemmArgs& g) {
+    if (g.flags & EPI_ROPE) return EM_ROPE;
+    if (g.ln) return EM_LN;
+    if (g.flags & EPI_SILU) return EM_SILU;
+    if (g.flags & EPI_GELU) return EM_GELU;
+    return EM_PLAIN;
+}
 
 inline void fill_tc_params(TcParams& p, const GemmArgs& g) {
     p.n_src = g.n_src; p.Cs0 = g.Cs[0]; p.Cs1 = g.Cs[1]; p.taps = g.taps; p.N = g.N; p.a_bmod = g.a_bmod; p.BB = g.BB; p.T = g.T;
     p.flags = g.flags; p.B = g.B; p.film_H = g.film_H; p.c_clamp = g.c_clamp; p.resid_clamp = g.resid_clamp; p.rope_H = g.rope_H;
     p.film_bstride = g.film_bstride; p.gate_bstride = g.gate_bstride;
     p.bias = g.bias; p.mask = g.mask; p.film = g.film; p.gate = g.gate; p.resid = g.resid; p.rope_cs = g.rope_cs;
-    p.out_f32 = g.out_f32; p.out_hi = g.out_hi; p.out_lo = g.out_lo;
+    p.mode = epilogue_mode(g);
+    p.has_f32 = g.out_f32 != nullptr; p.has_split = g.out_hi != nullptr;
+    p.ln_mask_out = g.ln_mask_out; p.has_film2 = g.film2 != nullptr;
+    p.ln_shift = g.ln_shift; p.ln_scale = g.ln_scale; p.film2 = g.film2;
+    p.ada_bstride = g.ada_bstride; p.film2_bstride = g.film2_bstride;
     static int tap_outer = -1;
     if (tap_outer < 0) { const char* e = getenv("STABLETTS_B200_TAP_OUTER"); tap_outer = (e && e[0] == '1') ? 1 : 0; }
     p.tap_outer = tap_outer;
-    static int dbg = -1;            // TEMPORARY timing experiments (results are wrong when set): 1 = no global stores, 2 = no stores, no math
-    if (dbg < 0) { const char* e = getenv("STABLETTS_B200_EPI_DBG"); dbg = e ? atoi(e) : 0; }
-    p.dbg = dbg;
 }
 
 // softmax scale folded into q: 1/sqrt(64) * log2(e) (attention runs in the exp2 domain)
 constexpr float kQScale = 0.125f * 1.4426950408889634f;
 
-// Per-tile RoPE table prefetch for the QKV GEMM: the (cos, sin) pairs a lane needs depend only on its frames
-// (t0 + 4*it + rs) and its pair group (c4 & 3), not on the column chunk, so they are loaded ONCE per tile --
-// before the wait on the accumulator barrier, which hides their L2 latency behind the MMAs.
-struct RopeRegs { float4 a[8], b[8]; };
-__device__ __forceinline__ void epilogue_rope_prefetch(const TcParams& p, int t0, int lane, RopeRegs& r) {
-    const int rs = lane >> 3, c4 = lane & 7;
+constexpr int EPI_WARPS = 4;                 // one per TMEM lane quarter
+constexpr int EPI_STAGE_BYTES = 8192;        // per warp: fp32 tile 4 KB (SW128) | hi tile 2 KB (SW64) | lo tile 2 KB (SW64)
+
+namespace epi {
+
+using namespace ptx;
+
+// warp-uniform 16-byte load of a per-column vector at column n (clamped so that a partial last chunk stays in bounds)
+__device__ __forceinline__ float4 colvec(const float* v, int n, int N) {
+    return __ldg(reinterpret_cast<const float4*>(v + min(n, N - 4)));
+}
+
+// this thread's 32 fp32 values -> row `lane` of the 32 x 128 B staging tile, 128-byte swizzle (chunk16 ^= row & 7)
+__device__ __forceinline__ void stage_f32(uint32_t stg, int lane, const float (&x)[32]) {
+    const uint32_t row = stg + (uint32_t)lane * 128u;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int tc = min(t0 + it * 4 + rs, p.T - 1);
-        const float* q = p.rope_cs + ((long)tc * 16 + (c4 & 3) * 4) * 2;
-        r.a[it] = __ldg(reinterpret_cast<const float4*>(q));
-        r.b[it] = __ldg(reinterpret_cast<const float4*>(q + 4));
+    for (int q = 0; q < 8; ++q)
+        st_shared_v4(row + (uint32_t)((q ^ (lane & 7)) << 4), __float_as_uint(x[4 * q]), __float_as_uint(x[4 * q + 1]),
+                     __float_as_uint(x[4 * q + 2]), __float_as_uint(x[4 * q + 3]));
+}
+
+// split-bf16 planes of the same 32 values -> rows of two 32 x 64 B tiles, 64-byte swizzle (chunk16 ^= (row >> 1) & 3)
+__device__ __forceinline__ void stage_split(uint32_t stg_hi, uint32_t stg_lo, int lane, const float (&x)[32]) {
+    const uint32_t off = (uint32_t)lane * 64u;
+    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_bf16x2(x[8 * c + 2 * e], x[8 * c + 2 * e + 1], h[e], l[e]);
+        const uint32_t o = off + (((uint32_t)c ^ sw) << 4);
+        st_shared_v4(stg_hi + o, h[0], h[1], h[2], h[3]);
+        st_shared_v4(stg_lo + o, l[0], l[1], l[2], l[3]);
     }
 }
 
-// bb: batch row, t0: first frame of this warp's 32-frame slab, n0: first column of the tile,
-// tmem_acc: TMEM address of (lane quarter, accumulator column 0), stg: this warp's 4 KB staging.
-// ROPE = true is the QKV variant (bias + partial RoPE + q pre-scale only; launch_gemm_tc rejects EPI_ROPE
-// combined with SiLU/FiLM/mask/gate/residual); ROPE = false is everything else.  Two instances keep each
-// one's registers and instruction footprint small; a launch only ever executes one of them.
-template <int BN, bool ROPE>
-__device__ __forceinline__ void epilogue_tile(const TcParams& p, int bb, int t0, int n0, uint32_t tmem_acc, float4* stg,
-                                              int eh, int lane, const RopeRegs* rr) {
-    using namespace ptx;
-    const int rs = lane >> 3, c4 = lane & 7;
-    const int mb = bb % p.B;
-    const long obase = (long)bb * p.T * p.N;
-    // The two warps of a lane quarter split the 32-column chunks as {0,3,4,7,..} / {1,2,5,6,..}: with RoPE only
-    // the even chunks (first half of every 64-wide head) carry the rotation, and this split gives each warp half of them.
-    auto chunk_col = [eh](int kc) { return (2 * kc + ((kc & 1) ^ eh)) * 32; };   // increasing in kc
-    uint32_t v[32];
-    if (n0 + chunk_col(0) < p.N) tmem_ld32(tmem_acc + (uint32_t)chunk_col(0), v);
+}  // namespace epi
 
-    float mrow[8];
-    const float *film = nullptr, *gate = nullptr, *resid = nullptr;
-    bool plain = true;
-    if constexpr (!ROPE) {
+// per-tile state of one epilogue thread (scalars only: the register arrays are passed separately so that every index
+// stays a compile-time constant after forced inlining)
+struct EpiCtx {
+    int bb, t0, n0, mb, lane;
+    uint32_t tacc, stg, stg_hi, stg_lo;
+    float m;
+    bool plain, has_resid;
+    const float *film, *gate, *resid_row;
+    float s1, s2, kshift;
+};
+
+template <bool ON>
+__device__ __forceinline__ void epi_load_resid(const TcParams& p, const EpiCtx& c, float (&r)[32], int nb) {
+    if constexpr (ON) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int t = t0 + it * 4 + rs;
-            mrow[it] = ((p.flags & EPI_MASK) && t < p.T) ? __ldg(p.mask + (long)mb * p.T + t) : 1.f;
+        for (int q = 0; q < 8; ++q) {
+            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c.has_resid) v4 = __ldg(reinterpret_cast<const float4*>(c.resid_row + min(nb + 4 * q, p.N - 4)));
+            r[4 * q] = v4.x; r[4 * q + 1] = v4.y; r[4 * q + 2] = v4.z; r[4 * q + 3] = v4.w;
         }
-        film = p.film + (long)mb * p.film_bstride;
-        gate = p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride;
-        resid = p.resid + (long)min(bb, p.resid_clamp) * p.T * p.N;
-        plain = (p.flags & (EPI_FILM | EPI_MASK | EPI_GATE | EPI_RESID)) == 0;
+    }
+}
+
+// ---- one 32-channel chunk: v (accumulator) [+ r (residual)] -> x -> staging -> TMA stores ----------------------------
+template <int BN, int MODE>
+__device__ __forceinline__ void epi_chunk(const TcParams& p, const EpiMaps& em, EpiCtx& c, const float (&cs)[32], int kc,
+                                          uint32_t (&v)[32], uint32_t (&vnext)[32], float (&r)[32], float (&rnext)[32]) {
+    using namespace ptx;
+    using namespace epi;
+    constexpr int NCH = BN / 32;
+    constexpr bool ROPE = MODE == EM_ROPE, LN = MODE == EM_LN;
+    const int c0 = kc * 32, nb = c.n0 + c0;
+    const int lane = c.lane;
+    tmem_ld_wait();
+    if (kc + 1 < NCH && nb + 32 < p.N) {               // next chunk's accumulator and residual fly during this chunk's math
+        tmem_ld32(c.tacc + (uint32_t)(c0 + 32), vnext);
+        epi_load_resid<!ROPE>(p, c, rnext, nb + 32);
+    }
+    if (nb >= p.N) return;                             // warp-uniform: tile wider than the remaining columns
+    float x[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.flags & EPI_BIAS) b4 = colvec(p.bias, nb + 4 * q, p.N);
+        x[4 * q] = __uint_as_float(v[4 * q]) + b4.x; x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b4.y;
+        x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b4.z; x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b4.w;
+    }
+    if constexpr (ROPE) {
+        // partial RoPE on the first 32 dims of every 64-wide head of q and k (columns [0, 2H)): pairs (j, j + 16),
+        // theta index j (models/diffusion_transformer.py:173-198); q additionally carries the softmax scale
+        if (nb < 2 * p.rope_H && (nb & 63) == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float a = x[j], b = x[j + 16], co = cs[2 * j], si = cs[2 * j + 1];
+                x[j] = a * co - b * si;
+                x[j + 16] = b * co + a * si;
+            }
+        }
+        if (nb < p.rope_H) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] *= kQScale;
+        }
+    } else {
+        if constexpr (MODE == EM_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
+        }
+        if constexpr (MODE == EM_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = gelu_f(x[j]);
+        }
+        if (!c.plain) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.flags & EPI_GATE) g4 = colvec(c.gate, nb + 4 * q, p.N);
+                if (p.flags & EPI_FILM) { fg = colvec(c.film, nb + 4 * q, p.N); fb = colvec(c.film + p.film_H, nb + 4 * q, p.N); }
+                x[4 * q] = (fg.x * x[4 * q] + fb.x) * c.m * g4.x + r[4 * q];
+                x[4 * q + 1] = (fg.y * x[4 * q + 1] + fb.y) * c.m * g4.y + r[4 * q + 1];
+                x[4 * q + 2] = (fg.z * x[4 * q + 2] + fb.z) * c.m * g4.z + r[4 * q + 2];
+                x[4 * q + 3] = (fg.w * x[4 * q + 3] + fb.w) * c.m * g4.w + r[4 * q + 3];
+            }
+        }
+    }
+    // results -> staging -> TMA.  The staging is rewritten only after the TMA unit has READ the previous chunk.
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+    if (p.has_f32) stage_f32(c.stg, lane, x);
+    if (p.has_split) stage_split(c.stg_hi, c.stg_lo, lane, x);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        if (p.has_f32) tma_store_3d(&em.o_f32, c.stg, nb, c.t0, c.bb);
+        if (p.has_split) { tma_store_3d(&em.o_hi, c.stg_hi, nb, c.t0, c.bb); tma_store_3d(&em.o_lo, c.stg_lo, nb, c.t0, c.bb); }
+        bulk_commit();
+    }
+    if constexpr (LN) {
+        if (p.has_film2) {                             // the next block's FiLM·mask on the finished residual stream
+            const float* f2 = p.film2 + (long)c.mb * p.film2_bstride;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 fg = colvec(f2, nb + 4 * q, p.N), fb = colvec(f2 + p.film_H, nb + 4 * q, p.N);
+                x[4 * q] = (fg.x * x[4 * q] + fb.x) * c.m; x[4 * q + 1] = (fg.y * x[4 * q + 1] + fb.y) * c.m;
+                x[4 * q + 2] = (fg.z * x[4 * q + 2] + fb.z) * c.m; x[4 * q + 3] = (fg.w * x[4 * q + 3] + fb.w) * c.m;
+            }
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+            stage_f32(c.stg, lane, x);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_3d(&em.o2_f32, c.stg, nb, c.t0, c.bb); bulk_commit(); }
+        }
+        if (kc == 0) c.kshift = x[0];                  // shift by a value of the row itself: no cancellation in s2 - s1^2 / n
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float d = x[j] - c.kshift; c.s1 += d; c.s2 = fmaf(d, d, c.s2); }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(x[j]);
+        tmem_st32(c.tacc + (uint32_t)c0, v);           // x back into the accumulator's own columns for pass 2
+    }
+}
+
+// pass 2 of the LayerNorm-fused mode: one chunk of u = ((x - mean) rstd (1 + scale) + shift) * mo -> split-bf16 U
+template <int BN>
+__device__ __forceinline__ void epi_chunk_ln2(const TcParams& p, const EpiMaps& em, const EpiCtx& c, float mean, float rstd, float mo,
+                                              const float* sh, const float* sc, int kc, uint32_t (&v)[32], uint32_t (&vnext)[32]) {
+    using namespace ptx;
+    using namespace epi;
+    constexpr int NCH = BN / 32;
+    const int c0 = kc * 32, nb = c.n0 + c0;
+    tmem_ld_wait();
+    if (kc + 1 < NCH) tmem_ld32(c.tacc + (uint32_t)(c0 + 32), vnext);
+    float u[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 s4 = colvec(sh, nb + 4 * q, p.N), c4 = colvec(sc, nb + 4 * q, p.N);
+        u[4 * q] = ((__uint_as_float(v[4 * q]) - mean) * rstd * (1.f + c4.x) + s4.x) * mo;
+        u[4 * q + 1] = ((__uint_as_float(v[4 * q + 1]) - mean) * rstd * (1.f + c4.y) + s4.y) * mo;
+        u[4 * q + 2] = ((__uint_as_float(v[4 * q + 2]) - mean) * rstd * (1.f + c4.z) + s4.z) * mo;
+        u[4 * q + 3] = ((__uint_as_float(v[4 * q + 3]) - mean) * rstd * (1.f + c4.w) + s4.w) * mo;
+    }
+    if (c.lane == 0) bulk_wait_read0();
+    __syncwarp();
+    stage_split(c.stg_hi, c.stg_lo, c.lane, u);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (c.lane == 0) { tma_store_3d(&em.u_hi, c.stg_hi, nb, c.t0, c.bb); tma_store_3d(&em.u_lo, c.stg_lo, nb, c.t0, c.bb); bulk_commit(); }
+}
+
+// Drains one finished accumulator tile: this warp's 32 frames x BN channels.
+//   bb: batch row, t0: first frame of this warp's slab, n0: first channel of the tile, tacc: TMEM address of (lane quarter,
+//   accumulator column 0), stg: 32-bit shared address of this warp's 8 KB staging (1024-byte aligned).
+// Everything with L2 latency that does not depend on the accumulator (mask, RoPE row, first residual chunk) is issued
+// BEFORE the wait on the accumulator barrier.
+template <int BN, int MODE, class WaitFn>
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& em, int bb, int t0, int n0, uint32_t tacc,
+                                              uint32_t stg, int lane, WaitFn wait_accumulator) {
+    using namespace ptx;
+    using namespace epi;
+    constexpr int NCH = BN / 32;
+    constexpr bool ROPE = MODE == EM_ROPE, LN = MODE == EM_LN;
+    const int tcl = min(t0 + lane, p.T - 1);           // this thread's frame, clamped for the loads (stores are clipped by TMA)
+    EpiCtx c;
+    c.bb = bb; c.t0 = t0; c.n0 = n0; c.mb = bb % p.B; c.lane = lane;
+    c.tacc = tacc; c.stg = stg; c.stg_hi = stg + 4096u; c.stg_lo = stg + 6144u;
+    c.plain = ROPE || (p.flags & (EPI_FILM | EPI_MASK | EPI_GATE | EPI_RESID)) == 0;
+    c.has_resid = !ROPE && (p.flags & EPI_RESID);
+    c.m = 1.f; c.film = nullptr; c.gate = nullptr; c.resid_row = nullptr;
+    c.s1 = 0.f; c.s2 = 0.f; c.kshift = 0.f;
+    float cs[32];                                      // RoPE: (cos, sin) x 16 of this frame
+    float ra[32], rb[32];                              // residual rows, read by their own thread (16 B x 8 of one 128-byte line)
+    if constexpr (ROPE) {
+        const float4* q = reinterpret_cast<const float4*>(p.rope_cs + (long)tcl * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 c4 = __ldg(q + i);
+            cs[4 * i] = c4.x; cs[4 * i + 1] = c4.y; cs[4 * i + 2] = c4.z; cs[4 * i + 3] = c4.w;
+        }
+    } else {
+        if (p.flags & EPI_MASK) c.m = __ldg(p.mask + (long)c.mb * p.T + tcl);
+        c.film = p.film + (long)c.mb * p.film_bstride;
+        c.gate = p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride;
+        c.resid_row = p.resid + ((long)min(bb, p.resid_clamp) * p.T + tcl) * p.N;
+        epi_load_resid<true>(p, c, ra, n0);
     }
 
+    wait_accumulator();
+
+    uint32_t va[32], vb[32];
+    tmem_ld32(tacc, va);
 #pragma unroll 1
-    for (int kc = 0; kc < BN / 64; ++kc) {
-        const int c0 = chunk_col(kc);
-        if (n0 + c0 >= p.N) break;             // warp-uniform; later chunks lie further right
-        const int nb = n0 + c0;                // chunk base column (multiple of 32), warp-uniform
-        const int n = nb + c4 * 4;
-        const bool col_ok = n < p.N;           // N % 4 == 0: a float4 column group is all-in or all-out
-        // per-column vectors: issued before the TMEM wait so their latency overlaps it
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = b4, bp4 = b4;
-        // RoPE applies to the first 32 dims of every 64-wide head of q and k (columns [0, 2H));
-        // pairs (j, j+16) live in lanes c4 and c4^4 of the same frame (models/diffusion_transformer.py:173-198)
-        const bool rope = ROPE && nb < 2 * p.rope_H && (nb & 63) == 0;
-        const float post = (ROPE && nb < p.rope_H) ? kQScale : 1.0f;
-        if (col_ok) {
-            if (p.flags & EPI_BIAS) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            if constexpr (ROPE) {
-                if (rope && (p.flags & EPI_BIAS)) bp4 = __ldg(reinterpret_cast<const float4*>(p.bias + (n ^ 16)));   // partner column
-            } else {
-                if (p.flags & EPI_GATE) g4 = __ldg(reinterpret_cast<const float4*>(gate + n));
-                if (p.flags & EPI_FILM) {
-                    fg = __ldg(reinterpret_cast<const float4*>(film + n));
-                    fb = __ldg(reinterpret_cast<const float4*>(film + p.film_H + n));
-                }
-            }
+    for (int kc = 0; kc < NCH; kc += 2) {
+        epi_chunk<BN, MODE>(p, em, c, cs, kc, va, vb, ra, rb);
+        epi_chunk<BN, MODE>(p, em, c, cs, kc + 1, vb, va, rb, ra);
+    }
+
+    if constexpr (LN) {
+        // ---- pass 2: LayerNorm(C = N, no affine, eps 1e-5) + adaLN modulate [+ FFN input mask] -> split-bf16 U ----------
+        tmem_st_wait();
+        const float inv_n = 1.0f / (float)p.N;
+        const float dm = c.s1 * inv_n;
+        const float mean = c.kshift + dm;
+        const float rstd = rsqrtf(fmaxf(c.s2 * inv_n - dm * dm, 0.f) + 1e-5f);
+        const float mo = p.ln_mask_out ? c.m : 1.0f;
+        const float* sh = p.ln_shift + (long)min(bb, p.c_clamp) * p.ada_bstride;
+        const float* sc = p.ln_scale + (long)min(bb, p.c_clamp) * p.ada_bstride;
+        tmem_ld32(tacc, va);
+#pragma unroll 1
+        for (int kc = 0; kc < NCH; kc += 2) {
+            epi_chunk_ln2<BN>(p, em, c, mean, rstd, mo, sh, sc, kc, va, vb);
+            epi_chunk_ln2<BN>(p, em, c, mean, rstd, mo, sh, sc, kc + 1, vb, va);
         }
-        float4 rv[8];
-        if constexpr (!ROPE) {                 // residual rows of the whole chunk, also ahead of the TMEM wait
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int t = t0 + it * 4 + rs;
-                rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((p.flags & EPI_RESID) && col_ok && t < p.T)
-                    rv[it] = __ldg(reinterpret_cast<const float4*>(resid + (long)t * p.N + n));
-            }
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-            stg[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
-                                                           __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
-        if (kc + 1 < BN / 64 && n0 + chunk_col(kc + 1) < p.N)      // next chunk's TMEM read flies during phase B
-            tmem_ld32(tmem_acc + (uint32_t)chunk_col(kc + 1), v);
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int rl = it * 4 + rs;
-            const int t = t0 + rl;
-            const float4 sv = stg[rl * 8 + (c4 ^ (rl & 7))];
-            if (p.dbg == 2) { if (sv.x == 1.2345e30f) stg[0].x = 1.f; continue; }     // TEMPORARY: phase A only
-            float x[4] = {sv.x + b4.x, sv.y + b4.y, sv.z + b4.z, sv.w + b4.w};
-            if constexpr (ROPE) {
-                if (rope) {                    // warp-uniform branch
-                    const float4 pv = stg[rl * 8 + ((c4 ^ 4) ^ (rl & 7))];      // partner dims (j +- 16) of the same frame
-                    const float sgn = (c4 < 4) ? -1.f : 1.f;      // r_j = -x_{j+16} (j<16), +x_{j-16} (j>=16)
-                    const float4 cs0 = rr->a[it], cs1 = rr->b[it];
-                    x[0] = x[0] * cs0.x + sgn * (pv.x + bp4.x) * cs0.y;
-                    x[1] = x[1] * cs0.z + sgn * (pv.y + bp4.y) * cs0.w;
-                    x[2] = x[2] * cs1.x + sgn * (pv.z + bp4.z) * cs1.y;
-                    x[3] = x[3] * cs1.z + sgn * (pv.w + bp4.w) * cs1.w;
-                }
-                x[0] *= post; x[1] *= post; x[2] *= post; x[3] *= post;
-            } else {
-                if (p.flags & EPI_SILU) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) x[e] = silu_f(x[e]);
-                } else if (p.flags & EPI_GELU) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) x[e] = gelu_f(x[e]);
-                }
-                if (!plain) {                  // bias / SiLU only (cond_proj) skips the neutral FiLM·mask·gate+resid chain
-                    const float m = mrow[it];
-                    x[0] = (fg.x * x[0] + fb.x) * m * g4.x + rv[it].x;
-                    x[1] = (fg.y * x[1] + fb.y) * m * g4.y + rv[it].y;
-                    x[2] = (fg.z * x[2] + fb.z) * m * g4.z + rv[it].z;
-                    x[3] = (fg.w * x[3] + fb.w) * m * g4.w + rv[it].w;
-                }
-            }
-            if (t < p.T && col_ok && (p.dbg == 0 || x[0] == 1.2345e30f)) {
-                const long o = obase + (long)t * p.N + n;
-                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(x[0], x[1], x[2], x[3]);
-                if (p.out_hi) {
-                    uint32_t h01, l01, h23, l23;
-                    split_bf16x2(x[0], x[1], h01, l01); split_bf16x2(x[2], x[3], h23, l23);
-                    *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(h01, h23);
-                    *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(l01, l23);
-                }
-            }
-        }
-        __syncwarp();
     }
 }
 

@@ -27,12 +27,16 @@
 
 namespace st {
 
+bool build_epi_maps(const GemmArgs& g, EpiMaps* em);
+bool tmap_encode_bf16(const void* ptr, int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                      CUtensorMap* out);
+
 namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;             // bf16 elements = 128 bytes = one SW128 row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 384;            // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue
+constexpr int NUM_THREADS = 256;            // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-7: epilogue (one per TMEM lane quarter)
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KB
 
 struct TcMaps {
@@ -49,17 +53,19 @@ template <int BN> struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = 3;
     static constexpr int TMEM_COLS = 2 * BN;                 // two accumulator stages (power of 2 >= 32)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
+    static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;                 // 1024-aligned: swizzled TMA-store tiles
+    static constexpr int BAR_OFF = STAGING_OFF + EPI_WARPS * EPI_STAGE_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 256 /*barriers*/ + 1024 /*align slack*/;
 };
 
 // ----------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ EpiMaps em, const TcParams p) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
     uint64_t* empty_bar = full_bar + C::STAGES;
     uint64_t* tmem_full = empty_bar + C::STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -79,7 +85,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -156,31 +162,26 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
-        // ================= epilogue (8 warps: 4 TMEM lane quarters x 2 column halves) =================
+        // ================= epilogue (4 warps, one per TMEM lane quarter; thread = frame) =================
         const int wq = warp & 3;                       // TMEM lane quarter this warp may access
-        const int eh = (warp - 4) >> 2;                // two warps share a lane quarter: even / odd 32-column chunks
-        float4* stg = reinterpret_cast<float4*>(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 4) * 256;   // 4 KB per warp
+        const uint32_t stg = smem_u32(smem + C::STAGING_OFF + (warp - 4) * EPI_STAGE_BYTES);
+        if (lane == 0) {
+            prefetch_tmap(&em.o_f32); prefetch_tmap(&em.o_hi); prefetch_tmap(&em.o_lo);
+        }
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
             const int bb = m_tile / p.m_tiles_per_b, t0 = (m_tile % p.m_tiles_per_b) * BLOCK_M + wq * 32;
             const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN);
-            if (p.flags & EPI_ROPE) {                  // kernel-uniform
-                RopeRegs rr;
-                epilogue_rope_prefetch(p, t0, lane, rr);
-                mbar_wait(&tmem_full[acc], acc_phase);
-                tc_fence_after();
-                epilogue_tile<BN, true>(p, bb, t0, n_tile * BN, tacc, stg, eh, lane, &rr);
-            } else {
-                mbar_wait(&tmem_full[acc], acc_phase);
-                tc_fence_after();
-                epilogue_tile<BN, false>(p, bb, t0, n_tile * BN, tacc, stg, eh, lane, nullptr);
-            }
+            uint64_t* fb = &tmem_full[acc];
+            const uint32_t ph = acc_phase;
+            epilogue_tile<BN, MODE>(p, em, bb, t0, n_tile * BN, tacc, stg, lane, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) bulk_wait0();                   // the TMA unit has drained this warp's staging before the CTA exits
     }
 
     tc_fence_before();
@@ -199,7 +200,7 @@ std::mutex g_mu;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
 struct MapKey {
-    const void* ptr; uint64_t d0, d1, d2; uint32_t b0, b1; int rank;
+    const void* ptr; uint64_t d0, d1, d2; uint32_t b0, b1; int rank;      // rank also carries dtype / swizzle (kind << 8)
     bool operator==(const MapKey& o) const {
         return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && b0 == o.b0 && b1 == o.b1 && rank == o.rank;
     }
@@ -227,18 +228,24 @@ bool ensure_encode() {
     return true;
 }
 
-// bf16 tensor, dim0 contiguous.  rank 3: (d0, d1, d2) box (b0, b1, 1); rank 2: (d0, d1) box (b0, b1)
-bool get_map(const void* ptr, int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1, CUtensorMap* out) {
-    MapKey key{ptr, d0, d1, d2, b0, b1, rank};
+// dim0 contiguous.  rank 3: (d0, d1, d2) box (b0, b1, 1); rank 2: (d0, d1) box (b0, b1).
+// kind 0: bf16 operand tile, 128-byte swizzle (TMA loads);  kind 1: fp32 output tile, 128-byte swizzle;  kind 2: bf16 output
+// tile with 64-byte rows, 64-byte swizzle (TMA stores of the epilogue)
+bool get_map(const void* ptr, int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1, CUtensorMap* out,
+             int kind = 0) {
+    MapKey key{ptr, d0, d1, d2, b0, b1, rank | (kind << 8)};
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return true; }
+    const uint64_t es = kind == 1 ? 4 : 2;
     cuuint64_t dims[3] = {d0, d1, d2};
-    cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+    cuuint64_t strides[2] = {d0 * es, d0 * d1 * es};
     cuuint32_t box[3] = {b0, b1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUtensorMap m;
-    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = g_encode(&m, kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                          const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          kind == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          kind == 0 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         g_err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " (rank " + std::to_string(rank) +
@@ -251,29 +258,40 @@ bool get_map(const void* ptr, int rank, uint64_t d0, uint64_t d1, uint64_t d2, u
     return true;
 }
 
+template <int BN, int MODE>
+cudaError_t launch_inst(const TcMaps& maps, const EpiMaps& em, const TcParams& p, int grid, cudaStream_t s) {
+    using C = Cfg<BN>;
+    static std::atomic<uint64_t> attr_done{0};      // one bit per device (per template instance)
+    cudaError_t e = ensure_dyn_smem(gemm_tc_kernel<BN, MODE>, C::SMEM_BYTES, attr_done);
+    if (e != cudaSuccess) { g_err = "cudaFuncSetAttribute(max dynamic smem) failed"; return e; }
+    return launch_k(gemm_tc_kernel<BN, MODE>, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, s, maps, em, p);
+}
+
 template <int BN>
 cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t s) {
     using C = Cfg<BN>;
     TcMaps maps;
     for (int i = 0; i < g.n_src; ++i) {
-        if (!get_map(g.A_hi[i], 3, (uint64_t)g.Cs[i], (uint64_t)g.T, (uint64_t)g.a_bmod, BLOCK_K, BLOCK_M, &maps.a_hi[i])) return cudaErrorInvalidValue;
-        if (!get_map(g.A_lo[i], 3, (uint64_t)g.Cs[i], (uint64_t)g.T, (uint64_t)g.a_bmod, BLOCK_K, BLOCK_M, &maps.a_lo[i])) return cudaErrorInvalidValue;
+        if (!tmap_encode_bf16(g.A_hi[i], 3, (uint64_t)g.Cs[i], (uint64_t)g.T, (uint64_t)g.a_bmod, BLOCK_K, BLOCK_M, &maps.a_hi[i])) return cudaErrorInvalidValue;
+        if (!tmap_encode_bf16(g.A_lo[i], 3, (uint64_t)g.Cs[i], (uint64_t)g.T, (uint64_t)g.a_bmod, BLOCK_K, BLOCK_M, &maps.a_lo[i])) return cudaErrorInvalidValue;
     }
     if (g.n_src == 1) { maps.a_hi[1] = maps.a_hi[0]; maps.a_lo[1] = maps.a_lo[0]; }
-    if (!get_map(g.W_hi, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BLOCK_K, BN, &maps.w_hi)) return cudaErrorInvalidValue;
-    if (!get_map(g.W_lo, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BLOCK_K, BN, &maps.w_lo)) return cudaErrorInvalidValue;
+    if (!tmap_encode_bf16(g.W_hi, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BLOCK_K, BN, &maps.w_hi)) return cudaErrorInvalidValue;
+    if (!tmap_encode_bf16(g.W_lo, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BLOCK_K, BN, &maps.w_lo)) return cudaErrorInvalidValue;
+    EpiMaps em;
+    if (!build_epi_maps(g, &em)) { if (g_err.empty()) g_err = "epilogue store maps: missing output plane"; return cudaErrorInvalidValue; }
     TcParams p;
     fill_tc_params(p, g);
     p.m_tiles_per_b = (g.T + BLOCK_M - 1) / BLOCK_M;
     p.n_tiles = (g.N + BN - 1) / BN;
     p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
-    {
-        static std::atomic<uint64_t> attr_done{0};  // one bit per device (per template instance)
-        cudaError_t e = ensure_dyn_smem(gemm_tc_kernel<BN>, C::SMEM_BYTES, attr_done);
-        if (e != cudaSuccess) { g_err = "cudaFuncSetAttribute(max dynamic smem) failed"; return e; }
-    }
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-    return launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, s, maps, p);
+    switch (p.mode) {                  // one kernel instance per epilogue mode (EM_LN needs full rows: 2-CTA kernel only)
+        case EM_ROPE: return launch_inst<BN, EM_ROPE>(maps, em, p, grid, s);
+        case EM_SILU: return launch_inst<BN, EM_SILU>(maps, em, p, grid, s);
+        case EM_GELU: return launch_inst<BN, EM_GELU>(maps, em, p, grid, s);
+        default:      return launch_inst<BN, EM_PLAIN>(maps, em, p, grid, s);
+    }
 }
 
 }  // namespace
@@ -286,6 +304,33 @@ bool tmap_encode_bf16(const void* ptr, int rank, uint64_t d0, uint64_t d1, uint6
     std::lock_guard<std::mutex> lk(g_mu);
     if (!ensure_encode()) return false;
     return get_map(ptr, rank, d0, d1, d2, b0, b1, out);
+}
+
+// TMA STORE maps of the epilogue: (N, T, BB) tensors, box 32 channels x 32 frames; fp32 or one split-bf16 plane
+bool tmap_encode_store(const void* ptr, bool f32, uint64_t N, uint64_t T, uint64_t BB, CUtensorMap* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!ensure_encode()) return false;
+    return get_map(ptr, 3, N, T, BB, 32, 32, out, f32 ? 1 : 2);
+}
+
+// every output form the GemmArgs names gets its store map; unused slots alias a valid one (never dereferenced)
+bool build_epi_maps(const GemmArgs& g, EpiMaps* em) {
+    const uint64_t N = (uint64_t)g.N, T = (uint64_t)g.T, BB = (uint64_t)g.BB;
+    const CUtensorMap* any = nullptr;
+    bool ok = true;
+    if (g.out_f32) { ok = ok && tmap_encode_store(g.out_f32, true, N, T, BB, &em->o_f32); any = &em->o_f32; }
+    if (g.out_hi) {
+        ok = ok && g.out_lo && tmap_encode_store(g.out_hi, false, N, T, BB, &em->o_hi) && tmap_encode_store(g.out_lo, false, N, T, BB, &em->o_lo);
+        any = &em->o_hi;
+    }
+    if (g.film2) { ok = ok && g.out2_f32 && tmap_encode_store(g.out2_f32, true, N, T, BB, &em->o2_f32); }
+    if (g.ln) ok = ok && g.u_hi && g.u_lo && tmap_encode_store(g.u_hi, false, N, T, BB, &em->u_hi) && tmap_encode_store(g.u_lo, false, N, T, BB, &em->u_lo);
+    if (!ok || !any) return false;
+    if (!g.out_f32) em->o_f32 = *any;
+    if (!g.out_hi) { em->o_hi = *any; em->o_lo = *any; }
+    if (!g.film2) em->o2_f32 = *any;
+    if (!g.ln) { em->u_hi = *any; em->u_lo = *any; }
+    return true;
 }
 
 bool gemm_tc2_eligible(const GemmArgs& g, int num_sms);
@@ -302,6 +347,16 @@ static int tc2_mode() {
     return mode;
 }
 
+static bool tc2_shapes_ok(const GemmArgs& g) {
+    return g.A_hi[0] && g.W_hi && g.N >= 256 && g.N % 128 == 0 && g.Ktot % 8 == 0 && g.Cs[0] % 8 == 0 &&
+           (g.n_src == 1 || (g.Cs[0] % BLOCK_K == 0 && g.Cs[1] % 8 == 0 && g.A_hi[1]));
+}
+
+bool gemm_tc_ln_fusable(const GemmArgs& g, int num_sms) {
+    const int mode = tc2_mode();
+    return g.N == 256 && mode && tc2_shapes_ok(g) && (mode == 2 || gemm_tc2_eligible(g, num_sms));
+}
+
 cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s) {
     if (g.BB == 0 || g.T == 0) return cudaSuccess;
     if ((g.flags & EPI_ROPE) && (g.flags & (EPI_SILU | EPI_GELU | EPI_FILM | EPI_MASK | EPI_GATE | EPI_RESID))) {
@@ -311,16 +366,22 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s) {
     }
     {
         const int mode = tc2_mode();
-        bool ok = g.A_hi[0] && g.W_hi && g.N >= 256 && g.N % 128 == 0 && g.Ktot % 8 == 0 && g.Cs[0] % 8 == 0 &&
-                  (g.n_src == 1 || (g.Cs[0] % BLOCK_K == 0 && g.Cs[1] % 8 == 0 && g.A_hi[1]));
+        const bool ok = tc2_shapes_ok(g);
         if (mode && ok && (mode == 2 || gemm_tc2_eligible(g, num_sms))) {
             cudaError_t e = launch_gemm_tc2(g, num_sms, s);
             if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(g_mu); g_err = std::string("2-CTA kernel: ") + gemm_tc2_last_error(); }
             return e;
         }
     }
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (!ensure_encode()) return cudaErrorNotSupported;
+    if (g.ln) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_err = "fused LayerNorm needs full-row 2-CTA tiles (check gemm_tc_ln_fusable before setting GemmArgs::ln)";
+        return cudaErrorInvalidValue;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!ensure_encode()) return cudaErrorNotSupported;
+    }
     for (int i = 0; i < g.n_src; ++i) {
         if (!g.A_hi[i] || !g.A_lo[i]) { g_err = "split-bf16 A planes missing"; return cudaErrorInvalidValue; }
         if (g.Cs[i] % 8) { g_err = "A channels must be a multiple of 8 (16-byte TMA stride)"; return cudaErrorInvalidValue; }

@@ -10,7 +10,7 @@
 //                                TMA loads complete_tx on the leader's barrier (cta_group::2 TMA form)
 //   empty[s]       each CTA      count 1: tcgen05.commit.cta_group::2 multicast from the leader's MMA thread
 //   tmem_full[a]   each CTA      count 1: multicast commit after a tile's last k-block
-//   tmem_empty[a]  leader only   count 16: 8 epilogue warps of each CTA (the peer arrives remotely, mapa)
+//   tmem_empty[a]  leader only   count 8: 4 epilogue warps of each CTA (the peer arrives remotely, mapa)
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "gemm_epilogue.cuh"
@@ -21,6 +21,7 @@ namespace st {
 
 bool tmap_encode_bf16(const void* ptr, int rank, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
                       CUtensorMap* out);
+bool build_epi_maps(const GemmArgs& g, EpiMaps* em);
 const char* gemm_tc_last_error();
 
 namespace {
@@ -30,7 +31,7 @@ using namespace ptx;
 constexpr int BM = 128;                 // rows per CTA (pair tile: 256)
 constexpr int BK = 64;
 constexpr int UK = 16;
-constexpr int THREADS = 384;            // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue
+constexpr int THREADS = 256;            // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-7: epilogue (one per TMEM lane quarter)
 constexpr int TILE_BYTES = 128 * BK * 2;            // 16 KB: one A plane tile (128 frames x 64 channels)
 
 // BN2 = pair tile width: 256 (each CTA stages 128 weight rows) or 128 (64 weight rows; twice as many, half as long
@@ -41,21 +42,26 @@ template <int BN2> struct Cfg2 {
     static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;    // A_hi, A_lo, Bh_hi, Bh_lo: 64 / 48 KB
     static constexpr int STAGES = BN2 == 256 ? 3 : 4;
     static constexpr int TMEM_COLS = 2 * BN2;                                // two accumulator stages
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 4096;
+    static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;                 // 1024-aligned: swizzled TMA-store tiles
+    static constexpr int BAR_OFF = STAGING_OFF + EPI_WARPS * EPI_STAGE_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
 };
 
 struct Maps2 { CUtensorMap a_hi[2], a_lo[2], w_hi, w_lo; };
 
 typedef TcParams Params2;
 
-template <int BN2>
+// One kernel instance per (tile width, epilogue mode): a combined kernel that switched over the modes at run time made
+// ptxas keep every mode's register arrays in one allocation (2 KB of spills); separate instances also keep the
+// instruction footprint of a launch small.
+template <int BN2, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
+gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiMaps em, const Params2 p) {
     constexpr int B_TILE_BYTES = Cfg2<BN2>::B_TILE_BYTES, STAGE_BYTES = Cfg2<BN2>::STAGE_BYTES, STAGES = Cfg2<BN2>::STAGES;
     constexpr int TMEM_COLS = Cfg2<BN2>::TMEM_COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg2<BN2>::BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -78,7 +84,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 16); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * EPI_WARPS); }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc_2sm<TMEM_COLS>(tmem_slot);
@@ -152,32 +158,28 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const Params2 p) {
             }
         }
     } else if (warp >= 4) {
-        // ================= epilogue (both CTAs, own 128 rows; 8 warps) =================
+        // ================= epilogue (both CTAs, own 128 rows; 4 warps, thread = frame) =================
         const int wq = warp & 3;
-        const int eh = (warp - 4) >> 2;
-        float4* stg = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 4) * 256;
+        const uint32_t stg = smem_u32(smem + Cfg2<BN2>::STAGING_OFF + (warp - 4) * EPI_STAGE_BYTES);
+        if (lane == 0) {
+            prefetch_tmap(&em.o_f32); prefetch_tmap(&em.o_hi); prefetch_tmap(&em.o_lo);
+            if (MODE == EM_LN) { prefetch_tmap(&em.u_hi); prefetch_tmap(&em.u_lo); prefetch_tmap(&em.o2_f32); }
+        }
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
             const int bb = m_tile / p.m_tiles_per_b;
             const int t0 = (m_tile % p.m_tiles_per_b) * (2 * BM) + (int)rank * BM + wq * 32;
             const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN2);
-            if (p.flags & EPI_ROPE) {                  // kernel-uniform
-                RopeRegs rr;
-                epilogue_rope_prefetch(p, t0, lane, rr);
-                mbar_wait(&tmem_full[acc], acc_phase);
-                tc_fence_after();
-                epilogue_tile<BN2, true>(p, bb, t0, n_tile * BN2, tacc, stg, eh, lane, &rr);
-            } else {
-                mbar_wait(&tmem_full[acc], acc_phase);
-                tc_fence_after();
-                epilogue_tile<BN2, false>(p, bb, t0, n_tile * BN2, tacc, stg, eh, lane, nullptr);
-            }
+            uint64_t* fb = &tmem_full[acc];
+            const uint32_t ph = acc_phase;
+            epilogue_tile<BN2, MODE>(p, em, bb, t0, n_tile * BN2, tacc, stg, lane, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);      // the LEADER's barrier gates the next MMA
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) bulk_wait0();                   // the TMA unit has drained this warp's staging before the CTA exits
     }
 
     tc_fence_before();
@@ -206,6 +208,7 @@ bool gemm_tc2_eligible(const GemmArgs& g, int num_sms) {
 static int pick_bn2(const GemmArgs& g, int pairs) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("STABLETTS_B200_TC2_BN"); forced = e ? atoi(e) : 0; }
+    if (g.ln) return 256;                          // fused LayerNorm: a CTA must own whole 256-channel rows
     if (forced == 128 || forced == 256) return forced;
     const long m_tiles = (long)g.BB * ((g.T + 2 * BM - 1) / (2 * BM));
     const long t256 = m_tiles * ((g.N + 255) / 256), t128 = m_tiles * ((g.N + 127) / 128);
@@ -213,17 +216,26 @@ static int pick_bn2(const GemmArgs& g, int pairs) {
     return w128 < 0.97 * w256 ? 128 : 256;
 }
 
-template <int BN2>
-static cudaError_t launch_tc2_bn(const Maps2& maps, Params2& p, const GemmArgs& g, int pairs, cudaStream_t s) {
+template <int BN2, int MODE>
+static cudaError_t launch_tc2_inst(const Maps2& maps, const EpiMaps& em, const Params2& p, int pairs, cudaStream_t s) {
     static std::atomic<uint64_t> attr_done{0};      // one bit per device
+    cudaError_t e = ensure_dyn_smem(gemm_tc2_kernel<BN2, MODE>, Cfg2<BN2>::SMEM_BYTES, attr_done);
+    if (e != cudaSuccess) { g_err2 = "cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc2_kernel"; return e; }
+    const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
+    return launch_k(gemm_tc2_kernel<BN2, MODE>, dim3(2 * clusters), dim3(THREADS), (size_t)Cfg2<BN2>::SMEM_BYTES, s, maps, em, p);
+}
+
+template <int BN2>
+static cudaError_t launch_tc2_bn(const Maps2& maps, const EpiMaps& em, Params2& p, const GemmArgs& g, int pairs, cudaStream_t s) {
     p.n_tiles = (g.N + BN2 - 1) / BN2;
     p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
-    {
-        cudaError_t e = ensure_dyn_smem(gemm_tc2_kernel<BN2>, Cfg2<BN2>::SMEM_BYTES, attr_done);
-        if (e != cudaSuccess) { g_err2 = "cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc2_kernel"; return e; }
+    switch (p.mode) {
+        case EM_ROPE: return launch_tc2_inst<BN2, EM_ROPE>(maps, em, p, pairs, s);
+        case EM_LN:   return launch_tc2_inst<BN2, EM_LN>(maps, em, p, pairs, s);
+        case EM_SILU: return launch_tc2_inst<BN2, EM_SILU>(maps, em, p, pairs, s);
+        case EM_GELU: return launch_tc2_inst<BN2, EM_GELU>(maps, em, p, pairs, s);
+        default:      return launch_tc2_inst<BN2, EM_PLAIN>(maps, em, p, pairs, s);
     }
-    const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
-    return launch_k(gemm_tc2_kernel<BN2>, dim3(2 * clusters), dim3(THREADS), (size_t)Cfg2<BN2>::SMEM_BYTES, s, maps, p);
 }
 
 cudaError_t launch_gemm_tc2(const GemmArgs& g, int num_sms, cudaStream_t s) {
@@ -241,10 +253,13 @@ cudaError_t launch_gemm_tc2(const GemmArgs& g, int num_sms, cudaStream_t s) {
         !tmap_encode_bf16(g.W_lo, 2, (uint64_t)g.Ktot, (uint64_t)g.taps * g.N, 1, BK, bn2 / 2, &maps.w_lo)) {
         g_err2 = gemm_tc_last_error(); return cudaErrorInvalidValue;
     }
+    if (g.ln && g.N != 256) { g_err2 = "fused LayerNorm needs N == 256 (one tile spans the whole row)"; return cudaErrorInvalidValue; }
+    EpiMaps em;
+    if (!build_epi_maps(g, &em)) { g_err2 = "epilogue store maps: missing output plane / " + std::string(gemm_tc_last_error()); return cudaErrorInvalidValue; }
     Params2 p;
     fill_tc_params(p, g);
     p.m_tiles_per_b = (g.T + 2 * BM - 1) / (2 * BM);
-    return bn2 == 128 ? launch_tc2_bn<128>(maps, p, g, pairs, s) : launch_tc2_bn<256>(maps, p, g, pairs, s);
+    return bn2 == 128 ? launch_tc2_bn<128>(maps, em, p, g, pairs, s) : launch_tc2_bn<256>(maps, em, p, g, pairs, s);
 }
 
 }  // namespace st
