@@ -190,7 +190,8 @@ int st_test_conv(st_handle* h, const float* x, const float* w, const float* bias
 
 /* Times `reps` launches of the selected engine's conv-GEMM on device-generated synthetic operands:
  * (B,T,Cin) x [k][Cout][Cin] -> (B,T,Cout); epi != 0 uses the conv_2-style epilogue (bias, mask, gate,
- * residual, fp32 + split-bf16 outputs), epi == 0 bias + split-bf16 output.  *ms_out = ms per launch. */
+ * residual, fp32 + split-bf16 outputs), epi == 2 the conv_1-style one (bias, SiLU, mask, split-bf16 output), epi == 0 bias +
+ * split-bf16 output.  *ms_out = ms per launch. */
 int st_bench_conv(st_handle* h, int B, int Cin, int Cout, int T, int k, int epi, int reps, float* ms_out);
 
 /* Masked multi-head attention with partial RoPE on packed qkv (B,T,3*hidden) -> (B,T,hidden). */
@@ -199,6 +200,9 @@ int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* 
 /* Debug hook: with STABLETTS_B200_ATT_TRACE=1 the attention kernel records clock64 stamps of one CTA's softmax and
  * MMA warps per key block; this copies the last launch's [32 blocks][16 slots] table to the host. */
 int st_test_attention_trace(long long* host_out);
+/* Debug hook: with STABLETTS_B200_EPI_TRACE=1 the 2-CTA GEMM records clock64 stamps of one epilogue warp per 32-channel chunk
+ * (chunk start, accumulator ready, math done, staging free, stores issued); copies [4 tiles][8 chunks][8] to the host. */
+int st_test_gemm_trace(long long* host_out);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ ST_PROF_NCAT = len(ST_PROF_NAMES)
 EXPORTS = [
     "st_create", "st_destroy", "st_last_error", "st_version", "st_load_weight", "st_finalize_weights",
     "st_set_engine", "st_workspace_bytes", "st_attach_workspace", "st_estimator_forward", "st_cfm_loss", "st_solve",
-    "st_solve_host", "st_solve_adaptive", "st_solve_adaptive_ex", "st_align_lengths", "st_align_expand", "st_create_text_encoder", "st_text_encoder_forward", "st_create_vocos", "st_vocos_forward", "st_launch_count", "st_profile_begin", "st_profile_end", "st_test_gemm", "st_test_conv", "st_test_attention", "st_test_attention_trace", "st_bench_conv",
+    "st_solve_host", "st_solve_adaptive", "st_solve_adaptive_ex", "st_align_lengths", "st_align_expand", "st_create_text_encoder", "st_text_encoder_forward", "st_create_vocos", "st_vocos_forward", "st_launch_count", "st_profile_begin", "st_profile_end", "st_test_gemm", "st_test_conv", "st_test_attention", "st_test_attention_trace", "st_test_gemm_trace", "st_bench_conv",
 ]
 
 
@@ -30,6 +30,11 @@ class StVocosDims(C.Structure):
 
 
 def library_path() -> str:
+    """The in-tree library; STABLETTS_B200_LIB=<file name or path> selects another build of it (A/B runs of kernel
+    generations on one box — never a different backend)."""
+    override = os.environ.get("STABLETTS_B200_LIB")
+    if override:
+        return override if os.path.isabs(override) else os.path.join(_HERE, override)
     return os.path.join(_HERE, "libstabletts_b200.so")
 
 
@@ -44,6 +49,16 @@ def load_library() -> C.CDLL:
             f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). stabletts_b200 has no CPU/PyTorch fallback.")
     lib = C.CDLL(path)
+    if os.environ.get("STABLETTS_B200_LIB"):       # an older build may lack the newest debug hooks: bind what it has
+        class _Tolerant:
+            def __init__(self, inner): object.__setattr__(self, "_inner", inner)
+            def __getattr__(self, name):
+                try:
+                    return getattr(self._inner, name)
+                except AttributeError:
+                    return type("_Missing", (), {"argtypes": None, "restype": None})()
+        real, lib = lib, _Tolerant(lib)
+        bind = lib
     vp, f32p, i64, i32 = C.c_void_p, C.c_void_p, C.c_int64, C.c_int
     lib.st_create.argtypes = [C.POINTER(StDims), i32, C.POINTER(vp)]
     lib.st_destroy.argtypes = [vp]
@@ -78,10 +93,13 @@ def load_library() -> C.CDLL:
     lib.st_bench_conv.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float)]
     lib.st_test_attention.argtypes = [vp, f32p, f32p, f32p, i32, i32, vp]
     lib.st_test_attention_trace.argtypes = [C.POINTER(C.c_longlong)]
+    lib.st_test_gemm_trace.argtypes = [C.POINTER(C.c_longlong)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("st_version",):
             fn.restype = C.c_int
+    if os.environ.get("STABLETTS_B200_LIB"):
+        lib = real
     _LIB = lib
     return lib
 

@@ -1230,11 +1230,11 @@ int st_bench_conv(st_handle* h, int B, int Cin, int Cout, int T, int k, int epi,
         if (launch_split(xf, xh, xl, (long)nx, s) != cudaSuccess || launch_split(wf, wh, wl, (long)nw, s) != cudaSuccess) { rc = fail(h, "split failed"); break; }
         GemmArgs g;
         g.BB = B; g.T = T; g.a_bmod = B; g.B = B; g.resid_clamp = B - 1; g.c_clamp = B - 1; g.mask = mask;
-        g.flags = epi ? (EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID) : EPI_BIAS;
+        g.flags = epi == 1 ? (EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID) : (epi == 2 ? (EPI_BIAS | EPI_SILU | EPI_MASK) : EPI_BIAS);
         g.gate = gate; g.gate_bstride = Cout; g.resid = of;
         GemmW w; w.f32 = wf; w.hi = wh; w.lo = wl; w.bias = bias; w.taps = k; w.N = Cout; w.K = Cin;
         Act a; a.C = Cin; a.f32 = xf; a.hi = tc ? xh : nullptr; a.lo = tc ? xl : nullptr;
-        Act o; o.C = Cout; o.f32 = epi ? of : nullptr; o.hi = oh; o.lo = ol;
+        Act o; o.C = Cout; o.f32 = epi == 1 ? of : nullptr; o.hi = oh; o.lo = ol;
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         for (int i = 0; i < 2 && !rc; ++i) rc = run_gemm(h, g, w, &a, nullptr, o, s);
         if (rc) break;
@@ -1255,6 +1255,7 @@ int st_bench_conv(st_handle* h, int B, int Cin, int Cout, int T, int k, int epi,
 }
 
 int st_test_attention_trace(long long* host_out) { return st::attention_tc_read_trace(host_out); }
+int st_test_gemm_trace(long long* host_out) { return st::gemm_tc2_read_trace(host_out); }
 
 int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* out, int B, int T, void* stream) {
     if (!h) return 1;

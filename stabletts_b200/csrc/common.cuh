@@ -77,6 +77,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s);
 const char* gemm_tc_last_error();
 // true when launch_gemm_tc would run this problem on full-row (256-channel) 2-CTA tiles, i.e. GemmArgs::ln may be set
 bool gemm_tc_ln_fusable(const GemmArgs& g, int num_sms);
+int gemm_tc2_read_trace(long long* host_out);       // debug (STABLETTS_B200_EPI_TRACE=1)
 
 // ----------------------------------------------------------------------------------------------
 // elementwise / reduction kernels (elementwise.cu)
@@ -192,6 +193,14 @@ inline cudaError_t ensure_dyn_smem(K kernel, int bytes, std::atomic<uint64_t>& d
 }
 
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// SiLU on the two SFU approximations directly (ex2.approx + rcp.approx, ~3e-7 relative): no range-fix-up code around them.
+// v -> -inf: ex2(+big) = +inf, rcp(inf) = 0, v * 0 = -0;  v -> +inf: ex2(-big) = 0, v * rcp(1) = v.
+__device__ __forceinline__ float silu_fast(float v) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return v * r;
+}
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 
 // two floats -> packed (hi0,hi1) and (lo0,lo1) bf16x2 words: one cvt.rn.bf16x2 per plane

@@ -1,6 +1,8 @@
 // Fused conv-GEMM epilogue shared by the 1-CTA (gemm_tc.cu) and 2-CTA (gemm_tc2.cu) tcgen05 kernels.
 //
-// Four epilogue warps per CTA, one per TMEM lane quarter; THREAD = FRAME: `tcgen05.ld.32x32b.x32` hands every thread 32
+// Eight epilogue warps per CTA in two groups of four (one warp per TMEM lane quarter); group g drains accumulator stage g,
+// i.e. every second tile, so two tiles are in flight and each scheduler has two epilogue warps to hide latencies behind
+// (a single warp per scheduler left every L2 / TMEM / fence latency exposed: profiles/r2f_epilogue_trace.md).  THREAD = FRAME: `tcgen05.ld.32x32b.x32` hands every thread 32
 // consecutive output channels of its own frame, so
 //   * all math runs on registers — bias / SiLU / GELU / FiLM / mask / gate / residual, the partial RoPE of the QKV
 //     projection (the rotation partners j, j+16 of a head live in the same thread) — with per-column vectors read through
@@ -23,7 +25,7 @@
 
 namespace st {
 
-enum : int { EM_PLAIN = 0, EM_SILU = 1, EM_GELU = 2, EM_ROPE = 3, EM_LN = 4 };
+enum : int { EM_PLAIN = 0, EM_SILU = 1, EM_GELU = 2, EM_ROPE = 3, EM_LN = 4, EM_RESID = 5 };   // EM_RESID: plain + residual rows
 
 struct EpiMaps { CUtensorMap o_f32, o_hi, o_lo, o2_f32, u_hi, u_lo; };     // TMA STORE maps: (N, T, BB), box 32 x 32 x 1
 
@@ -40,6 +42,7 @@ struct TcParams {
     int ln_mask_out, has_film2;
     const float *ln_shift, *ln_scale, *film2;
     long ada_bstride, film2_bstride;
+    long long* dbg;                   // debug: clock64 stamps of one epilogue warp (STABLETTS_B200_EPI_TRACE=1), else nullptr
 };
 
 inline int epilogue_mode(const GemmArgs& g) {
@@ -47,6 +50,7 @@ inline int epilogue_mode(const GemmArgs& g) {
     if (g.ln) return EM_LN;
     if (g.flags & EPI_SILU) return EM_SILU;
     if (g.flags & EPI_GELU) return EM_GELU;
+    if (g.flags & EPI_RESID) return EM_RESID;
     return EM_PLAIN;
 }
 
@@ -60,6 +64,7 @@ inline void fill_tc_params(TcParams& p, const GemmArgs& g) {
     p.ln_mask_out = g.ln_mask_out; p.has_film2 = g.film2 != nullptr;
     p.ln_shift = g.ln_shift; p.ln_scale = g.ln_scale; p.film2 = g.film2;
     p.ada_bstride = g.ada_bstride; p.film2_bstride = g.film2_bstride;
+    p.dbg = nullptr;
     static int tap_outer = -1;
     if (tap_outer < 0) { const char* e = getenv("STABLETTS_B200_TAP_OUTER"); tap_outer = (e && e[0] == '1') ? 1 : 0; }
     p.tap_outer = tap_outer;
@@ -68,8 +73,8 @@ inline void fill_tc_params(TcParams& p, const GemmArgs& g) {
 // softmax scale folded into q: 1/sqrt(64) * log2(e) (attention runs in the exp2 domain)
 constexpr float kQScale = 0.125f * 1.4426950408889634f;
 
-constexpr int EPI_WARPS = 4;                 // one per TMEM lane quarter
-constexpr int EPI_STAGE_BYTES = 8192;        // per warp: fp32 tile 4 KB (SW128) | hi tile 2 KB (SW64) | lo tile 2 KB (SW64)
+constexpr int EPI_WARPS = 8;                 // two groups of four (one warp per TMEM lane quarter): group g drains accumulator stage g
+constexpr int EPI_STAGE_BYTES = 4096;        // per warp: one fp32 tile (SW128), or a hi tile 2 KB + a lo tile 2 KB (SW64)
 
 namespace epi {
 
@@ -110,9 +115,10 @@ __device__ __forceinline__ void stage_split(uint32_t stg_hi, uint32_t stg_lo, in
 // stays a compile-time constant after forced inlining)
 struct EpiCtx {
     int bb, t0, n0, mb, lane;
-    uint32_t tacc, stg, stg_hi, stg_lo;
-    float m;
-    bool plain, has_resid;
+    uint32_t tacc, stg;
+    float m, mrow;                    // m: mask factor of the GEMM-output chain (1 without EPI_MASK); mrow: the frame's mask itself
+    int tile_it;
+    bool plain, has_resid, mask_only;
     const float *film, *gate, *resid_row;
     float s1, s2, kshift;
 };
@@ -129,22 +135,44 @@ __device__ __forceinline__ void epi_load_resid(const TcParams& p, const EpiCtx& 
     }
 }
 
+// this thread's 32 values -> the warp's 4 KB staging -> TMA store(s); the staging is rewritten only after the TMA unit has
+// READ what it held (cp.async.bulk.wait_group.read)
+__device__ __forceinline__ void epi_store_f32(const CUtensorMap* map, const EpiCtx& c, int nb, const float (&x)[32]) {
+    using namespace ptx;
+    if (c.lane == 0) bulk_wait_read0();
+    __syncwarp();
+    epi::stage_f32(c.stg, c.lane, x);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (c.lane == 0) { tma_store_3d(map, c.stg, nb, c.t0, c.bb); bulk_commit(); }
+}
+__device__ __forceinline__ void epi_store_split(const CUtensorMap* mhi, const CUtensorMap* mlo, const EpiCtx& c, int nb, const float (&x)[32]) {
+    using namespace ptx;
+    if (c.lane == 0) bulk_wait_read0();
+    __syncwarp();
+    epi::stage_split(c.stg, c.stg + 2048u, c.lane, x);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (c.lane == 0) { tma_store_3d(mhi, c.stg, nb, c.t0, c.bb); tma_store_3d(mlo, c.stg + 2048u, nb, c.t0, c.bb); bulk_commit(); }
+}
+
 // ---- one 32-channel chunk: v (accumulator) [+ r (residual)] -> x -> staging -> TMA stores ----------------------------
 template <int BN, int MODE>
 __device__ __forceinline__ void epi_chunk(const TcParams& p, const EpiMaps& em, EpiCtx& c, const float (&cs)[32], int kc,
-                                          uint32_t (&v)[32], uint32_t (&vnext)[32], float (&r)[32], float (&rnext)[32]) {
+                                          uint32_t (&v)[32], uint32_t (&vnext)[32], float (&r)[32]) {
     using namespace ptx;
     using namespace epi;
     constexpr int NCH = BN / 32;
-    constexpr bool ROPE = MODE == EM_ROPE, LN = MODE == EM_LN;
+    constexpr bool ROPE = MODE == EM_ROPE, LN = MODE == EM_LN, RES = MODE == EM_RESID || MODE == EM_LN;
     const int c0 = kc * 32, nb = c.n0 + c0;
-    const int lane = c.lane;
+    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 128 && c.tile_it < 8;
+    long long tk0 = 0, tk1 = 0, tk2 = 0;
+    if (trace) tk0 = clock64();
     tmem_ld_wait();
-    if (kc + 1 < NCH && nb + 32 < p.N) {               // next chunk's accumulator and residual fly during this chunk's math
-        tmem_ld32(c.tacc + (uint32_t)(c0 + 32), vnext);
-        epi_load_resid<!ROPE>(p, c, rnext, nb + 32);
-    }
+    const bool has_next = kc + 1 < NCH && nb + 32 < p.N;
+    if (has_next) tmem_ld32(c.tacc + (uint32_t)(c0 + 32), vnext);     // next chunk's accumulator flies during this chunk's math
     if (nb >= p.N) return;                             // warp-uniform: tile wider than the remaining columns
+    if (trace) tk1 = clock64();
     float x[32];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -171,36 +199,42 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const EpiMaps& em, 
     } else {
         if constexpr (MODE == EM_SILU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
+            for (int j = 0; j < 32; ++j) x[j] = silu_fast(x[j]);
         }
         if constexpr (MODE == EM_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = gelu_f(x[j]);
         }
-        if (!c.plain) {
+        if (c.mask_only) {                             // (h * mask): the FFN hidden activation, cond features
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] *= c.m;
+        } else if (!c.plain) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.flags & EPI_GATE) g4 = colvec(c.gate, nb + 4 * q, p.N);
                 if (p.flags & EPI_FILM) { fg = colvec(c.film, nb + 4 * q, p.N); fb = colvec(c.film + p.film_H, nb + 4 * q, p.N); }
-                x[4 * q] = (fg.x * x[4 * q] + fb.x) * c.m * g4.x + r[4 * q];
-                x[4 * q + 1] = (fg.y * x[4 * q + 1] + fb.y) * c.m * g4.y + r[4 * q + 1];
-                x[4 * q + 2] = (fg.z * x[4 * q + 2] + fb.z) * c.m * g4.z + r[4 * q + 2];
-                x[4 * q + 3] = (fg.w * x[4 * q + 3] + fb.w) * c.m * g4.w + r[4 * q + 3];
+                g4.x *= c.m; g4.y *= c.m; g4.z *= c.m; g4.w *= c.m;
+                if constexpr (RES) {
+                    x[4 * q] = fmaf(fmaf(fg.x, x[4 * q], fb.x), g4.x, r[4 * q]);
+                    x[4 * q + 1] = fmaf(fmaf(fg.y, x[4 * q + 1], fb.y), g4.y, r[4 * q + 1]);
+                    x[4 * q + 2] = fmaf(fmaf(fg.z, x[4 * q + 2], fb.z), g4.z, r[4 * q + 2]);
+                    x[4 * q + 3] = fmaf(fmaf(fg.w, x[4 * q + 3], fb.w), g4.w, r[4 * q + 3]);
+                } else {
+                    x[4 * q] = fmaf(fg.x, x[4 * q], fb.x) * g4.x; x[4 * q + 1] = fmaf(fg.y, x[4 * q + 1], fb.y) * g4.y;
+                    x[4 * q + 2] = fmaf(fg.z, x[4 * q + 2], fb.z) * g4.z; x[4 * q + 3] = fmaf(fg.w, x[4 * q + 3], fb.w) * g4.w;
+                }
             }
         }
+        // the residual registers are dead now: the next chunk's residual row flies during the staging below
+        if (has_next) epi_load_resid<RES>(p, c, r, nb + 32);
     }
-    // results -> staging -> TMA.  The staging is rewritten only after the TMA unit has READ the previous chunk.
-    if (lane == 0) bulk_wait_read0();
-    __syncwarp();
-    if (p.has_f32) stage_f32(c.stg, lane, x);
-    if (p.has_split) stage_split(c.stg_hi, c.stg_lo, lane, x);
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-        if (p.has_f32) tma_store_3d(&em.o_f32, c.stg, nb, c.t0, c.bb);
-        if (p.has_split) { tma_store_3d(&em.o_hi, c.stg_hi, nb, c.t0, c.bb); tma_store_3d(&em.o_lo, c.stg_lo, nb, c.t0, c.bb); }
-        bulk_commit();
+    if (trace) tk2 = clock64();
+    if (p.has_f32) epi_store_f32(&em.o_f32, c, nb, x);
+    if (p.has_split) epi_store_split(&em.o_hi, &em.o_lo, c, nb, x);
+    if (trace) {
+        long long* d = p.dbg + ((long)(c.tile_it >> 1) * NCH + kc) * 8;
+        d[0] = tk0; d[1] = tk1; d[2] = tk2; d[3] = tk2; d[4] = clock64();
     }
     if constexpr (LN) {
         if (p.has_film2) {                             // the next block's FiLM·mask on the finished residual stream
@@ -208,15 +242,10 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const EpiMaps& em, 
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 fg = colvec(f2, nb + 4 * q, p.N), fb = colvec(f2 + p.film_H, nb + 4 * q, p.N);
-                x[4 * q] = (fg.x * x[4 * q] + fb.x) * c.m; x[4 * q + 1] = (fg.y * x[4 * q + 1] + fb.y) * c.m;
-                x[4 * q + 2] = (fg.z * x[4 * q + 2] + fb.z) * c.m; x[4 * q + 3] = (fg.w * x[4 * q + 3] + fb.w) * c.m;
+                x[4 * q] = (fg.x * x[4 * q] + fb.x) * c.mrow; x[4 * q + 1] = (fg.y * x[4 * q + 1] + fb.y) * c.mrow;
+                x[4 * q + 2] = (fg.z * x[4 * q + 2] + fb.z) * c.mrow; x[4 * q + 3] = (fg.w * x[4 * q + 3] + fb.w) * c.mrow;
             }
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-            stage_f32(c.stg, lane, x);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) { tma_store_3d(&em.o2_f32, c.stg, nb, c.t0, c.bb); bulk_commit(); }
+            epi_store_f32(&em.o2_f32, c, nb, x);
         }
         if (kc == 0) c.kshift = x[0];                  // shift by a value of the row itself: no cancellation in s2 - s1^2 / n
 #pragma unroll
@@ -246,36 +275,33 @@ __device__ __forceinline__ void epi_chunk_ln2(const TcParams& p, const EpiMaps& 
         u[4 * q + 2] = ((__uint_as_float(v[4 * q + 2]) - mean) * rstd * (1.f + c4.z) + s4.z) * mo;
         u[4 * q + 3] = ((__uint_as_float(v[4 * q + 3]) - mean) * rstd * (1.f + c4.w) + s4.w) * mo;
     }
-    if (c.lane == 0) bulk_wait_read0();
-    __syncwarp();
-    stage_split(c.stg_hi, c.stg_lo, c.lane, u);
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (c.lane == 0) { tma_store_3d(&em.u_hi, c.stg_hi, nb, c.t0, c.bb); tma_store_3d(&em.u_lo, c.stg_lo, nb, c.t0, c.bb); bulk_commit(); }
+    epi_store_split(&em.u_hi, &em.u_lo, c, nb, u);
 }
 
 // Drains one finished accumulator tile: this warp's 32 frames x BN channels.
 //   bb: batch row, t0: first frame of this warp's slab, n0: first channel of the tile, tacc: TMEM address of (lane quarter,
-//   accumulator column 0), stg: 32-bit shared address of this warp's 8 KB staging (1024-byte aligned).
+//   accumulator column 0), stg: 32-bit shared address of this warp's 4 KB staging (1024-byte aligned).
 // Everything with L2 latency that does not depend on the accumulator (mask, RoPE row, first residual chunk) is issued
 // BEFORE the wait on the accumulator barrier.
 template <int BN, int MODE, class WaitFn>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& em, int bb, int t0, int n0, uint32_t tacc,
-                                              uint32_t stg, int lane, WaitFn wait_accumulator) {
+                                              uint32_t stg, int lane, int tile_it, WaitFn wait_accumulator) {
     using namespace ptx;
     using namespace epi;
     constexpr int NCH = BN / 32;
-    constexpr bool ROPE = MODE == EM_ROPE, LN = MODE == EM_LN;
+    constexpr bool ROPE = MODE == EM_ROPE, LN = MODE == EM_LN, RES = MODE == EM_RESID || MODE == EM_LN;
     const int tcl = min(t0 + lane, p.T - 1);           // this thread's frame, clamped for the loads (stores are clipped by TMA)
     EpiCtx c;
     c.bb = bb; c.t0 = t0; c.n0 = n0; c.mb = bb % p.B; c.lane = lane;
-    c.tacc = tacc; c.stg = stg; c.stg_hi = stg + 4096u; c.stg_lo = stg + 6144u;
+    c.tacc = tacc; c.stg = stg;
+    c.tile_it = tile_it;
     c.plain = ROPE || (p.flags & (EPI_FILM | EPI_MASK | EPI_GATE | EPI_RESID)) == 0;
-    c.has_resid = !ROPE && (p.flags & EPI_RESID);
-    c.m = 1.f; c.film = nullptr; c.gate = nullptr; c.resid_row = nullptr;
+    c.mask_only = !ROPE && (p.flags & (EPI_FILM | EPI_MASK | EPI_GATE | EPI_RESID)) == EPI_MASK;
+    c.has_resid = RES && (p.flags & EPI_RESID);
+    c.m = 1.f; c.mrow = 1.f; c.film = nullptr; c.gate = nullptr; c.resid_row = nullptr;
     c.s1 = 0.f; c.s2 = 0.f; c.kshift = 0.f;
     float cs[32];                                      // RoPE: (cos, sin) x 16 of this frame
-    float ra[32], rb[32];                              // residual rows, read by their own thread (16 B x 8 of one 128-byte line)
+    float ra[32];                                      // residual row chunk, read by its own thread (16 B x 8 of one 128-byte line)
     if constexpr (ROPE) {
         const float4* q = reinterpret_cast<const float4*>(p.rope_cs + (long)tcl * 32);
 #pragma unroll
@@ -284,11 +310,12 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& 
             cs[4 * i] = c4.x; cs[4 * i + 1] = c4.y; cs[4 * i + 2] = c4.z; cs[4 * i + 3] = c4.w;
         }
     } else {
-        if (p.flags & EPI_MASK) c.m = __ldg(p.mask + (long)c.mb * p.T + tcl);
+        if (p.mask) c.mrow = __ldg(p.mask + (long)c.mb * p.T + tcl);
+        if (p.flags & EPI_MASK) c.m = c.mrow;
         c.film = p.film + (long)c.mb * p.film_bstride;
         c.gate = p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride;
         c.resid_row = p.resid + ((long)min(bb, p.resid_clamp) * p.T + tcl) * p.N;
-        epi_load_resid<true>(p, c, ra, n0);
+        epi_load_resid<RES>(p, c, ra, n0);
     }
 
     wait_accumulator();
@@ -297,8 +324,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& 
     tmem_ld32(tacc, va);
 #pragma unroll 1
     for (int kc = 0; kc < NCH; kc += 2) {
-        epi_chunk<BN, MODE>(p, em, c, cs, kc, va, vb, ra, rb);
-        epi_chunk<BN, MODE>(p, em, c, cs, kc + 1, vb, va, rb, ra);
+        epi_chunk<BN, MODE>(p, em, c, cs, kc, va, vb, ra);
+        epi_chunk<BN, MODE>(p, em, c, cs, kc + 1, vb, va, ra);
     }
 
     if constexpr (LN) {
@@ -308,7 +335,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& 
         const float dm = c.s1 * inv_n;
         const float mean = c.kshift + dm;
         const float rstd = rsqrtf(fmaxf(c.s2 * inv_n - dm * dm, 0.f) + 1e-5f);
-        const float mo = p.ln_mask_out ? c.m : 1.0f;
+        const float mo = p.ln_mask_out ? c.mrow : 1.0f;
         const float* sh = p.ln_shift + (long)min(bb, p.c_clamp) * p.ada_bstride;
         const float* sc = p.ln_scale + (long)min(bb, p.c_clamp) * p.ada_bstride;
         tmem_ld32(tacc, va);

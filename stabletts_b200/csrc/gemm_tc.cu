@@ -36,7 +36,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;             // bf16 elements = 128 bytes = one SW128 row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 256;            // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-7: epilogue (one per TMEM lane quarter)
+constexpr int NUM_THREADS = 384;            // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue (two groups of four)
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KB
 
 struct TcMaps {
@@ -85,7 +85,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ EpiM
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -162,24 +162,26 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ EpiM
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
-        // ================= epilogue (4 warps, one per TMEM lane quarter; thread = frame) =================
-        const int wq = warp & 3;                       // TMEM lane quarter this warp may access
+        // ================= epilogue (thread = frame) =================
+        // warps 4-7 drain accumulator stage 0 (tiles 0, 2, 4, ... of this CTA), warps 8-11 stage 1 (tiles 1, 3, ...)
+        const int wq = warp & 3, grp = (warp - 4) >> 2;
         const uint32_t stg = smem_u32(smem + C::STAGING_OFF + (warp - 4) * EPI_STAGE_BYTES);
         if (lane == 0) {
             prefetch_tmap(&em.o_f32); prefetch_tmap(&em.o_hi); prefetch_tmap(&em.o_lo);
         }
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int acc = grp;
+        int tile_it = grp; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, tile_it += 2) {
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
             const int bb = m_tile / p.m_tiles_per_b, t0 = (m_tile % p.m_tiles_per_b) * BLOCK_M + wq * 32;
             const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN);
             uint64_t* fb = &tmem_full[acc];
             const uint32_t ph = acc_phase;
-            epilogue_tile<BN, MODE>(p, em, bb, t0, n_tile * BN, tacc, stg, lane, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
+            epilogue_tile<BN, MODE>(p, em, bb, t0, n_tile * BN, tacc, stg, lane, tile_it, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            acc_phase ^= 1;
         }
         if (lane == 0) bulk_wait0();                   // the TMA unit has drained this warp's staging before the CTA exits
     }
@@ -290,6 +292,7 @@ cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t s) {
         case EM_ROPE: return launch_inst<BN, EM_ROPE>(maps, em, p, grid, s);
         case EM_SILU: return launch_inst<BN, EM_SILU>(maps, em, p, grid, s);
         case EM_GELU: return launch_inst<BN, EM_GELU>(maps, em, p, grid, s);
+        case EM_RESID: return launch_inst<BN, EM_RESID>(maps, em, p, grid, s);
         default:      return launch_inst<BN, EM_PLAIN>(maps, em, p, grid, s);
     }
 }

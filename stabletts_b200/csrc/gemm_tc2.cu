@@ -10,7 +10,7 @@
 //                                TMA loads complete_tx on the leader's barrier (cta_group::2 TMA form)
 //   empty[s]       each CTA      count 1: tcgen05.commit.cta_group::2 multicast from the leader's MMA thread
 //   tmem_full[a]   each CTA      count 1: multicast commit after a tile's last k-block
-//   tmem_empty[a]  leader only   count 8: 4 epilogue warps of each CTA (the peer arrives remotely, mapa)
+//   tmem_empty[a]  leader only   count 8: the 4 epilogue warps of group a in each CTA (the peer arrives remotely, mapa)
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "gemm_epilogue.cuh"
@@ -31,7 +31,7 @@ using namespace ptx;
 constexpr int BM = 128;                 // rows per CTA (pair tile: 256)
 constexpr int BK = 64;
 constexpr int UK = 16;
-constexpr int THREADS = 256;            // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-7: epilogue (one per TMEM lane quarter)
+constexpr int THREADS = 384;            // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue (two groups of four)
 constexpr int TILE_BYTES = 128 * BK * 2;            // 16 KB: one A plane tile (128 frames x 64 channels)
 
 // BN2 = pair tile width: 256 (each CTA stages 128 weight rows) or 128 (64 weight rows; twice as many, half as long
@@ -84,7 +84,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiM
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS); }   // 4 warps of group i x 2 CTAs
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc_2sm<TMEM_COLS>(tmem_slot);
@@ -158,26 +158,28 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiM
             }
         }
     } else if (warp >= 4) {
-        // ================= epilogue (both CTAs, own 128 rows; 4 warps, thread = frame) =================
-        const int wq = warp & 3;
+        // ================= epilogue (both CTAs, own 128 rows; thread = frame) =================
+        // warps 4-7 drain accumulator stage 0 (tiles 0, 2, 4, ... of this cluster), warps 8-11 stage 1 (tiles 1, 3, ...)
+        const int wq = warp & 3, grp = (warp - 4) >> 2;
         const uint32_t stg = smem_u32(smem + Cfg2<BN2>::STAGING_OFF + (warp - 4) * EPI_STAGE_BYTES);
         if (lane == 0) {
             prefetch_tmap(&em.o_f32); prefetch_tmap(&em.o_hi); prefetch_tmap(&em.o_lo);
             if (MODE == EM_LN) { prefetch_tmap(&em.u_hi); prefetch_tmap(&em.u_lo); prefetch_tmap(&em.o2_f32); }
         }
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+        const int acc = grp;
+        int tile_it = grp; uint32_t acc_phase = 0;
+        for (int tile = cluster_id + grp * num_clusters; tile < p.total_tiles; tile += 2 * num_clusters, tile_it += 2) {
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
             const int bb = m_tile / p.m_tiles_per_b;
             const int t0 = (m_tile % p.m_tiles_per_b) * (2 * BM) + (int)rank * BM + wq * 32;
             const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN2);
             uint64_t* fb = &tmem_full[acc];
             const uint32_t ph = acc_phase;
-            epilogue_tile<BN2, MODE>(p, em, bb, t0, n_tile * BN2, tacc, stg, lane, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
+            epilogue_tile<BN2, MODE>(p, em, bb, t0, n_tile * BN2, tacc, stg, lane, tile_it, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);      // the LEADER's barrier gates the next MMA
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            acc_phase ^= 1;
         }
         if (lane == 0) bulk_wait0();                   // the TMA unit has drained this warp's staging before the CTA exits
     }
@@ -191,8 +193,14 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiM
 }
 
 std::string g_err2;
+long long* g_epi_trace = nullptr;      // debug: [4 tiles][8 chunks][8] clock64 stamps of CTA 0 / warp 4 (STABLETTS_B200_EPI_TRACE=1)
 
 }  // namespace
+
+int gemm_tc2_read_trace(long long* host_out) {
+    if (!g_epi_trace) return 1;
+    return cudaMemcpy(host_out, g_epi_trace, 4 * 8 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+}
 
 const char* gemm_tc2_last_error() { return g_err2.c_str(); }
 
@@ -234,6 +242,7 @@ static cudaError_t launch_tc2_bn(const Maps2& maps, const EpiMaps& em, Params2& 
         case EM_LN:   return launch_tc2_inst<BN2, EM_LN>(maps, em, p, pairs, s);
         case EM_SILU: return launch_tc2_inst<BN2, EM_SILU>(maps, em, p, pairs, s);
         case EM_GELU: return launch_tc2_inst<BN2, EM_GELU>(maps, em, p, pairs, s);
+        case EM_RESID: return launch_tc2_inst<BN2, EM_RESID>(maps, em, p, pairs, s);
         default:      return launch_tc2_inst<BN2, EM_PLAIN>(maps, em, p, pairs, s);
     }
 }
@@ -259,6 +268,11 @@ cudaError_t launch_gemm_tc2(const GemmArgs& g, int num_sms, cudaStream_t s) {
     Params2 p;
     fill_tc_params(p, g);
     p.m_tiles_per_b = (g.T + 2 * BM - 1) / (2 * BM);
+    if (getenv("STABLETTS_B200_EPI_TRACE")) {
+        if (!g_epi_trace) cudaMalloc(&g_epi_trace, 4 * 8 * 8 * sizeof(long long));
+        cudaMemsetAsync(g_epi_trace, 0, 4 * 8 * 8 * sizeof(long long), s);
+        p.dbg = g_epi_trace;
+    }
     return bn2 == 128 ? launch_tc2_bn<128>(maps, em, p, g, pairs, s) : launch_tc2_bn<256>(maps, em, p, g, pairs, s);
 }
 
