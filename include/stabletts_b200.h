@@ -201,7 +201,7 @@ int st_test_attention(st_handle* h, const float* qkv, const float* mask, float* 
  * MMA warps per key block; this copies the last launch's [32 blocks][16 slots] table to the host. */
 int st_test_attention_trace(long long* host_out);
 /* Debug hook: with STABLETTS_B200_EPI_TRACE=1 the 2-CTA GEMM records clock64 stamps of one epilogue warp per 32-channel chunk
- * (chunk start, accumulator ready, math done, staging free, stores issued); copies [4 tiles][8 chunks][8] to the host. */
+ * (chunk start, accumulator ready, math done, staging free, stores issued); copies [4 tiles][16 chunk slots: 8 of pass 1, 8 of the LayerNorm pass][8] to the host. */
 int st_test_gemm_trace(long long* host_out);
 
 #ifdef __cplusplus

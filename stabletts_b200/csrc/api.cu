@@ -1230,11 +1230,14 @@ int st_bench_conv(st_handle* h, int B, int Cin, int Cout, int T, int k, int epi,
         if (launch_split(xf, xh, xl, (long)nx, s) != cudaSuccess || launch_split(wf, wh, wl, (long)nw, s) != cudaSuccess) { rc = fail(h, "split failed"); break; }
         GemmArgs g;
         g.BB = B; g.T = T; g.a_bmod = B; g.B = B; g.resid_clamp = B - 1; g.c_clamp = B - 1; g.mask = mask;
-        g.flags = epi == 1 ? (EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID) : (epi == 2 ? (EPI_BIAS | EPI_SILU | EPI_MASK) : EPI_BIAS);
+        g.flags = (epi == 1 || epi == 3) ? (EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID) : (epi == 2 ? (EPI_BIAS | EPI_SILU | EPI_MASK) : EPI_BIAS);
         g.gate = gate; g.gate_bstride = Cout; g.resid = of;
+        if (epi == 3) {                // O-style: fp32 residual stream out + fused LayerNorm/modulate -> split-bf16 U
+            g.ln = 1; g.ln_mask_out = 1; g.ln_shift = gate; g.ln_scale = gate; g.ada_bstride = Cout; g.u_hi = oh; g.u_lo = ol;
+        }
         GemmW w; w.f32 = wf; w.hi = wh; w.lo = wl; w.bias = bias; w.taps = k; w.N = Cout; w.K = Cin;
         Act a; a.C = Cin; a.f32 = xf; a.hi = tc ? xh : nullptr; a.lo = tc ? xl : nullptr;
-        Act o; o.C = Cout; o.f32 = epi == 1 ? of : nullptr; o.hi = oh; o.lo = ol;
+        Act o; o.C = Cout; o.f32 = (epi == 1 || epi == 3) ? of : nullptr; o.hi = epi == 3 ? nullptr : oh; o.lo = epi == 3 ? nullptr : ol;
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         for (int i = 0; i < 2 && !rc; ++i) rc = run_gemm(h, g, w, &a, nullptr, o, s);
         if (rc) break;

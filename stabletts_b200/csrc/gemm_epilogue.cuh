@@ -27,7 +27,7 @@ namespace st {
 
 enum : int { EM_PLAIN = 0, EM_SILU = 1, EM_GELU = 2, EM_ROPE = 3, EM_LN = 4, EM_RESID = 5 };   // EM_RESID: plain + residual rows
 
-struct EpiMaps { CUtensorMap o_f32, o_hi, o_lo, o2_f32, u_hi, u_lo; };     // TMA STORE maps: (N, T, BB), box 32 x 32 x 1
+struct EpiMaps { CUtensorMap o_f32, o_hi, o_lo, o2_f32, u_hi, u_lo, resid; };     // TMA store maps (+ the residual LOAD map): (N, T, BB), box 32 x 32 x 1
 
 struct TcParams {
     int n_src, Cs0, Cs1, taps, N, a_bmod, BB, T;
@@ -80,10 +80,23 @@ namespace epi {
 
 using namespace ptx;
 
-// warp-uniform 16-byte load of a per-column vector at column n (clamped so that a partial last chunk stays in bounds)
-__device__ __forceinline__ float4 colvec(const float* v, int n, int N) {
-    return __ldg(reinterpret_cast<const float4*>(v + min(n, N - 4)));
+// The L1 that is left beside 225 KB of shared memory is small: the per-column vectors (re-read by every chunk of every
+// tile) are kept in it (evict_last).  The residual / RoPE rows are read by their own thread as 8 x 16 B of one 128-byte
+// line and NEED the L1 allocation: with no_allocate every 16-byte piece became its own L2 request (O: 94 -> 131 us).
+__device__ __forceinline__ float4 ldg_keep(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
 }
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// warp-uniform 16-byte load of a per-column vector at column n (clamped so that a partial last chunk stays in bounds)
+__device__ __forceinline__ float4 colvec(const float* v, int n, int N) { return ldg_keep(v + min(n, N - 4)); }
 
 // this thread's 32 fp32 values -> row `lane` of the 32 x 128 B staging tile, 128-byte swizzle (chunk16 ^= row & 7)
 __device__ __forceinline__ void stage_f32(uint32_t stg, int lane, const float (&x)[32]) {
@@ -121,6 +134,9 @@ struct EpiCtx {
     bool plain, has_resid, mask_only;
     const float *film, *gate, *resid_row;
     float s1, s2, kshift;
+    // residual tiles through the TMA unit (kernels with a shallow main loop have the shared memory for it): two 4 KB
+    // buffers per warp, one mbarrier each; phase bits persist across tiles (rphase is owned by the kernel's tile loop)
+    uint32_t rbuf; uint64_t* rbar; uint32_t* rphase; int rb;
 };
 
 template <bool ON>
@@ -133,6 +149,31 @@ __device__ __forceinline__ void epi_load_resid(const TcParams& p, const EpiCtx& 
             r[4 * q] = v4.x; r[4 * q + 1] = v4.y; r[4 * q + 2] = v4.z; r[4 * q + 3] = v4.w;
         }
     }
+}
+
+// residual chunk kc of this warp's 32 frames: issue the TMA load (one lane), or wait for it and read this thread's row
+__device__ __forceinline__ void epi_resid_issue(const TcParams& p, const EpiMaps& em, const EpiCtx& c, int kc) {
+    using namespace ptx;
+    if (c.lane == 0) {
+        uint64_t* bar = c.rbar + (kc & 1);
+        mbar_expect_tx(bar, 4096);
+        tma_load_3d_addr(&em.resid, bar, c.rbuf + (uint32_t)(kc & 1) * 4096u, c.n0 + kc * 32, c.t0, c.rb);
+    }
+}
+__device__ __forceinline__ void epi_resid_take(EpiCtx& c, int kc, float (&r)[32]) {
+    using namespace ptx;
+    const int b = kc & 1;
+    mbar_wait(c.rbar + b, (*c.rphase >> b) & 1u);
+    *c.rphase ^= 1u << b;
+    const uint32_t row = c.rbuf + (uint32_t)b * 4096u + (uint32_t)c.lane * 128u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float4 v4;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v4.x), "=f"(v4.y), "=f"(v4.z), "=f"(v4.w)
+                     : "r"(row + (uint32_t)((q ^ (c.lane & 7)) << 4)));
+        r[4 * q] = v4.x; r[4 * q + 1] = v4.y; r[4 * q + 2] = v4.z; r[4 * q + 3] = v4.w;
+    }
+    __syncwarp();                                      // every lane has read the buffer: it may be refilled
 }
 
 // this thread's 32 values -> the warp's 4 KB staging -> TMA store(s); the staging is rewritten only after the TMA unit has
@@ -157,7 +198,7 @@ __device__ __forceinline__ void epi_store_split(const CUtensorMap* mhi, const CU
 }
 
 // ---- one 32-channel chunk: v (accumulator) [+ r (residual)] -> x -> staging -> TMA stores ----------------------------
-template <int BN, int MODE>
+template <int BN, int MODE, bool TRES>
 __device__ __forceinline__ void epi_chunk(const TcParams& p, const EpiMaps& em, EpiCtx& c, const float (&cs)[32], int kc,
                                           uint32_t (&v)[32], uint32_t (&vnext)[32], float (&r)[32]) {
     using namespace ptx;
@@ -168,18 +209,33 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const EpiMaps& em, 
     const bool trace = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 128 && c.tile_it < 8;
     long long tk0 = 0, tk1 = 0, tk2 = 0;
     if (trace) tk0 = clock64();
+    // per-column vectors are fetched in BATCHES of eight independent 16-byte loads (a flag test inside the unrolled
+    // element loop made every load wait for the previous one's use: 8 serialised L1 / L2 latencies per vector and chunk);
+    // the bias batch does not depend on the accumulator and is issued before the wait for it
+    float4 bq[8];
+    if (nb < p.N && (p.flags & EPI_BIAS)) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) bq[q] = colvec(p.bias, nb + 4 * q, p.N);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) bq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     tmem_ld_wait();
     const bool has_next = kc + 1 < NCH && nb + 32 < p.N;
     if (has_next) tmem_ld32(c.tacc + (uint32_t)(c0 + 32), vnext);     // next chunk's accumulator flies during this chunk's math
     if (nb >= p.N) return;                             // warp-uniform: tile wider than the remaining columns
+    if constexpr (RES && TRES) {                       // this chunk's residual tile has landed in shared memory (TMA)
+        if (c.has_resid) {
+            epi_resid_take(c, kc, r);
+            if (kc + 2 < NCH && nb + 64 < p.N) epi_resid_issue(p, em, c, kc + 2);
+        }
+    }
     if (trace) tk1 = clock64();
     float x[32];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.flags & EPI_BIAS) b4 = colvec(p.bias, nb + 4 * q, p.N);
-        x[4 * q] = __uint_as_float(v[4 * q]) + b4.x; x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b4.y;
-        x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b4.z; x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b4.w;
+        x[4 * q] = __uint_as_float(v[4 * q]) + bq[q].x; x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bq[q].y;
+        x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bq[q].z; x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bq[q].w;
     }
     if constexpr (ROPE) {
         // partial RoPE on the first 32 dims of every 64-wide head of q and k (columns [0, 2H)): pairs (j, j + 16),
@@ -209,32 +265,45 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const EpiMaps& em, 
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] *= c.m;
         } else if (!c.plain) {
+            if (p.flags & EPI_FILM) {                  // x = gamma * x + beta
+                float4 fg[8], fb[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { fg[q] = colvec(c.film, nb + 4 * q, p.N); fb[q] = colvec(c.film + p.film_H, nb + 4 * q, p.N); }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    x[4 * q] = fmaf(fg[q].x, x[4 * q], fb[q].x); x[4 * q + 1] = fmaf(fg[q].y, x[4 * q + 1], fb[q].y);
+                    x[4 * q + 2] = fmaf(fg[q].z, x[4 * q + 2], fb[q].z); x[4 * q + 3] = fmaf(fg[q].w, x[4 * q + 3], fb[q].w);
+                }
+            }
+            float4 g4[8];                              // gate * mask
+            if (p.flags & EPI_GATE) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) g4[q] = colvec(c.gate, nb + 4 * q, p.N);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { g4[q].x *= c.m; g4[q].y *= c.m; g4[q].z *= c.m; g4[q].w *= c.m; }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) g4[q] = make_float4(c.m, c.m, c.m, c.m);
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), fg = g4, fb = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.flags & EPI_GATE) g4 = colvec(c.gate, nb + 4 * q, p.N);
-                if (p.flags & EPI_FILM) { fg = colvec(c.film, nb + 4 * q, p.N); fb = colvec(c.film + p.film_H, nb + 4 * q, p.N); }
-                g4.x *= c.m; g4.y *= c.m; g4.z *= c.m; g4.w *= c.m;
                 if constexpr (RES) {
-                    x[4 * q] = fmaf(fmaf(fg.x, x[4 * q], fb.x), g4.x, r[4 * q]);
-                    x[4 * q + 1] = fmaf(fmaf(fg.y, x[4 * q + 1], fb.y), g4.y, r[4 * q + 1]);
-                    x[4 * q + 2] = fmaf(fmaf(fg.z, x[4 * q + 2], fb.z), g4.z, r[4 * q + 2]);
-                    x[4 * q + 3] = fmaf(fmaf(fg.w, x[4 * q + 3], fb.w), g4.w, r[4 * q + 3]);
+                    x[4 * q] = fmaf(x[4 * q], g4[q].x, r[4 * q]); x[4 * q + 1] = fmaf(x[4 * q + 1], g4[q].y, r[4 * q + 1]);
+                    x[4 * q + 2] = fmaf(x[4 * q + 2], g4[q].z, r[4 * q + 2]); x[4 * q + 3] = fmaf(x[4 * q + 3], g4[q].w, r[4 * q + 3]);
                 } else {
-                    x[4 * q] = fmaf(fg.x, x[4 * q], fb.x) * g4.x; x[4 * q + 1] = fmaf(fg.y, x[4 * q + 1], fb.y) * g4.y;
-                    x[4 * q + 2] = fmaf(fg.z, x[4 * q + 2], fb.z) * g4.z; x[4 * q + 3] = fmaf(fg.w, x[4 * q + 3], fb.w) * g4.w;
+                    x[4 * q] *= g4[q].x; x[4 * q + 1] *= g4[q].y; x[4 * q + 2] *= g4[q].z; x[4 * q + 3] *= g4[q].w;
                 }
             }
         }
         // the residual registers are dead now: the next chunk's residual row flies during the staging below
-        if (has_next) epi_load_resid<RES>(p, c, r, nb + 32);
+        if constexpr (!TRES) { if (has_next) epi_load_resid<RES>(p, c, r, nb + 32); }
     }
     if (trace) tk2 = clock64();
     if (p.has_f32) epi_store_f32(&em.o_f32, c, nb, x);
     if (p.has_split) epi_store_split(&em.o_hi, &em.o_lo, c, nb, x);
     if (trace) {
-        long long* d = p.dbg + ((long)(c.tile_it >> 1) * NCH + kc) * 8;
-        d[0] = tk0; d[1] = tk1; d[2] = tk2; d[3] = tk2; d[4] = clock64();
+        long long* d = p.dbg + ((long)(c.tile_it >> 1) * 2 * NCH + kc) * 8;
+        d[0] = tk0; d[1] = tk1; d[2] = tk2; d[3] = 0; d[4] = clock64();
     }
     if constexpr (LN) {
         if (p.has_film2) {                             // the next block's FiLM·mask on the finished residual stream
@@ -248,11 +317,17 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const EpiMaps& em, 
             epi_store_f32(&em.o2_f32, c, nb, x);
         }
         if (kc == 0) c.kshift = x[0];                  // shift by a value of the row itself: no cancellation in s2 - s1^2 / n
+        float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;          // two independent chains per sum
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = x[j] - c.kshift; c.s1 += d; c.s2 = fmaf(d, d, c.s2); }
+        for (int j = 0; j < 32; j += 2) {
+            const float d0 = x[j] - c.kshift, d1 = x[j + 1] - c.kshift;
+            a1 += d0; a2 = fmaf(d0, d0, a2); b1 += d1; b2 = fmaf(d1, d1, b2);
+        }
+        c.s1 += a1 + b1; c.s2 += a2 + b2;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(x[j]);
         tmem_st32(c.tacc + (uint32_t)c0, v);           // x back into the accumulator's own columns for pass 2
+        if (trace) p.dbg[((long)(c.tile_it >> 1) * 2 * NCH + kc) * 8 + 3] = clock64();
     }
 }
 
@@ -264,8 +339,12 @@ __device__ __forceinline__ void epi_chunk_ln2(const TcParams& p, const EpiMaps& 
     using namespace epi;
     constexpr int NCH = BN / 32;
     const int c0 = kc * 32, nb = c.n0 + c0;
+    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 128 && c.tile_it < 8;
+    long long tk0 = 0, tk1 = 0, tk2 = 0;
+    if (trace) tk0 = clock64();
     tmem_ld_wait();
     if (kc + 1 < NCH) tmem_ld32(c.tacc + (uint32_t)(c0 + 32), vnext);
+    if (trace) tk1 = clock64();
     float u[32];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -275,7 +354,12 @@ __device__ __forceinline__ void epi_chunk_ln2(const TcParams& p, const EpiMaps& 
         u[4 * q + 2] = ((__uint_as_float(v[4 * q + 2]) - mean) * rstd * (1.f + c4.z) + s4.z) * mo;
         u[4 * q + 3] = ((__uint_as_float(v[4 * q + 3]) - mean) * rstd * (1.f + c4.w) + s4.w) * mo;
     }
+    if (trace) tk2 = clock64();
     epi_store_split(&em.u_hi, &em.u_lo, c, nb, u);
+    if (trace) {
+        long long* d = p.dbg + ((long)(c.tile_it >> 1) * 2 * NCH + NCH + kc) * 8;
+        d[0] = tk0; d[1] = tk1; d[2] = tk2; d[3] = 0; d[4] = clock64();
+    }
 }
 
 // Drains one finished accumulator tile: this warp's 32 frames x BN channels.
@@ -283,9 +367,11 @@ __device__ __forceinline__ void epi_chunk_ln2(const TcParams& p, const EpiMaps& 
 //   accumulator column 0), stg: 32-bit shared address of this warp's 4 KB staging (1024-byte aligned).
 // Everything with L2 latency that does not depend on the accumulator (mask, RoPE row, first residual chunk) is issued
 // BEFORE the wait on the accumulator barrier.
-template <int BN, int MODE, class WaitFn>
+struct ResidPipe { uint32_t buf = 0; uint64_t* bar = nullptr; uint32_t phase = 0; };     // per warp, lives across tiles
+
+template <int BN, int MODE, bool TRES, class WaitFn>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& em, int bb, int t0, int n0, uint32_t tacc,
-                                              uint32_t stg, int lane, int tile_it, WaitFn wait_accumulator) {
+                                              uint32_t stg, int lane, int tile_it, ResidPipe& rp, WaitFn wait_accumulator) {
     using namespace ptx;
     using namespace epi;
     constexpr int NCH = BN / 32;
@@ -300,6 +386,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& 
     c.has_resid = RES && (p.flags & EPI_RESID);
     c.m = 1.f; c.mrow = 1.f; c.film = nullptr; c.gate = nullptr; c.resid_row = nullptr;
     c.s1 = 0.f; c.s2 = 0.f; c.kshift = 0.f;
+    c.rbuf = rp.buf; c.rbar = rp.bar; c.rphase = &rp.phase; c.rb = min(bb, p.resid_clamp);
     float cs[32];                                      // RoPE: (cos, sin) x 16 of this frame
     float ra[32];                                      // residual row chunk, read by its own thread (16 B x 8 of one 128-byte line)
     if constexpr (ROPE) {
@@ -315,17 +402,28 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& 
         c.film = p.film + (long)c.mb * p.film_bstride;
         c.gate = p.gate + (long)min(bb, p.c_clamp) * p.gate_bstride;
         c.resid_row = p.resid + ((long)min(bb, p.resid_clamp) * p.T + tcl) * p.N;
-        epi_load_resid<RES>(p, c, ra, n0);
+        if constexpr (RES && TRES) {   // residual tiles of chunks 0 and 1: TMA -> this warp's two buffers, before the MMAs finish
+            if (c.has_resid) {
+                epi_resid_issue(p, em, c, 0);
+                if (NCH > 1 && n0 + 32 < p.N) epi_resid_issue(p, em, c, 1);
+            }
+        } else {
+            epi_load_resid<RES>(p, c, ra, n0);
+        }
     }
 
+    const bool trace_tile = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 128 && tile_it < 8;
+    long long tt0 = 0, tt1 = 0;
+    if (trace_tile) tt0 = clock64();
     wait_accumulator();
+    if (trace_tile) tt1 = clock64();
 
     uint32_t va[32], vb[32];
     tmem_ld32(tacc, va);
 #pragma unroll 1
     for (int kc = 0; kc < NCH; kc += 2) {
-        epi_chunk<BN, MODE>(p, em, c, cs, kc, va, vb, ra);
-        epi_chunk<BN, MODE>(p, em, c, cs, kc + 1, vb, va, ra);
+        epi_chunk<BN, MODE, TRES>(p, em, c, cs, kc, va, vb, ra);
+        epi_chunk<BN, MODE, TRES>(p, em, c, cs, kc + 1, vb, va, ra);
     }
 
     if constexpr (LN) {
@@ -344,6 +442,10 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& 
             epi_chunk_ln2<BN>(p, em, c, mean, rstd, mo, sh, sc, kc, va, vb);
             epi_chunk_ln2<BN>(p, em, c, mean, rstd, mo, sh, sc, kc + 1, vb, va);
         }
+    }
+    if (trace_tile) {
+        long long* d = p.dbg + ((long)(tile_it >> 1) * 2 * NCH) * 8;
+        d[5] = tt0; d[6] = tt1; d[7] = clock64();
     }
 }
 

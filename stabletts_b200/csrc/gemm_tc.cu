@@ -170,6 +170,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ EpiM
             prefetch_tmap(&em.o_f32); prefetch_tmap(&em.o_hi); prefetch_tmap(&em.o_lo);
         }
         const int acc = grp;
+        ResidPipe rp;                                  // unused here: residual rows are read by their own threads
         int tile_it = grp; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, tile_it += 2) {
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
@@ -177,7 +178,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ EpiM
             const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN);
             uint64_t* fb = &tmem_full[acc];
             const uint32_t ph = acc_phase;
-            epilogue_tile<BN, MODE>(p, em, bb, t0, n_tile * BN, tacc, stg, lane, tile_it, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
+            epilogue_tile<BN, MODE, false>(p, em, bb, t0, n_tile * BN, tacc, stg, lane, tile_it, rp, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -329,6 +330,11 @@ bool build_epi_maps(const GemmArgs& g, EpiMaps* em) {
     if (g.film2) { ok = ok && g.out2_f32 && tmap_encode_store(g.out2_f32, true, N, T, BB, &em->o2_f32); }
     if (g.ln) ok = ok && g.u_hi && g.u_lo && tmap_encode_store(g.u_hi, false, N, T, BB, &em->u_hi) && tmap_encode_store(g.u_lo, false, N, T, BB, &em->u_lo);
     if (!ok || !any) return false;
+    em->resid = *any;
+    if (g.flags & EPI_RESID) {         // residual LOAD map (rows beyond T read as zero; used by the shallow-main-loop kernels)
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!get_map(g.resid, 3, N, T, (uint64_t)g.resid_clamp + 1, 32, 32, &em->resid, 1)) return false;
+    }
     if (!g.out_f32) em->o_f32 = *any;
     if (!g.out_hi) { em->o_hi = *any; em->o_lo = *any; }
     if (!g.film2) em->o2_f32 = *any;

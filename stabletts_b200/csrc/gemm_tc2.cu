@@ -16,6 +16,7 @@
 #include "gemm_epilogue.cuh"
 #include <string>
 #include <cstdlib>
+#include <cstring>
 
 namespace st {
 
@@ -37,13 +38,18 @@ constexpr int TILE_BYTES = 128 * BK * 2;            // 16 KB: one A plane tile (
 // BN2 = pair tile width: 256 (each CTA stages 128 weight rows) or 128 (64 weight rows; twice as many, half as long
 // tiles — chosen when that shortens the partial last wave, e.g. N = 256 outputs at cfg1: 250 tiles = 3.4 waves of 74
 // CTA pairs -> 500 half tiles = 6.8 half waves)
-template <int BN2> struct Cfg2 {
+// SHALLOW = 1: two main-loop stages instead of 3 / 4 — for GEMMs whose whole K fits a few k-blocks (O: 4, in_proj: 2) —
+// which leaves 64 KB for per-warp residual tiles brought in by the TMA unit (2 x 4 KB per epilogue warp).  A thread reading
+// its own residual row (8 x 16 B of one line) costs ~3000 cycles per chunk when nothing hides it (profiles/r2i_trace.log);
+// the long k-tap convs hide it behind their main loop and keep the deep pipeline.
+template <int BN2, int SHALLOW = 0> struct Cfg2 {
     static constexpr int B_TILE_BYTES = (BN2 / 2) * BK * 2;                  // B-half plane tile
     static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;    // A_hi, A_lo, Bh_hi, Bh_lo: 64 / 48 KB
-    static constexpr int STAGES = BN2 == 256 ? 3 : 4;
+    static constexpr int STAGES = SHALLOW ? 2 : (BN2 == 256 ? 3 : 4);
     static constexpr int TMEM_COLS = 2 * BN2;                                // two accumulator stages
     static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;                 // 1024-aligned: swizzled TMA-store tiles
-    static constexpr int BAR_OFF = STAGING_OFF + EPI_WARPS * EPI_STAGE_BYTES;
+    static constexpr int RESID_OFF = STAGING_OFF + EPI_WARPS * EPI_STAGE_BYTES;          // SHALLOW: 8 warps x 2 x 4 KB
+    static constexpr int BAR_OFF = RESID_OFF + (SHALLOW ? EPI_WARPS * 2 * 4096 : 0);
     static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
 };
 
@@ -54,18 +60,20 @@ typedef TcParams Params2;
 // One kernel instance per (tile width, epilogue mode): a combined kernel that switched over the modes at run time made
 // ptxas keep every mode's register arrays in one allocation (2 KB of spills); separate instances also keep the
 // instruction footprint of a launch small.
-template <int BN2, int MODE>
+template <int BN2, int MODE, int SHALLOW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiMaps em, const Params2 p) {
-    constexpr int B_TILE_BYTES = Cfg2<BN2>::B_TILE_BYTES, STAGE_BYTES = Cfg2<BN2>::STAGE_BYTES, STAGES = Cfg2<BN2>::STAGES;
-    constexpr int TMEM_COLS = Cfg2<BN2>::TMEM_COLS;
+    using CF = Cfg2<BN2, SHALLOW>;
+    constexpr int B_TILE_BYTES = CF::B_TILE_BYTES, STAGE_BYTES = CF::STAGE_BYTES, STAGES = CF::STAGES;
+    constexpr int TMEM_COLS = CF::TMEM_COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg2<BN2>::BAR_OFF);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + CF::BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* resid_bar = tmem_empty + 2;              // SHALLOW: [8 warps][2 buffers]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 2 * EPI_WARPS);
 
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -85,6 +93,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiM
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS); }   // 4 warps of group i x 2 CTAs
+        if (SHALLOW) for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&resid_bar[i], 1);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc_2sm<TMEM_COLS>(tmem_slot);
@@ -161,11 +170,14 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiM
         // ================= epilogue (both CTAs, own 128 rows; thread = frame) =================
         // warps 4-7 drain accumulator stage 0 (tiles 0, 2, 4, ... of this cluster), warps 8-11 stage 1 (tiles 1, 3, ...)
         const int wq = warp & 3, grp = (warp - 4) >> 2;
-        const uint32_t stg = smem_u32(smem + Cfg2<BN2>::STAGING_OFF + (warp - 4) * EPI_STAGE_BYTES);
+        const uint32_t stg = smem_u32(smem + CF::STAGING_OFF + (warp - 4) * EPI_STAGE_BYTES);
         if (lane == 0) {
             prefetch_tmap(&em.o_f32); prefetch_tmap(&em.o_hi); prefetch_tmap(&em.o_lo);
             if (MODE == EM_LN) { prefetch_tmap(&em.u_hi); prefetch_tmap(&em.u_lo); prefetch_tmap(&em.o2_f32); }
+            if (SHALLOW) prefetch_tmap(&em.resid);
         }
+        ResidPipe rp;
+        if (SHALLOW) { rp.buf = smem_u32(smem + CF::RESID_OFF + (warp - 4) * 2 * 4096); rp.bar = resid_bar + 2 * (warp - 4); }
         const int acc = grp;
         int tile_it = grp; uint32_t acc_phase = 0;
         for (int tile = cluster_id + grp * num_clusters; tile < p.total_tiles; tile += 2 * num_clusters, tile_it += 2) {
@@ -175,7 +187,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiM
             const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN2);
             uint64_t* fb = &tmem_full[acc];
             const uint32_t ph = acc_phase;
-            epilogue_tile<BN2, MODE>(p, em, bb, t0, n_tile * BN2, tacc, stg, lane, tile_it, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
+            epilogue_tile<BN2, MODE, SHALLOW != 0>(p, em, bb, t0, n_tile * BN2, tacc, stg, lane, tile_it, rp, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);      // the LEADER's barrier gates the next MMA
@@ -193,13 +205,13 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiM
 }
 
 std::string g_err2;
-long long* g_epi_trace = nullptr;      // debug: [4 tiles][8 chunks][8] clock64 stamps of CTA 0 / warp 4 (STABLETTS_B200_EPI_TRACE=1)
+long long* g_epi_trace = nullptr;      // debug: [4 tiles][8 pass-1 + 8 pass-2 chunks][8] clock64 stamps of CTA 0 / warp 4 (STABLETTS_B200_EPI_TRACE=1)
 
 }  // namespace
 
 int gemm_tc2_read_trace(long long* host_out) {
     if (!g_epi_trace) return 1;
-    return cudaMemcpy(host_out, g_epi_trace, 4 * 8 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+    return cudaMemcpy(host_out, g_epi_trace, 4 * 16 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
 }
 
 const char* gemm_tc2_last_error() { return g_err2.c_str(); }
@@ -224,26 +236,35 @@ static int pick_bn2(const GemmArgs& g, int pairs) {
     return w128 < 0.97 * w256 ? 128 : 256;
 }
 
-template <int BN2, int MODE>
+template <int BN2, int MODE, int SHALLOW>
 static cudaError_t launch_tc2_inst(const Maps2& maps, const EpiMaps& em, const Params2& p, int pairs, cudaStream_t s) {
     static std::atomic<uint64_t> attr_done{0};      // one bit per device
-    cudaError_t e = ensure_dyn_smem(gemm_tc2_kernel<BN2, MODE>, Cfg2<BN2>::SMEM_BYTES, attr_done);
+    cudaError_t e = ensure_dyn_smem(gemm_tc2_kernel<BN2, MODE, SHALLOW>, Cfg2<BN2, SHALLOW>::SMEM_BYTES, attr_done);
     if (e != cudaSuccess) { g_err2 = "cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc2_kernel"; return e; }
     const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
-    return launch_k(gemm_tc2_kernel<BN2, MODE>, dim3(2 * clusters), dim3(THREADS), (size_t)Cfg2<BN2>::SMEM_BYTES, s, maps, em, p);
+    return launch_k(gemm_tc2_kernel<BN2, MODE, SHALLOW>, dim3(2 * clusters), dim3(THREADS), (size_t)Cfg2<BN2, SHALLOW>::SMEM_BYTES, s,
+                    maps, em, p);
+}
+
+// residual GEMMs whose K is a few k-blocks (O, in_proj) run the shallow-pipeline instance with TMA-loaded residual tiles
+static bool use_shallow(const GemmArgs& g) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("STABLETTS_B200_SHALLOW"); env = (e && !strcmp(e, "0")) ? 0 : 1; }
+    return env && (g.flags & EPI_RESID) && g.resid && (long)g.Ktot * g.taps <= 512;
 }
 
 template <int BN2>
 static cudaError_t launch_tc2_bn(const Maps2& maps, const EpiMaps& em, Params2& p, const GemmArgs& g, int pairs, cudaStream_t s) {
     p.n_tiles = (g.N + BN2 - 1) / BN2;
     p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
+    const bool sh = use_shallow(g);
     switch (p.mode) {
-        case EM_ROPE: return launch_tc2_inst<BN2, EM_ROPE>(maps, em, p, pairs, s);
-        case EM_LN:   return launch_tc2_inst<BN2, EM_LN>(maps, em, p, pairs, s);
-        case EM_SILU: return launch_tc2_inst<BN2, EM_SILU>(maps, em, p, pairs, s);
-        case EM_GELU: return launch_tc2_inst<BN2, EM_GELU>(maps, em, p, pairs, s);
-        case EM_RESID: return launch_tc2_inst<BN2, EM_RESID>(maps, em, p, pairs, s);
-        default:      return launch_tc2_inst<BN2, EM_PLAIN>(maps, em, p, pairs, s);
+        case EM_ROPE: return launch_tc2_inst<BN2, EM_ROPE, 0>(maps, em, p, pairs, s);
+        case EM_LN:   return sh ? launch_tc2_inst<BN2, EM_LN, 1>(maps, em, p, pairs, s) : launch_tc2_inst<BN2, EM_LN, 0>(maps, em, p, pairs, s);
+        case EM_SILU: return launch_tc2_inst<BN2, EM_SILU, 0>(maps, em, p, pairs, s);
+        case EM_GELU: return launch_tc2_inst<BN2, EM_GELU, 0>(maps, em, p, pairs, s);
+        case EM_RESID: return sh ? launch_tc2_inst<BN2, EM_RESID, 1>(maps, em, p, pairs, s) : launch_tc2_inst<BN2, EM_RESID, 0>(maps, em, p, pairs, s);
+        default:      return launch_tc2_inst<BN2, EM_PLAIN, 0>(maps, em, p, pairs, s);
     }
 }
 
@@ -269,8 +290,8 @@ cudaError_t launch_gemm_tc2(const GemmArgs& g, int num_sms, cudaStream_t s) {
     fill_tc_params(p, g);
     p.m_tiles_per_b = (g.T + 2 * BM - 1) / (2 * BM);
     if (getenv("STABLETTS_B200_EPI_TRACE")) {
-        if (!g_epi_trace) cudaMalloc(&g_epi_trace, 4 * 8 * 8 * sizeof(long long));
-        cudaMemsetAsync(g_epi_trace, 0, 4 * 8 * 8 * sizeof(long long), s);
+        if (!g_epi_trace) cudaMalloc(&g_epi_trace, 4 * 16 * 8 * sizeof(long long));
+        cudaMemsetAsync(g_epi_trace, 0, 4 * 16 * 8 * sizeof(long long), s);
         p.dbg = g_epi_trace;
     }
     return bn2 == 128 ? launch_tc2_bn<128>(maps, em, p, g, pairs, s) : launch_tc2_bn<256>(maps, em, p, g, pairs, s);
