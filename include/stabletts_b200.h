@@ -74,6 +74,15 @@ int st_finalize_weights(st_handle* h, void* stream);
 /* Selects the GEMM engine (see enum above).  Default ST_ENGINE_TCGEN05. */
 int st_set_engine(st_handle* h, int engine);
 
+/* Precision of the tensor-core engine's operands.  ST_PRECISION_DEFAULT: every contraction runs split-bf16 x 3 (hi / lo
+ * planes of both operands, three MMA passes, ~16 mantissa bits; measured 1e-5 against the reference).  ST_PRECISION_FFN_FP16X2
+ * (opt-in): the two k = 3 FFN convs of every DiT block (models/diffusion_transformer.py:20-30, 48-55 % of the FLOPs) take their
+ * activations as ONE fp16 plane against fp16 hi / lo weights — two MMA passes instead of three and half the hidden-activation
+ * traffic — at about 2e-4 per estimator call instead of 1e-5 (still inside the 1e-3 bar; DESIGN.md has the measured table).
+ * Applies to problems large enough for the 2-CTA kernel; smaller ones keep three passes. */
+enum { ST_PRECISION_DEFAULT = 0, ST_PRECISION_FFN_FP16X2 = 1 };
+int st_set_precision(st_handle* h, int precision);
+
 /* Workspace: bytes needed for a (B, T) problem (cfg != 0 doubles the estimator batch), and
  * attachment of a caller-owned device buffer of at least that size (e.g. a torch uint8 tensor).
  * The buffer must stay alive until the next attach or st_destroy. */

@@ -9,6 +9,7 @@ _LIB = None
 
 ST_EULER, ST_MIDPOINT, ST_RK4, ST_DOPRI5_FIXED = 0, 1, 2, 3
 ST_ENGINE_TCGEN05, ST_ENGINE_SIMT = 0, 1
+ST_PRECISION_DEFAULT, ST_PRECISION_FFN_FP16X2 = 0, 1
 ST_ADAPT_DOPRI5, ST_ADAPT_BOSH3, ST_ADAPT_FEHLBERG2, ST_ADAPT_HEUN = 0, 1, 2, 3
 ST_PROF_NAMES = ("gemm_other", "attention", "ln", "gemm_qkv", "gemm_o", "gemm_conv1", "gemm_conv2", "gemm_lsc", "gemm_cond")
 ST_PROF_NCAT = len(ST_PROF_NAMES)
@@ -16,7 +17,7 @@ ST_PROF_NCAT = len(ST_PROF_NAMES)
 # every symbol include/stabletts_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "st_create", "st_destroy", "st_last_error", "st_version", "st_load_weight", "st_finalize_weights",
-    "st_set_engine", "st_workspace_bytes", "st_attach_workspace", "st_estimator_forward", "st_cfm_loss", "st_solve",
+    "st_set_engine", "st_set_precision", "st_workspace_bytes", "st_attach_workspace", "st_estimator_forward", "st_cfm_loss", "st_solve",
     "st_solve_host", "st_solve_adaptive", "st_solve_adaptive_ex", "st_align_lengths", "st_align_expand", "st_create_text_encoder", "st_text_encoder_forward", "st_create_vocos", "st_vocos_forward", "st_launch_count", "st_profile_begin", "st_profile_end", "st_test_gemm", "st_test_conv", "st_test_attention", "st_test_attention_trace", "st_test_gemm_trace", "st_bench_conv",
 ]
 
@@ -68,6 +69,7 @@ def load_library() -> C.CDLL:
     lib.st_load_weight.argtypes = [vp, C.c_char_p, f32p, i64, vp]
     lib.st_finalize_weights.argtypes = [vp, vp]
     lib.st_set_engine.argtypes = [vp, i32]
+    lib.st_set_precision.argtypes = [vp, i32]
     lib.st_workspace_bytes.argtypes = [vp, i32, i32, i32]
     lib.st_workspace_bytes.restype = C.c_size_t
     lib.st_attach_workspace.argtypes = [vp, vp, C.c_size_t]

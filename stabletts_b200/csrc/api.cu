@@ -190,6 +190,14 @@ int ensure_ws(st_handle* h, Workspace& w, int B, int T, int cfg) {
 
 }  // namespace
 
+// fp16 hi / lo planes of a packed weight (the FFN convs; used by ST_PRECISION_FFN_FP16X2)
+static int pack_f16_planes(st_handle* h, GemmW* w, cudaStream_t s) {
+    const size_t n = (size_t)w->taps * w->N * w->K;
+    if (dev_alloc(h, &w->h_hi, n) || dev_alloc(h, &w->h_lo, n)) return 1;
+    ST_CUDA(launch_split_f16(w->f32, w->h_hi, w->h_lo, (long)n, s));
+    return 0;
+}
+
 // ----- GEMM dispatch -------------------------------------------------------------------------------
 int st::run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const Act* a1, const Act& out, cudaStream_t s,
                  int prof_cat) {
@@ -204,6 +212,10 @@ int st::run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const
     }
     if (ktot != w.K) return fail(h, "internal: GEMM K mismatch");
     g.W_f32 = w.f32; g.W_hi = w.hi; g.W_lo = w.lo; g.bias = w.bias;
+    if (g.prec) {
+        if (!w.h_hi) return fail(h, "internal: fp16 weight planes missing for the two-pass FFN precision");
+        g.W_hi = w.h_hi; g.W_lo = w.h_lo;
+    }
     if ((g.flags & EPI_BIAS) && !w.bias) return fail(h, "internal: bias requested but absent");
     g.taps = w.taps; g.N = w.N; g.Ktot = w.K;
     g.out_f32 = out.f32; g.out_hi = out.hi; g.out_lo = out.lo;
@@ -276,6 +288,17 @@ bool ln_fusion_on(const st_handle* h, const Workspace& w) {
     return gemm_tc_ln_fusable(g, h->num_sms);
 }
 
+// The opt-in two-pass FFN precision applies when both FFN convs of this problem run on the 2-CTA kernel.
+bool ffn16_on(const st_handle* h, const Workspace& w) {
+    if (h->precision != ST_PRECISION_FFN_FP16X2 || h->engine != ST_ENGINE_TCGEN05) return false;
+    const int H = h->d.hidden, F = h->d.filter;
+    GemmArgs g1, g2;
+    g1.BB = g2.BB = w.BB; g1.T = g2.T = w.T; g1.n_src = g2.n_src = 1;
+    g1.N = F; g1.Ktot = H; g1.Cs[0] = H; g2.N = H; g2.Ktot = F; g2.Cs[0] = F;
+    g1.A_hi[0] = g2.A_hi[0] = w.U.hi; g1.W_hi = g2.W_hi = w.U.hi;       // non-null placeholders: only shapes matter
+    return gemm_tc2_runs(g1, h->num_sms) && gemm_tc2_runs(g2, h->num_sms);
+}
+
 struct NextLn {                 // the LayerNorm that directly follows this block's conv_2 (nullptr: none / not fused)
     const float* film2; long film2_bs; float* x2_out;   // the next block's FiLM (estimator blocks < L/2), else nullptr
     const float* shift; const float* scale;
@@ -289,6 +312,7 @@ int dit_block_core(st_handle* h, Workspace& w, int l, LnArgs ln, const float* ad
                    cudaStream_t s, bool fuse = false, bool ln1_done = false, const NextLn* next = nullptr) {
     const st_dims& d = h->d;
     const int H = d.hidden;
+    const bool f16 = ffn16_on(h, w);   // LN2's U and the hidden activation travel as ONE fp16 plane (in the hi buffers)
     auto base = [&](int flags) {
         GemmArgs g;
         g.BB = w.BB; g.T = w.T; g.a_bmod = w.BB; g.B = w.B; g.mask = mask; g.flags = flags;
@@ -321,23 +345,25 @@ int dit_block_core(st_handle* h, Workspace& w, int l, LnArgs ln, const float* ad
     {   // x += gate_msa * conv_o(attn) * mask   (:65, :111)  [+ LN2 + modulate, FFN input mask (:112, :26) in the epilogue]
         GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
         g.gate = ada_l + 2 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
-        if (fuse) { g.ln = 1; g.ln_mask_out = 1; g.ln_shift = ada_l + 3 * H; g.ln_scale = ada_l + 4 * H; }
+        if (fuse) { g.ln = 1; g.ln_mask_out = 1; g.ln_shift = ada_l + 3 * H; g.ln_scale = ada_l + 4 * H; g.u16 = f16; }
         Act out = w.X[xb]; out.hi = nullptr; out.lo = nullptr;
         if (run_gemm(h, g, h->wo[l], &w.AO, nullptr, out, s, ST_PROF_GEMM_O)) return 1;
     }
     if (!fuse) {   // LN2 + modulate, FFN input mask (:112, :26)
         LnArgs l2 = ln;
-        l2.xin = w.X[xb].f32; l2.xout = nullptr; l2.has_film = 0; l2.mask_out = 1;
+        l2.xin = w.X[xb].f32; l2.xout = nullptr; l2.has_film = 0; l2.mask_out = 1; l2.u16 = f16;
         l2.shift = ada_l + 3 * H; l2.scale = ada_l + 4 * H;
         ST_LAUNCH_P(ST_PROF_LN, 0, (double)w.BB * w.T * H * 8, s, launch_film_ln_mod(l2, s));
     }
     {   // conv_1 + SiLU, (h * mask) feeds conv_2 (:26-29)
         GemmArgs g = base(EPI_BIAS | EPI_SILU | EPI_MASK);
+        if (f16) { g.prec = 1; g.out16 = 1; }
         if (run_gemm(h, g, h->c1[l], &w.U, nullptr, w.Hid, s, ST_PROF_GEMM_C1)) return 1;
     }
     {   // x += gate_mlp * (conv_2(h) * mask)   (:29-30, :112)  [+ the next block's (FiLM·mask,) LN1 + modulate in the epilogue]
         GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
         g.gate = ada_l + 5 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
+        if (f16) g.prec = 1;
         if (fuse && next) {
             g.ln = 1; g.ln_mask_out = 0; g.ln_shift = next->shift; g.ln_scale = next->scale;
             g.film2 = next->film2; g.film2_bstride = next->film2_bs; g.out2_f32 = next->x2_out;
@@ -518,6 +544,14 @@ int st_set_engine(st_handle* h, int engine) {
     return 0;
 }
 
+int st_set_precision(st_handle* h, int precision) {
+    if (!h) return 1;
+    if (precision != ST_PRECISION_DEFAULT && precision != ST_PRECISION_FFN_FP16X2) return fail(h, "unknown precision mode");
+    h->drop_graphs();                  // cached graphs bake the kernel instances in
+    h->precision = precision;
+    return 0;
+}
+
 int64_t st_launch_count(const st_handle* h) { return h ? h->launches : 0; }
 
 int st_profile_begin(st_handle* h) {
@@ -586,6 +620,7 @@ int st_finalize_weights(st_handle* h, void* stream) {
             if (pack_gemm(h, &h->wo[l], {p + "attn.conv_o"}, H, H, 1, 0, H, true, s)) return 1;
             if (pack_gemm(h, &h->c1[l], {p + "mlp.conv_1"}, F, H, k, 0, H, true, s)) return 1;
             if (pack_gemm(h, &h->c2[l], {p + "mlp.conv_2"}, H, F, k, 0, F, true, s)) return 1;
+            if (pack_f16_planes(h, &h->c1[l], s) || pack_f16_planes(h, &h->c2[l], s)) return 1;
             if (get_raw(h, p + "adaLN_modulation.2.weight", (int64_t)6 * H * H, &h->ada_w[l])) return 1;
             if (get_raw(h, p + "adaLN_modulation.2.bias", 6 * H, &h->ada_b[l])) return 1;
         }
@@ -607,6 +642,7 @@ int st_finalize_weights(st_handle* h, void* stream) {
         if (pack_gemm(h, &h->wo[l], {p + "block.attn.conv_o"}, H, H, 1, 0, H, true, s)) return 1;
         if (pack_gemm(h, &h->c1[l], {p + "block.mlp.conv_1"}, F, H, k, 0, H, true, s)) return 1;
         if (pack_gemm(h, &h->c2[l], {p + "block.mlp.conv_2"}, H, F, k, 0, F, true, s)) return 1;
+        if (pack_f16_planes(h, &h->c1[l], s) || pack_f16_planes(h, &h->c2[l], s)) return 1;
         if (get_raw(h, p + "time_fusion.film.weight", (int64_t)2 * H * H, &h->film_w[l])) return 1;
         if (get_raw(h, p + "time_fusion.film.bias", 2 * H, &h->film_b[l])) return 1;
         if (get_raw(h, p + "block.adaLN_modulation.2.weight", (int64_t)6 * H * H, &h->ada_w[l])) return 1;

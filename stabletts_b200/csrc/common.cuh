@@ -68,6 +68,11 @@ struct GemmArgs {
     const float* ln_shift = nullptr; const float* ln_scale = nullptr; long ada_bstride = 0;
     bf16* u_hi = nullptr; bf16* u_lo = nullptr;
     const float* film2 = nullptr; long film2_bstride = 0; float* out2_f32 = nullptr;
+    // opt-in two-pass FFN precision (ST_PRECISION_FFN_FP16X2, 2-CTA kernel only): prec = 1 -> the A operand is ONE fp16
+    // plane (A_hi[i] points to it, A_lo is ignored), the weights are an fp16 hi / lo pair (W_hi / W_lo point to them) and
+    // each k-step issues A16·Wlo + A16·Whi (kind::f16 with fp16 operands).  out16: the split output becomes one fp16 plane
+    // written to out_hi (out_lo ignored); u16: likewise for the fused LayerNorm output u_hi.
+    int prec = 0, out16 = 0, u16 = 0;
 };
 
 // engines
@@ -77,6 +82,8 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s);
 const char* gemm_tc_last_error();
 // true when launch_gemm_tc would run this problem on full-row (256-channel) 2-CTA tiles, i.e. GemmArgs::ln may be set
 bool gemm_tc_ln_fusable(const GemmArgs& g, int num_sms);
+// true when launch_gemm_tc would run this problem on the 2-CTA kernel at all (GemmArgs::prec / out16 need it)
+bool gemm_tc2_runs(const GemmArgs& g, int num_sms);
 int gemm_tc2_read_trace(long long* host_out);       // debug (STABLETTS_B200_EPI_TRACE=1)
 
 // ----------------------------------------------------------------------------------------------
@@ -97,6 +104,7 @@ struct LnArgs {
     int has_film = 0;             // x = (gamma*xin+beta)*mask  (models/estimator.py:16)
     int mask_out = 0;             // u *= mask (FFN input, models/diffusion_transformer.py:26)
     float* u_f32 = nullptr; bf16* u_hi = nullptr; bf16* u_lo = nullptr;
+    int u16 = 0;                  // u_hi receives ONE fp16 plane instead of the bf16 hi / lo pair (two-pass FFN mode)
     int BB = 0, T = 0, H = 0;
 };
 cudaError_t launch_film_ln_mod(const LnArgs& a, cudaStream_t s);
@@ -127,6 +135,8 @@ cudaError_t launch_cfm_mix(const float* x1, const float* z, const float* t, floa
 cudaError_t launch_cfm_loss(const float* v, const float* x1, const float* z, const float* mask, float sigma_min, int B, int C,
                             int T, double* acc2, float* loss, cudaStream_t s);
 cudaError_t launch_split(const float* in, bf16* hi, bf16* lo, long numel, cudaStream_t s);
+// fp32 -> fp16 hi / lo planes (hi = fp16(x), lo = fp16(x - hi)), stored in 2-byte slots typed bf16* like every plane here
+cudaError_t launch_split_f16(const float* in, bf16* hi, bf16* lo, long numel, cudaStream_t s);
 
 // duration -> alignment -> mu_y expansion (align.cu; models/model.py:81-95)
 cudaError_t launch_align_lengths(const float* logw, const float* x_mask, float length_scale, int B, int Tx, float* cum,
@@ -210,6 +220,14 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
     const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xFFFF0000u);
     __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
     lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// two floats -> one packed fp16x2 word, saturated to the finite fp16 range (fp16 overflows at 65504 where bf16 does not)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));       // low half = a, high half = b
+    return r;
 }
 
 __device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {

@@ -2,6 +2,7 @@
 // LayerNorm → adaLN-modulate (one pass, warp-shuffle reductions), tiny GEMVs for the
 // t-/c-conditioning vectors, CFG combine and Runge–Kutta linear combinations.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
@@ -154,7 +155,9 @@ __global__ void __launch_bounds__(256) film_ln_mod_kernel(LnArgs a) {
             float u3 = ((x[r][j * 4 + 3] - mean) * rstd * (1.f + c4.w) + s4.w) * mo;
             long o = row * H + c;
             if (a.u_f32) *reinterpret_cast<float4*>(a.u_f32 + o) = make_float4(u0, u1, u2, u3);
-            if (a.u_hi) {
+            if (a.u_hi && a.u16) {
+                *reinterpret_cast<uint2*>(a.u_hi + o) = make_uint2(pack_f16x2_sat(u0, u1), pack_f16x2_sat(u2, u3));
+            } else if (a.u_hi) {
                 uint32_t h01, l01, h23, l23;
                 split_bf16x2(u0, u1, h01, l01); split_bf16x2(u2, u3, h23, l23);
                 *reinterpret_cast<uint2*>(a.u_hi + o) = make_uint2(h01, h23);
@@ -385,6 +388,23 @@ __global__ void split_kernel(const float* __restrict__ in, bf16* __restrict__ hi
 cudaError_t launch_split(const float* in, bf16* hi, bf16* lo, long numel, cudaStream_t s) {
     if (numel == 0) return cudaSuccess;
     return launch_k(split_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, s, in, hi, lo, numel);
+}
+
+// fp16 hi / lo planes of a weight tensor (two-pass FFN precision): hi = fp16(x), lo = fp16(x - hi); 22 mantissa bits
+// while |x - hi| stays above the fp16 subnormal step 2^-24
+__global__ void split_f16_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = in[i];
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
+    hi[i] = __half_as_ushort(h); lo[i] = __half_as_ushort(l);
+}
+
+cudaError_t launch_split_f16(const float* in, bf16* hi, bf16* lo, long numel, cudaStream_t s) {
+    if (numel == 0) return cudaSuccess;
+    split_f16_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, s>>>(in, reinterpret_cast<uint16_t*>(hi), reinterpret_cast<uint16_t*>(lo), numel);
+    return cudaGetLastError();
 }
 
 // ----- conditional-flow-matching objective (models/flow_matching.py:69-100), forward value only -----

@@ -37,6 +37,7 @@ struct TcParams {
     const float *bias, *mask, *film, *gate, *resid, *rope_cs;
     int mode;                         // EM_* (kernel-uniform)
     int has_f32, has_split;           // which forms of the output exist (o_f32 / o_hi + o_lo)
+    int out16, u16;                   // two-pass FFN mode: the split form is ONE fp16 plane (o_hi / u_hi), see GemmArgs::prec
     // EM_LN: u = ((x - mean) * rstd * (1 + scale) + shift) [* mask] over the finished row -> u_hi / u_lo;
     // film2: x2 = (gamma2 * x + beta2) * mask first (the NEXT block's time fusion, models/estimator.py:16) -> o2_f32, LN over x2
     int ln_mask_out, has_film2;
@@ -61,6 +62,7 @@ inline void fill_tc_params(TcParams& p, const GemmArgs& g) {
     p.bias = g.bias; p.mask = g.mask; p.film = g.film; p.gate = g.gate; p.resid = g.resid; p.rope_cs = g.rope_cs;
     p.mode = epilogue_mode(g);
     p.has_f32 = g.out_f32 != nullptr; p.has_split = g.out_hi != nullptr;
+    p.out16 = g.out16; p.u16 = g.u16;
     p.ln_mask_out = g.ln_mask_out; p.has_film2 = g.film2 != nullptr;
     p.ln_shift = g.ln_shift; p.ln_scale = g.ln_scale; p.film2 = g.film2;
     p.ada_bstride = g.ada_bstride; p.film2_bstride = g.film2_bstride;
@@ -120,6 +122,16 @@ __device__ __forceinline__ void stage_split(uint32_t stg_hi, uint32_t stg_lo, in
         st_shared_v4(stg_hi + o, h[0], h[1], h[2], h[3]);
         st_shared_v4(stg_lo + o, l[0], l[1], l[2], l[3]);
     }
+}
+
+// the same 32 values as ONE fp16 plane (saturating) -> rows of a 32 x 64 B tile, 64-byte swizzle
+__device__ __forceinline__ void stage_f16(uint32_t stg, int lane, const float (&x)[32]) {
+    const uint32_t off = (uint32_t)lane * 64u;
+    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        st_shared_v4(stg + off + (((uint32_t)c ^ sw) << 4), pack_f16x2_sat(x[8 * c], x[8 * c + 1]), pack_f16x2_sat(x[8 * c + 2], x[8 * c + 3]),
+                     pack_f16x2_sat(x[8 * c + 4], x[8 * c + 5]), pack_f16x2_sat(x[8 * c + 6], x[8 * c + 7]));
 }
 
 }  // namespace epi
@@ -195,6 +207,16 @@ __device__ __forceinline__ void epi_store_split(const CUtensorMap* mhi, const CU
     fence_proxy_async_smem();
     __syncwarp();
     if (c.lane == 0) { tma_store_3d(mhi, c.stg, nb, c.t0, c.bb); tma_store_3d(mlo, c.stg + 2048u, nb, c.t0, c.bb); bulk_commit(); }
+}
+
+__device__ __forceinline__ void epi_store_f16(const CUtensorMap* map, const EpiCtx& c, int nb, const float (&x)[32]) {
+    using namespace ptx;
+    if (c.lane == 0) bulk_wait_read0();
+    __syncwarp();
+    epi::stage_f16(c.stg, c.lane, x);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (c.lane == 0) { tma_store_3d(map, c.stg, nb, c.t0, c.bb); bulk_commit(); }
 }
 
 // ---- one 32-channel chunk: v (accumulator) [+ r (residual)] -> x -> staging -> TMA stores ----------------------------
@@ -300,7 +322,7 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const EpiMaps& em, 
     }
     if (trace) tk2 = clock64();
     if (p.has_f32) epi_store_f32(&em.o_f32, c, nb, x);
-    if (p.has_split) epi_store_split(&em.o_hi, &em.o_lo, c, nb, x);
+    if (p.has_split) { if (p.out16) epi_store_f16(&em.o_hi, c, nb, x); else epi_store_split(&em.o_hi, &em.o_lo, c, nb, x); }
     if (trace) {
         long long* d = p.dbg + ((long)(c.tile_it >> 1) * 2 * NCH + kc) * 8;
         d[0] = tk0; d[1] = tk1; d[2] = tk2; d[3] = 0; d[4] = clock64();
@@ -355,7 +377,7 @@ __device__ __forceinline__ void epi_chunk_ln2(const TcParams& p, const EpiMaps& 
         u[4 * q + 3] = ((__uint_as_float(v[4 * q + 3]) - mean) * rstd * (1.f + c4.w) + s4.w) * mo;
     }
     if (trace) tk2 = clock64();
-    epi_store_split(&em.u_hi, &em.u_lo, c, nb, u);
+    if (p.u16) epi_store_f16(&em.u_hi, c, nb, u); else epi_store_split(&em.u_hi, &em.u_lo, c, nb, u);
     if (trace) {
         long long* d = p.dbg + ((long)(c.tile_it >> 1) * 2 * NCH + NCH + kc) * 8;
         d[0] = tk0; d[1] = tk1; d[2] = tk2; d[3] = 0; d[4] = clock64();

@@ -324,11 +324,17 @@ bool build_epi_maps(const GemmArgs& g, EpiMaps* em) {
     bool ok = true;
     if (g.out_f32) { ok = ok && tmap_encode_store(g.out_f32, true, N, T, BB, &em->o_f32); any = &em->o_f32; }
     if (g.out_hi) {
-        ok = ok && g.out_lo && tmap_encode_store(g.out_hi, false, N, T, BB, &em->o_hi) && tmap_encode_store(g.out_lo, false, N, T, BB, &em->o_lo);
+        ok = ok && tmap_encode_store(g.out_hi, false, N, T, BB, &em->o_hi);
+        if (g.out16) em->o_lo = em->o_hi;          // one fp16 plane: there is no lo plane
+        else ok = ok && g.out_lo && tmap_encode_store(g.out_lo, false, N, T, BB, &em->o_lo);
         any = &em->o_hi;
     }
     if (g.film2) { ok = ok && g.out2_f32 && tmap_encode_store(g.out2_f32, true, N, T, BB, &em->o2_f32); }
-    if (g.ln) ok = ok && g.u_hi && g.u_lo && tmap_encode_store(g.u_hi, false, N, T, BB, &em->u_hi) && tmap_encode_store(g.u_lo, false, N, T, BB, &em->u_lo);
+    if (g.ln) {
+        ok = ok && g.u_hi && tmap_encode_store(g.u_hi, false, N, T, BB, &em->u_hi);
+        if (g.u16) em->u_lo = em->u_hi;
+        else ok = ok && g.u_lo && tmap_encode_store(g.u_lo, false, N, T, BB, &em->u_lo);
+    }
     if (!ok || !any) return false;
     em->resid = *any;
     if (g.flags & EPI_RESID) {         // residual LOAD map (rows beyond T read as zero; used by the shallow-main-loop kernels)
@@ -361,6 +367,11 @@ static bool tc2_shapes_ok(const GemmArgs& g) {
            (g.n_src == 1 || (g.Cs[0] % BLOCK_K == 0 && g.Cs[1] % 8 == 0 && g.A_hi[1]));
 }
 
+bool gemm_tc2_runs(const GemmArgs& g, int num_sms) {
+    const int mode = tc2_mode();
+    return mode && tc2_shapes_ok(g) && (mode == 2 || gemm_tc2_eligible(g, num_sms));
+}
+
 bool gemm_tc_ln_fusable(const GemmArgs& g, int num_sms) {
     const int mode = tc2_mode();
     return g.N == 256 && mode && tc2_shapes_ok(g) && (mode == 2 || gemm_tc2_eligible(g, num_sms));
@@ -382,9 +393,10 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s) {
             return e;
         }
     }
-    if (g.ln) {
+    if (g.ln || g.prec) {
         std::lock_guard<std::mutex> lk(g_mu);
-        g_err = "fused LayerNorm needs full-row 2-CTA tiles (check gemm_tc_ln_fusable before setting GemmArgs::ln)";
+        g_err = g.ln ? "fused LayerNorm needs full-row 2-CTA tiles (check gemm_tc_ln_fusable before setting GemmArgs::ln)"
+                     : "the two-pass fp16 FFN precision runs on the 2-CTA kernel only (check gemm_tc2_runs before setting GemmArgs::prec)";
         return cudaErrorInvalidValue;
     }
     {

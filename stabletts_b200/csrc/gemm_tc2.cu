@@ -42,10 +42,13 @@ constexpr int TILE_BYTES = 128 * BK * 2;            // 16 KB: one A plane tile (
 // which leaves 64 KB for per-warp residual tiles brought in by the TMA unit (2 x 4 KB per epilogue warp).  A thread reading
 // its own residual row (8 x 16 B of one line) costs ~3000 cycles per chunk when nothing hides it (profiles/r2i_trace.log);
 // the long k-tap convs hide it behind their main loop and keep the deep pipeline.
-template <int BN2, int SHALLOW = 0> struct Cfg2 {
+// PREC = 1: the opt-in two-pass FFN precision — ONE fp16 A plane, fp16 hi / lo weight planes, two MMAs per k-step
+// (A16·Wlo + A16·Whi): a stage is A16 | Bh_hi | Bh_lo = 48 / 32 KB, so four stages fit where three did.
+template <int BN2, int SHALLOW = 0, int PREC = 0> struct Cfg2 {
     static constexpr int B_TILE_BYTES = (BN2 / 2) * BK * 2;                  // B-half plane tile
-    static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;    // A_hi, A_lo, Bh_hi, Bh_lo: 64 / 48 KB
-    static constexpr int STAGES = SHALLOW ? 2 : (BN2 == 256 ? 3 : 4);
+    static constexpr int A_PLANES = PREC ? 1 : 2;
+    static constexpr int STAGE_BYTES = A_PLANES * TILE_BYTES + 2 * B_TILE_BYTES;    // [A_hi, A_lo | A16], Bh_hi, Bh_lo
+    static constexpr int STAGES = SHALLOW ? 2 : (PREC ? 4 : (BN2 == 256 ? 3 : 4));
     static constexpr int TMEM_COLS = 2 * BN2;                                // two accumulator stages
     static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;                 // 1024-aligned: swizzled TMA-store tiles
     static constexpr int RESID_OFF = STAGING_OFF + EPI_WARPS * EPI_STAGE_BYTES;          // SHALLOW: 8 warps x 2 x 4 KB
@@ -60,10 +63,11 @@ typedef TcParams Params2;
 // One kernel instance per (tile width, epilogue mode): a combined kernel that switched over the modes at run time made
 // ptxas keep every mode's register arrays in one allocation (2 KB of spills); separate instances also keep the
 // instruction footprint of a launch small.
-template <int BN2, int MODE, int SHALLOW>
+template <int BN2, int MODE, int SHALLOW, int PREC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiMaps em, const Params2 p) {
-    using CF = Cfg2<BN2, SHALLOW>;
+    using CF = Cfg2<BN2, SHALLOW, PREC>;
+    constexpr int A_BYTES = CF::A_PLANES * TILE_BYTES;          // offset of the B tiles inside a stage
     constexpr int B_TILE_BYTES = CF::B_TILE_BYTES, STAGE_BYTES = CF::STAGE_BYTES, STAGES = CF::STAGES;
     constexpr int TMEM_COLS = CF::TMEM_COLS;
     extern __shared__ uint8_t smem_raw[];
@@ -124,10 +128,10 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiM
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* s = smem + stage * STAGE_BYTES;
                         if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-                        tma_load_3d_2sm(&maps.a_hi[src], &full_bar[stage], s, kc, t0 + tap - pad, ab);
-                        tma_load_3d_2sm(&maps.a_lo[src], &full_bar[stage], s + TILE_BYTES, kc, t0 + tap - pad, ab);
-                        tma_load_2d_2sm(&maps.w_hi, &full_bar[stage], s + 2 * TILE_BYTES, kw, tap * p.N + n0);
-                        tma_load_2d_2sm(&maps.w_lo, &full_bar[stage], s + 2 * TILE_BYTES + B_TILE_BYTES, kw, tap * p.N + n0);
+                        tma_load_3d_2sm(&maps.a_hi[src], &full_bar[stage], s, kc, t0 + tap - pad, ab);          // PREC: the fp16 plane
+                        if (!PREC) tma_load_3d_2sm(&maps.a_lo[src], &full_bar[stage], s + TILE_BYTES, kc, t0 + tap - pad, ab);
+                        tma_load_2d_2sm(&maps.w_hi, &full_bar[stage], s + A_BYTES, kw, tap * p.N + n0);
+                        tma_load_2d_2sm(&maps.w_lo, &full_bar[stage], s + A_BYTES + B_TILE_BYTES, kw, tap * p.N + n0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -136,7 +140,7 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiM
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA only) =================
         if (leader) {
-            constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN2);
+            constexpr uint32_t idesc = PREC ? make_idesc_f16(2 * BM, BN2) : make_idesc_bf16(2 * BM, BN2);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
@@ -149,13 +153,18 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiM
                     if (elect_one()) {
                         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                         const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + TILE_BYTES);
-                        const uint64_t b_hi = make_sw128_desc(sa + 2 * TILE_BYTES), b_lo = make_sw128_desc(sa + 2 * TILE_BYTES + B_TILE_BYTES);
+                        const uint64_t b_hi = make_sw128_desc(sa + A_BYTES), b_lo = make_sw128_desc(sa + A_BYTES + B_TILE_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / UK; ++k) {
                             const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);
-                            umma_bf16_2sm(tmem_d, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-                            umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
-                            umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+                            if (PREC) {                    // fp16 operands: A16·Wlo + A16·Whi (small term first)
+                                umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, (kb | k) != 0);
+                                umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+                            } else {
+                                umma_bf16_2sm(tmem_d, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+                                umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+                                umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+                            }
                         }
                         umma_commit_2sm(&empty_bar[stage], 0b11);                       // both CTAs' stage s may be refilled
                         if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[acc], 0b11);   // both epilogues may drain
@@ -236,14 +245,14 @@ static int pick_bn2(const GemmArgs& g, int pairs) {
     return w128 < 0.97 * w256 ? 128 : 256;
 }
 
-template <int BN2, int MODE, int SHALLOW>
+template <int BN2, int MODE, int SHALLOW, int PREC = 0>
 static cudaError_t launch_tc2_inst(const Maps2& maps, const EpiMaps& em, const Params2& p, int pairs, cudaStream_t s) {
     static std::atomic<uint64_t> attr_done{0};      // one bit per device
-    cudaError_t e = ensure_dyn_smem(gemm_tc2_kernel<BN2, MODE, SHALLOW>, Cfg2<BN2, SHALLOW>::SMEM_BYTES, attr_done);
+    using CF = Cfg2<BN2, SHALLOW, PREC>;
+    cudaError_t e = ensure_dyn_smem(gemm_tc2_kernel<BN2, MODE, SHALLOW, PREC>, CF::SMEM_BYTES, attr_done);
     if (e != cudaSuccess) { g_err2 = "cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc2_kernel"; return e; }
     const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
-    return launch_k(gemm_tc2_kernel<BN2, MODE, SHALLOW>, dim3(2 * clusters), dim3(THREADS), (size_t)Cfg2<BN2, SHALLOW>::SMEM_BYTES, s,
-                    maps, em, p);
+    return launch_k(gemm_tc2_kernel<BN2, MODE, SHALLOW, PREC>, dim3(2 * clusters), dim3(THREADS), (size_t)CF::SMEM_BYTES, s, maps, em, p);
 }
 
 // residual GEMMs whose K is a few k-blocks (O, in_proj) run the shallow-pipeline instance with TMA-loaded residual tiles
@@ -258,6 +267,14 @@ static cudaError_t launch_tc2_bn(const Maps2& maps, const EpiMaps& em, Params2& 
     p.n_tiles = (g.N + BN2 - 1) / BN2;
     p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
     const bool sh = use_shallow(g);
+    if (g.prec) {                      // two-pass fp16 FFN convs: conv_1 (SiLU), conv_2 (residual, with or without the fused LayerNorm)
+        switch (p.mode) {
+            case EM_SILU:  return launch_tc2_inst<BN2, EM_SILU, 0, 1>(maps, em, p, pairs, s);
+            case EM_LN:    return launch_tc2_inst<BN2, EM_LN, 0, 1>(maps, em, p, pairs, s);
+            case EM_RESID: return launch_tc2_inst<BN2, EM_RESID, 0, 1>(maps, em, p, pairs, s);
+            default: g_err2 = "the two-pass fp16 precision is built for the FFN convs only (SiLU / residual epilogues)"; return cudaErrorInvalidValue;
+        }
+    }
     switch (p.mode) {
         case EM_ROPE: return launch_tc2_inst<BN2, EM_ROPE, 0>(maps, em, p, pairs, s);
         case EM_LN:   return sh ? launch_tc2_inst<BN2, EM_LN, 1>(maps, em, p, pairs, s) : launch_tc2_inst<BN2, EM_LN, 0>(maps, em, p, pairs, s);
@@ -272,9 +289,12 @@ cudaError_t launch_gemm_tc2(const GemmArgs& g, int num_sms, cudaStream_t s) {
     Maps2 maps;
     const int pairs = num_sms / 2;
     const int bn2 = pick_bn2(g, pairs);
-    for (int i = 0; i < g.n_src; ++i) {
-        if (!tmap_encode_bf16(g.A_hi[i], 3, (uint64_t)g.Cs[i], (uint64_t)g.T, (uint64_t)g.a_bmod, BK, BM, &maps.a_hi[i]) ||
-            !tmap_encode_bf16(g.A_lo[i], 3, (uint64_t)g.Cs[i], (uint64_t)g.T, (uint64_t)g.a_bmod, BK, BM, &maps.a_lo[i])) {
+    for (int i = 0; i < g.n_src; ++i) {            // (a 2-byte-element map serves bf16 and fp16 planes alike)
+        if (!tmap_encode_bf16(g.A_hi[i], 3, (uint64_t)g.Cs[i], (uint64_t)g.T, (uint64_t)g.a_bmod, BK, BM, &maps.a_hi[i])) {
+            g_err2 = gemm_tc_last_error(); return cudaErrorInvalidValue;
+        }
+        if (g.prec) maps.a_lo[i] = maps.a_hi[i];
+        else if (!tmap_encode_bf16(g.A_lo[i], 3, (uint64_t)g.Cs[i], (uint64_t)g.T, (uint64_t)g.a_bmod, BK, BM, &maps.a_lo[i])) {
             g_err2 = gemm_tc_last_error(); return cudaErrorInvalidValue;
         }
     }

@@ -11,6 +11,7 @@ namespace st {
 
 struct GemmW {           // one packed conv/linear weight
     float* f32 = nullptr; bf16* hi = nullptr; bf16* lo = nullptr; float* bias = nullptr;
+    bf16 *h_hi = nullptr, *h_lo = nullptr;      // fp16 hi / lo planes (FFN convs only; the opt-in two-pass precision)
     int taps = 1, N = 0, K = 0;
 };
 
@@ -38,6 +39,7 @@ struct st_handle {
     void* vocos = nullptr;             // kind 2: st::VocosState (vocos_api.cu)
     int n_vocab = 0; float* emb = nullptr;
     int device = 0, engine = ST_ENGINE_TCGEN05, num_sms = 148;
+    int precision = ST_PRECISION_DEFAULT;
     std::string err;
     std::map<std::string, std::pair<float*, int64_t>> raw;   // name -> (device copy, numel)
     bool finalized = false;

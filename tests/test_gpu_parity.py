@@ -387,3 +387,43 @@ def test_text_encoder_rejects_out_of_range_ids_and_empty_inputs(dev):
         enc(torch.tensor([[1, 2, 50]], device=dev), c, torch.tensor([3], device=dev))
     x, mu, mask = enc(torch.zeros(0, 5, dtype=torch.long, device=dev), torch.zeros(0, 256, device=dev), torch.zeros(0, dtype=torch.long, device=dev))
     assert x.shape == (0, 256, 5) and mu.shape == (0, 80, 5) and mask.shape == (0, 1, 5)
+
+
+def test_ffn_fp16x2_precision_mode(dev):
+    """The opt-in two-pass FFN precision (st_set_precision / Decoder.set_precision('ffn_fp16x2')): fp16 activations against fp16
+    hi / lo weights in conv_1 / conv_2.  At a shape that runs on the 2-CTA kernel (20 x 1024 frames) it must stay inside the
+    1e-3 bar, be measurably less exact than the default (proof that the mode is active), leave the default results
+    bit-identical after switching back; a 10-step CFG Euler solve at 24 x 512 must stay inside the bar as well."""
+    from stabletts_b200 import CFMDecoder
+    st = weights.make_state(cases.WEIGHT_SEED, 80)
+    m = CFMDecoder(80, 80, 256, 80, 1024, 4, 6, 3, 0.1, 256).eval()
+    m.estimator.load_state_dict(st, strict=True)
+    m = m.to(dev)
+    lens = [1024] * 20
+    lens[7], lens[19] = 700, 1001
+    big = weights.make_inputs(4, lens, 1024, 80)
+    args = [big[k].to(dev) for k in ("t", "x", "mask", "mu", "c")]
+    rows = [0, 7, 19]
+    with torch.inference_mode():
+        ref = R.estimator_forward(st, big["t"], big["x"][rows], big["mask"][rows], big["mu"][rows], big["c"][rows])
+    base = m.estimator(*args).cpu()
+    e_def = max(rel_errs(base[rows], ref))
+    m.estimator.set_precision("ffn_fp16x2")
+    out16 = m.estimator(*args).cpu()
+    e_16 = max(rel_errs(out16[rows], ref))
+    assert e_16 < 1e-3, e_16
+    assert e_16 > 2 * e_def, (e_16, e_def)                     # the mode is on: fp16 activations cost accuracy
+    assert float((out16 * (1 - big["mask"])).abs().max()) == 0.0
+    # a full solve in the mode
+    inp = weights.make_inputs(9, [512] * 23 + [401], 512, 80)
+    fs, fc = weights.make_cfg_params(cases.CFG_SEED)
+    kw = dict(fake_speaker=fs.to(dev), fake_content=fc.to(dev), cfg_strength=3.0)
+    sol = m(inp["mu"].to(dev), inp["mask"].to(dev), 10, 1.0, inp["c"].to(dev), "euler", kw, z=inp["x"].to(dev)).cpu()
+    with torch.inference_mode():
+        rs = _oracle_solve_rows(st, inp, (0, 23), 10, "euler", dict(fake_speaker=fs, fake_content=fc, cfg_strength=3.0))
+    e_solve = max(rel_errs(sol[[0, 23]], rs))
+    assert e_solve < 1e-3, e_solve
+    print(f"ffn_fp16x2: estimator call {e_16:.2e} (default {e_def:.2e}), 10-step CFG Euler solve {e_solve:.2e}")
+    m.estimator.set_precision("default")
+    again = m.estimator(*args).cpu()
+    assert torch.equal(again, base)
