@@ -291,7 +291,7 @@ def set_cfg_params(inp, cfgd):
 _CPU_REF_CACHE = {}      # (config name, rows) -> (rows, ref, seconds, note, kind): the CPU arm runs once per config, not once per precision
 
 
-def run_config(args, name, model, dev, rank, world, steps, warmup, flush, *, full=True, precision="default"):
+def run_config(args, name, model, dev, rank, world, steps, warmup, flush, *, full=True, precision="ffn_fp16x2"):
     """Measures one BASELINE config on this process group.  Every rank generates the same seeded GLOBAL batch on the
     host and keeps its own contiguous slice (pinned): a one-process-per-GPU server owns its requests' buffers.
       value  : every rank's slice resident in its HBM, no collective in the timed region ("per_rank_inputs")
@@ -450,7 +450,7 @@ def run_config(args, name, model, dev, rank, world, steps, warmup, flush, *, ful
             _CPU_REF_CACHE[key] = cpu_reference_solve(arm, inp, cfgd, sample_rows(nb), budget_s=args.cpu_budget)
         rows, ref, dt, note = _CPU_REF_CACHE[key]
         fr = int(inp["lens"][torch.as_tensor(rows)].sum())
-        if world == 1 and full and precision == "default":
+        if world == 1 and full and precision == args.precision:
             res["cpu_baseline"] = {"value": fr / dt, "unit": "frames/s", "cores": threads, "kind": arm.kind,
                                    "sample": f"utterances {rows} of the batch (T={T}); {note}; os.cpu_count()={os.cpu_count()}"}
         if ref is not None:
@@ -538,9 +538,10 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=30.0, help="seconds of CPU work for the cpu_baseline / parity leg")
     ap.add_argument("--no-cfg4", action="store_true", help="at N=8 skip the additional BASELINE cfg4 block (128/GPU = 1024 global)")
     ap.add_argument("--no-vocoder", action="store_true", help="skip the vocoder hand-off block (row f4)")
-    ap.add_argument("--precision", default="default", choices=["default", "ffn_fp16x2"],
-                    help="operand precision of the headline run (default: split-bf16 x 3 everywhere); at N = 1 the OTHER mode is measured "
-                         "beside it and reported under the key 'ffn_fp16x2' / 'default_precision'")
+    ap.add_argument("--precision", default="ffn_fp16x2", choices=["ffn_fp16x2", "bf16x3"],
+                    help="operand precision of the headline run: ffn_fp16x2 (the library default: split-bf16 x 3 everywhere except the FFN "
+                         "convs, fp16 activations x fp16 hi/lo weights in 2 passes) or bf16x3 (3 passes everywhere); at N = 1 the OTHER mode "
+                         "is measured beside it and reported under 'other_precision'")
     ap.add_argument("--no-second-precision", action="store_true", help="skip the secondary precision block")
     ap.add_argument("--ncu-mode", action="store_true",
                     help="for `ncu` launch lists only: honours --warmup < 3, skips e2e / instrumented / CPU legs (numbers printed under a profiler are never bench values)")
@@ -580,7 +581,7 @@ def main():
     # the other precision mode on the same box, same inputs (decide-with-evidence block: throughput, parity, GEMM roofline)
     other = None
     if world == 1 and not args.no_second_precision and args.engine == "tcgen05":
-        other_name = "ffn_fp16x2" if args.precision == "default" else "default"
+        other_name = "bf16x3" if args.precision == "ffn_fp16x2" else "ffn_fp16x2"
         try:
             other = run_config(args, args.config, model, dev, rank, world, min(args.steps, 4), 3, flush, full=True, precision=other_name)
             other["precision"] = other_name
@@ -596,7 +597,7 @@ def main():
     # BASELINE cfg4 AS WRITTEN (batch 1024 over 8 GPUs = 128 per GPU) rides along in the N = 8 run of the default config
     r4 = None
     if world == 8 and args.config == "cfg1" and not args.no_cfg4:
-        r4 = run_config(args, "cfg4", model, dev, rank, world, min(args.steps, 3), 3, flush, full=False)
+        r4 = run_config(args, "cfg4", model, dev, rank, world, min(args.steps, 3), 3, flush, full=False, precision=args.precision)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -635,7 +636,7 @@ def main():
         "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "warmup_steps_run": r["n_warm"],
         "ms_per_step": 1e3 * sec_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": ("f32" if args.engine != "tcgen05" else
-                  "f32 (split-bf16x3 tensor-core operands, fp32 accumulate)" if args.precision == "default" else
+                  "f32 (split-bf16x3 tensor-core operands, fp32 accumulate)" if args.precision == "bf16x3" else
                   "f32 (split-bf16x3 tensor-core operands; FFN convs fp16 activations x fp16 hi/lo weights, 2 passes; fp32 accumulate)"),
         "data": "synthetic",
         "config": {"workload": f"{args.config}: {cfgd['desc']}", "global_batch": r["Bglob"], "T": r["T"], "nfe": nfe,
@@ -657,7 +658,9 @@ def main():
                      "traffic_note": "dram__bytes_read+write per launch, mean over the ncu --set full capture in profiles/gemm_traffic.json",
                      "achieved_per_launch_gflop": gm["flops"] / max(gm["launches"], 1) / 1e9,
                      "peak_source": peak_src, "launches": gm["launches"], "kernel_ms_per_step": gm["ms"],
-                     "note": "algorithmic FLOPs (2*rows*N*K*taps); the bf16x3 split issues 3 MMAs per algorithmic MAC"},
+                     "note": "algorithmic FLOPs (2*rows*N*K*taps); the bf16x3 split issues 3 MMAs per algorithmic MAC"
+                             + (", the FFN convs 2 (fp16 activations x fp16 hi/lo weights)" if args.precision == "ffn_fp16x2" else ""),
+                     "precision": args.precision},
         "breakdown_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
         "breakdown_tflops": {k: round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1) for k, v in prof.items() if v["flops"] > 0},
         "attention": {"tflops": prof["attention"]["flops"] / max(prof["attention"]["ms"], 1e-9) / 1e9},
@@ -683,7 +686,7 @@ def main():
                 "roofline": {"achieved": o_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": o_tf / peak_tf,
                              "note": "same algorithmic FLOPs; the FFN convs issue 2 MMAs per MAC in ffn_fp16x2 mode, 3 in default"},
                 "breakdown_ms_per_step": {k: round(v["ms"], 3) for k, v in other["prof"].items()},
-                "note": "opt-in st_set_precision mode measured on the same box right after the headline run; the headline (value, e2e) is the --precision mode"}
+                "note": "the other st_set_precision mode measured on the same box right after the headline run; the headline (value, e2e) is the --precision mode"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -74,13 +74,18 @@ int st_finalize_weights(st_handle* h, void* stream);
 /* Selects the GEMM engine (see enum above).  Default ST_ENGINE_TCGEN05. */
 int st_set_engine(st_handle* h, int engine);
 
-/* Precision of the tensor-core engine's operands.  ST_PRECISION_DEFAULT: every contraction runs split-bf16 x 3 (hi / lo
- * planes of both operands, three MMA passes, ~16 mantissa bits; measured 1e-5 against the reference).  ST_PRECISION_FFN_FP16X2
- * (opt-in): the two k = 3 FFN convs of every DiT block (models/diffusion_transformer.py:20-30, 48-55 % of the FLOPs) take their
- * activations as ONE fp16 plane against fp16 hi / lo weights — two MMA passes instead of three and half the hidden-activation
- * traffic — at about 2e-4 per estimator call instead of 1e-5 (still inside the 1e-3 bar; DESIGN.md has the measured table).
- * Applies to problems large enough for the 2-CTA kernel; smaller ones keep three passes. */
-enum { ST_PRECISION_DEFAULT = 0, ST_PRECISION_FFN_FP16X2 = 1 };
+/* Precision of the tensor-core engine's operands.
+ *   ST_PRECISION_FFN_FP16X2 (the default since round 2): every contraction runs split-bf16 x 3 (hi / lo planes of both
+ *     operands, three MMA passes, ~16 mantissa bits) EXCEPT the two k = 3 FFN convs of every DiT block
+ *     (models/diffusion_transformer.py:20-30; 48-55 % of the FLOPs), which take their activations as ONE fp16 plane against
+ *     fp16 hi / lo weights: two MMA passes and half the hidden-activation traffic.  Measured against the reference:
+ *     2.0e-4 per estimator call, 1.3e-4 on the cfg1 solve, 2.9e-4 at n_mel = 128 / T = 1000, 2.4e-4 at T = 2000,
+ *     4.1e-5 on the 150-evaluation cfg2 solve (tests/test_gpu_parity.py::test_ffn_fp16x2_margin_at_maximum_sizes holds
+ *     every one of them under 5e-4 = 2x margin below the 1e-3 bar); -15 % time per solve.  Applies to problems large
+ *     enough for the 2-CTA kernel; smaller ones run three passes everywhere.
+ *   ST_PRECISION_BF16X3: three passes everywhere (measured 1e-5 .. 2.5e-5): the round-1 behaviour, for callers who want
+ *     the widest margin.  The environment variable STABLETTS_B200_PRECISION=bf16x3|ffn_fp16x2 sets the initial mode. */
+enum { ST_PRECISION_BF16X3 = 0, ST_PRECISION_FFN_FP16X2 = 1 };
 int st_set_precision(st_handle* h, int precision);
 
 /* Workspace: bytes needed for a (B, T) problem (cfg != 0 doubles the estimator batch), and

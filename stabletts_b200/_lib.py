@@ -9,7 +9,7 @@ _LIB = None
 
 ST_EULER, ST_MIDPOINT, ST_RK4, ST_DOPRI5_FIXED = 0, 1, 2, 3
 ST_ENGINE_TCGEN05, ST_ENGINE_SIMT = 0, 1
-ST_PRECISION_DEFAULT, ST_PRECISION_FFN_FP16X2 = 0, 1
+ST_PRECISION_BF16X3, ST_PRECISION_FFN_FP16X2 = 0, 1
 ST_ADAPT_DOPRI5, ST_ADAPT_BOSH3, ST_ADAPT_FEHLBERG2, ST_ADAPT_HEUN = 0, 1, 2, 3
 ST_PROF_NAMES = ("gemm_other", "attention", "ln", "gemm_qkv", "gemm_o", "gemm_conv1", "gemm_conv2", "gemm_lsc", "gemm_cond")
 ST_PROF_NCAT = len(ST_PROF_NAMES)

@@ -29,7 +29,7 @@ class NativeModule(nn.Module):
         self._workspace = None
         # debugging switch between the two CUDA engines (not a backend dispatch; both are this library)
         self._engine = _lib.ST_ENGINE_SIMT if os.environ.get("STABLETTS_B200_ENGINE") == "simt" else _lib.ST_ENGINE_TCGEN05
-        self._precision = _lib.ST_PRECISION_DEFAULT
+        self._precision = None                  # None: the library's default (ffn_fp16x2, or STABLETTS_B200_PRECISION)
 
     # -- module tree ------------------------------------------------------------------------------
     def _register(self, dotted: str, p: nn.Parameter) -> None:
@@ -58,9 +58,11 @@ class NativeModule(nn.Module):
             _lib.check(lib, self._handle, lib.st_set_engine(self._handle, self._engine), "st_set_engine")
 
     def set_precision(self, name: str) -> None:
-        """'default' (split-bf16 x 3 everywhere, ~1e-5) or 'ffn_fp16x2' (opt-in: the FFN convs take fp16 activations
-        against fp16 hi / lo weights, two MMA passes, ~2e-4 per call) — see st_set_precision in the C header."""
-        self._precision = {"default": _lib.ST_PRECISION_DEFAULT, "ffn_fp16x2": _lib.ST_PRECISION_FFN_FP16X2}[name]
+        """'ffn_fp16x2' (= 'default': split-bf16 x 3 everywhere except the FFN convs, which take fp16 activations against
+        fp16 hi / lo weights in two MMA passes; <= 3e-4 against the reference, -15 % time) or 'bf16x3' (three passes
+        everywhere, ~1e-5) — see st_set_precision in the C header."""
+        self._precision = {"default": _lib.ST_PRECISION_FFN_FP16X2, "ffn_fp16x2": _lib.ST_PRECISION_FFN_FP16X2,
+                           "bf16x3": _lib.ST_PRECISION_BF16X3}[name]
         if self._handle is not None:
             lib = _lib.load_library()
             _lib.check(lib, self._handle, lib.st_set_precision(self._handle, self._precision), "st_set_precision")
@@ -77,7 +79,7 @@ class NativeModule(nn.Module):
             self._handle, self._handle_device = h, index
             self._synced.clear()
             _lib.check(lib, h, lib.st_set_engine(h, self._engine), "st_set_engine")
-            if self._precision != _lib.ST_PRECISION_DEFAULT:
+            if self._precision is not None:
                 _lib.check(lib, h, lib.st_set_precision(h, self._precision), "st_set_precision")
         return lib, self._handle
 

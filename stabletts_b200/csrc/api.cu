@@ -501,6 +501,10 @@ int st_create(const st_dims* dims, int device, st_handle** out) {
     if (dims->filter % 64 || dims->filter <= 0) return fail(nullptr, "filter_channels must be a multiple of 64");
     h = new st_handle();
     h->d = *dims; h->device = device; h->num_sms = p.multiProcessorCount;
+    if (const char* e = getenv("STABLETTS_B200_PRECISION")) {
+        if (!strcmp(e, "bf16x3")) h->precision = ST_PRECISION_BF16X3;
+        else if (!strcmp(e, "ffn_fp16x2")) h->precision = ST_PRECISION_FFN_FP16X2;
+    }
     *out = h;
     return 0;
 }
@@ -546,7 +550,7 @@ int st_set_engine(st_handle* h, int engine) {
 
 int st_set_precision(st_handle* h, int precision) {
     if (!h) return 1;
-    if (precision != ST_PRECISION_DEFAULT && precision != ST_PRECISION_FFN_FP16X2) return fail(h, "unknown precision mode");
+    if (precision != ST_PRECISION_BF16X3 && precision != ST_PRECISION_FFN_FP16X2) return fail(h, "unknown precision mode");
     h->drop_graphs();                  // cached graphs bake the kernel instances in
     h->precision = precision;
     return 0;

@@ -15,8 +15,7 @@
 //     reduced first and the max in use moves (O and l rescaled through tcgen05.ld/st) only when it is
 //     exceeded by 2^32 — one exp pass per block, never a retry;
 //   * P (split-bf16) overwrites the thread's own S columns in TMEM and is the A operand of P·V.
-// Two kernels: attention_tc5_kernel (default: Q also in TMEM, one O accumulator, per-block max exchange
-// between the two threads of a row) and attention_tc4_kernel (A/B: Q tile in shared memory, O_A / O_B).
+// attention_tc5_kernel: Q also in TMEM, one O accumulator, per-block max exchange between the two threads of a row.
 // Mask semantics: keys with mask == 0 get probability exactly 0; query rows with mask == 0 are written
 // as 0 (the reference multiplies them by the mask afterwards, :111).
 #include "common.cuh"
@@ -43,7 +42,6 @@ constexpr int AQ = 128;          // queries per CTA (TMEM lanes)
 constexpr int AK = 64;           // keys per block
 constexpr int DH = 64;
 constexpr int A_THREADS = 320;            // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (2 warps per TMEM lane quarter)
-constexpr int Q_BYTES = AQ * DH * 2;        // 16 KB per plane
 constexpr int K_BYTES = AK * DH * 2;        // 8 KB per plane
 constexpr int TMEM_COLS_ATT = 256;          // S0 [0,64) S1 [64,128) O_A [128,192) O_B [192,256)
 constexpr float LAZY4 = 32.0f;              // log2 domain: the running max moves only when a block max exceeds it by 2^32
@@ -100,13 +98,13 @@ __global__ void rope_split_kernel(const float* __restrict__ qkv, const float* __
 }
 
 // ==============================================================================================
-// v4: P in TENSOR MEMORY.  Each softmax thread overwrites its own 32 fp32 S columns with its packed split-bf16
+// P in TENSOR MEMORY (since v4; that kernel — Q tile in shared memory, O_A / O_B — was removed in round 2 once v5 had its
+// own ncu capture, profiles/r2q_*).  Each softmax thread overwrites its own 32 fp32 S columns with its packed split-bf16
 // P half-row (tcgen05.st) and the P·V MMAs take their A operand from TMEM (tcgen05.mma [d], [a_tmem], b_desc):
 // no P tile in shared memory, no generic->async proxy fence, no wait on the previous P·V before writing P (P
-// inherits S's double buffering).  The freed 32 KB double-buffer V, which removes the serial TMA-latency chain
-// pv_done -> V load -> P·V that bounded v3.  96 KB smem -> still two CTAs per SM.
+// inherits S's double buffering).  The freed shared memory double-buffers V, which removes the serial TMA-latency
+// chain pv_done -> V load -> P·V.
 // ==============================================================================================
-constexpr int ATT4_SMEM = 2 * Q_BYTES + 4 * K_BYTES + 4 * K_BYTES + 1024;
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -115,279 +113,6 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-
-// ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(A_THREADS, 2)
-attention_tc4_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);          // barriers + TMEM slot live in the alignment slack
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 160 + 1023) & ~uintptr_t(1023));
-    uint8_t* sQh = smem;                 uint8_t* sQl = sQh + Q_BYTES;
-    uint8_t* sK = sQl + Q_BYTES;         // ring of 2: [hi 8K | lo 8K]
-    uint8_t* sV = sK + 4 * K_BYTES;      // ring of 2: [hi 8K | lo 8K]
-    uint64_t *q_full = bars, *k_full = bars + 1 /*[2]*/, *k_empty = bars + 3 /*[2]*/, *v_full = bars + 5 /*[2]*/,
-             *v_empty = bars + 7 /*[2]*/, *pv_done = bars + 9, *s_full = bars + 10 /*[2]*/, *p_full = bars + 12;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-    if (sV + 4 * K_BYTES > smem_raw + ATT4_SMEM) __trap();           // dynamic smem base less aligned than assumed
-    pdl_trigger(); pdl_wait();         // (this kernel's prologue is tiny: wait up front, before the kvlen read)
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bb = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
-    const int b = bb % p.B;
-    const int kvlen = p.kvlen[b];
-    const int cq = h * DH, ck = p.H + h * DH, cv = 2 * p.H + h * DH;     // channel offsets of this head
-
-    if (q0 >= kvlen) {
-        // whole query tile is padding (or the utterance is empty): exact zeros, no pipeline needed
-        for (int i = threadIdx.x; i < AQ * (DH / 4); i += A_THREADS) {
-            const int r = i / (DH / 4), c4 = (i % (DH / 4)) * 4, t = q0 + r;
-            if (t < p.T) {
-                const long o = ((long)bb * p.T + t) * p.H + h * DH + c4;
-                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.out_hi) { *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(0, 0); *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(0, 0); }
-            }
-        }
-        return;
-    }
-    const int nb = (kvlen + AK - 1) / AK;
-
-    if (warp == 0 && lane == 0) {
-        for (int i = 0; i < 13; ++i) mbar_init(&bars[i], i == 12 ? 8 : 1);     // p_full: one arrive per softmax warp
-        mbar_fence_init();
-    }
-    if (warp == 1) tmem_alloc_1sm<TMEM_COLS_ATT>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_O = tmem_base + 128;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            mbar_expect_tx(q_full, 2 * Q_BYTES);
-            tma_load_3d(&maps.q_hi, q_full, sQh, cq, q0, bb);
-            tma_load_3d(&maps.q_lo, q_full, sQl, cq, q0, bb);
-            for (int j = 0; j < nb; ++j) {
-                const int slot = j & 1;
-                mbar_wait(&k_empty[slot], ((j >> 1) & 1) ^ 1);
-                mbar_expect_tx(&k_full[slot], 2 * K_BYTES);
-                tma_load_3d(&maps.kv_hi, &k_full[slot], sK + slot * 2 * K_BYTES, ck, j * AK, bb);
-                tma_load_3d(&maps.kv_lo, &k_full[slot], sK + slot * 2 * K_BYTES + K_BYTES, ck, j * AK, bb);
-                mbar_wait(&v_empty[slot], ((j >> 1) & 1) ^ 1);   // PV_{j-2} finished reading this V slot
-                mbar_expect_tx(&v_full[slot], 2 * K_BYTES);
-                uint8_t* sVh = sV + slot * 2 * K_BYTES; uint8_t* sVl = sVh + K_BYTES;
-                tma_load_3d(&maps.kv_hi, &v_full[slot], sVh, cv, j * AK, bb);
-                tma_load_3d(&maps.kv_lo, &v_full[slot], sVl, cv, j * AK, bb);
-            }
-        }
-    } else if (warp == 1) {
-        constexpr uint32_t idesc_s = att_idesc(false), idesc_pv = att_idesc(true);
-        constexpr uint64_t v_adv = (uint64_t)((16 * 128) >> 4);      // P·V k-step of 16 keys of the MN-major V tile: +2048 B
-        const uint64_t dQh = make_sw128_desc(smem_u32(sQh)), dQl = make_sw128_desc(smem_u32(sQl));
-        auto issue_S = [&](int j) {          // S_j -> TMEM buffer j&1, from K ring slot j&1
-            const int slot = j & 1;
-            const uint64_t dKh = make_sw128_desc(smem_u32(sK + slot * 2 * K_BYTES));
-            const uint64_t dKl = make_sw128_desc(smem_u32(sK + slot * 2 * K_BYTES + K_BYTES));
-            const uint32_t tS = tmem_base + slot * 64;
-#pragma unroll
-            for (int k = 0; k < DH / 16; ++k) {
-                const uint64_t adv = (uint64_t)(k * 2);
-                umma_bf16(tS, dQl + adv, dKh + adv, idesc_s, k != 0);
-                umma_bf16(tS, dQh + adv, dKl + adv, idesc_s, 1);
-                umma_bf16(tS, dQh + adv, dKh + adv, idesc_s, 1);
-            }
-            umma_commit(&k_empty[slot]);
-            umma_commit(&s_full[slot]);
-        };
-        mbar_wait(q_full, 0);
-        for (int j = 0; j < 2 && j < nb; ++j) {
-            mbar_wait(&k_full[j], 0);
-            tc_fence_after();
-            if (elect_one()) issue_S(j);
-            __syncwarp();
-        }
-        for (int j = 0; j < nb; ++j) {
-            mbar_wait(p_full, j & 1);
-            mbar_wait(&v_full[j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            if (elect_one()) {
-                // P_j lives in TMEM, aliased onto S_j: per 32-key half, columns [0,16) = hi, [16,32) = lo
-                // (16-bit A operand: lane = query row, two keys per 32-bit column)
-                const uint32_t tP = tmem_base + (j & 1) * 64;
-                const uint64_t dVh = make_sw128_desc(smem_u32(sV + (j & 1) * 2 * K_BYTES));
-                const uint64_t dVl = make_sw128_desc(smem_u32(sV + (j & 1) * 2 * K_BYTES + K_BYTES));
-#pragma unroll
-                for (int k = 0; k < AK / 16; ++k) {            // keys [0,32) -> O_A, keys [32,64) -> O_B
-                    const uint64_t va = (uint64_t)k * v_adv;
-                    const uint32_t tO = tmem_O + (k >> 1) * 64;
-                    const uint32_t aH = tP + (k >> 1) * 32 + (k & 1) * 8, aL = aH + 16;
-                    umma_bf16_ts(tO, aL, dVh + va, idesc_pv, (j != 0) || (k & 1));
-                    umma_bf16_ts(tO, aH, dVl + va, idesc_pv, 1);
-                    umma_bf16_ts(tO, aH, dVh + va, idesc_pv, 1);
-                }
-                umma_commit(&v_empty[j & 1]);
-                umma_commit(pv_done);
-            }
-            __syncwarp();
-            if (j + 2 < nb) {                // S buffer j&1 was consumed by softmax_j (implied by p_full_j)
-                mbar_wait(&k_full[j & 1], ((j + 2) >> 1) & 1);
-                tc_fence_after();
-                if (elect_one()) issue_S(j + 2);
-                __syncwarp();
-            }
-        }
-    } else {
-        // ================= softmax / epilogue: thread <-> (query row, key half) =================
-        const int wq = warp & 3;                       // TMEM lane quarter (warps w and w+4 share it)
-        const int half = (warp - 2) >> 2;              // 0: keys [0,32) of every block -> O_A, 1: keys [32,64) -> O_B
-        const int r = wq * 32 + lane;
-        const int t = q0 + r;
-        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        const uint32_t tOh = tmem_O + half * 64 + lane_addr;     // this thread's O accumulator row (64 columns)
-        const int prefix = p.prefix[b];
-        const float* mrow = p.mask + (long)b * p.T;
-        float m_used = -CUDART_INF_F, l_run = 0.f;
-        uint32_t v[32];
-
-        for (int j = 0; j < nb; ++j) {
-            const int k0 = j * AK + half * 32;
-            const uint32_t tS = tmem_base + (j & 1) * 64 + half * 32 + lane_addr;
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            // key validity of this half-block as a warp-uniform 32-bit word (only blocks reaching past the
-            // all-ones prefix of the mask need it; interior blocks skip the test entirely)
-            const bool need_mask = k0 + 32 > prefix;
-            uint32_t bits = 0xffffffffu;
-            if (need_mask) {
-                const int ka = k0 + lane;
-                bits = __ballot_sync(0xffffffffu, ka < kvlen && __ldg(mrow + min(ka, p.T - 1)) != 0.f);
-            }
-            // max first, then ONE exp pass (no optimistic retry): the row max of this half-block decides whether the
-            // running max moves.  It only moves when the block max exceeds the max in use by 2^LAZY4 — p and the
-            // partial sums stay far inside fp32/bf16 exponent range, so this is exact up to rounding and rare.
-            bool waited_pv = (j == 0);
-            auto load_scores = [&]() {
-                tmem_ld32(tS, v);
-                tmem_ld_wait();
-                if (need_mask) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) if (!((bits >> i) & 1u)) v[i] = 0xff800000u;     // -inf
-                }
-            };
-            load_scores();
-            float c0 = -CUDART_INF_F, c1 = -CUDART_INF_F;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                c0 = fmaxf(c0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-                c1 = fmaxf(c1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
-            }
-            const float cand = fmaxf(c0, c1);
-            if (__any_sync(0xffffffffu, cand > m_used + LAZY4)) {
-                const float m_new = (cand > m_used + LAZY4) ? cand : m_used;     // rows below the threshold keep their max
-                const float factor = (m_new == -CUDART_INF_F || m_used == -CUDART_INF_F) ? 1.f : ex2_approx(m_used - m_new);
-                l_run *= factor;                                                  // (m_used = -inf: l_run = 0, O = 0)
-                if (j > 0) {                 // rescale this half's O accumulator in TMEM: no PV may be in flight
-                    mbar_wait(pv_done, (j - 1) & 1);
-                    tc_fence_after();
-                    waited_pv = true;
-#pragma unroll 1
-                    for (int hh = 0; hh < 2; ++hh) {          // (v is the scratch: the scores are re-read below)
-                        tmem_ld32(tOh + hh * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
-                        tmem_st32(tOh + hh * 32, v);
-                    }
-                    tmem_st_wait();
-                    load_scores();
-                }
-                m_used = m_new;
-            }
-            uint32_t hw[16], lw[16];                          // packed P half-row: 32 keys x (hi, lo)
-            float psum;
-            {
-                const float m_eff = (m_used == -CUDART_INF_F) ? 0.f : m_used;
-                float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;   // short dependency chains
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float p0 = ex2_approx(__uint_as_float(v[i]) - m_eff), p1 = ex2_approx(__uint_as_float(v[i + 1]) - m_eff);
-                    const float p2 = ex2_approx(__uint_as_float(v[i + 2]) - m_eff), p3 = ex2_approx(__uint_as_float(v[i + 3]) - m_eff);
-                    ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
-                    split_bf16x2(p0, p1, hw[i / 2], lw[i / 2]);
-                    split_bf16x2(p2, p3, hw[i / 2 + 1], lw[i / 2 + 1]);
-                }
-                psum = (ps0 + ps1) + (ps2 + ps3);
-            }
-            l_run += psum;
-            // P_j overwrites this thread's own 32 S_j columns in TMEM (hi in [0,16), lo in [16,32)): no shared-memory
-            // round trip, no proxy fence, no wait on the previous P·V (S/P buffers are double-buffered with S)
-            {
-                uint32_t pk[32];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { pk[i] = hw[i]; pk[16 + i] = lw[i]; }
-                tmem_st32(tS, pk);
-                tmem_st_wait();
-            }
-            // Observe EVERY pv_done phase, in order, BEFORE signalling P_j: an mbarrier parity wait is only meaningful
-            // within one phase of the barrier, and P·V_j cannot be issued until this warp has arrived, so the barrier is
-            // at phase j-1 or j here — never further.  P·V_{j-1} was issued a whole softmax block ago (V is double
-            // buffered, so it did not wait for a load): this wait does not stall in steady state.
-            if (!waited_pv) mbar_wait(pv_done, (j - 1) & 1);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
-        }
-        // O_A and O_B complete after PV_{nb-1}; merge the two halves of every row exactly:
-        //   out = (O_A 2^(mA-m) + O_B 2^(mB-m)) / (lA 2^(mA-m) + lB 2^(mB-m)),  m = max(mA, mB)
-        mbar_wait(pv_done, (nb - 1) & 1);
-        tc_fence_after();
-        float2* xch = reinterpret_cast<float2*>(sQh);                     // all MMAs retired: the Q tile is free: [half][row] (m, l)
-        xch[half * AQ + r] = make_float2(m_used, l_run);
-        asm volatile("bar.sync 1, 256;" ::: "memory");                    // the 8 softmax warps only
-        const float2 oth = xch[(half ^ 1) * AQ + r];
-        const float mA = half ? oth.x : m_used, lA = half ? oth.y : l_run;
-        const float mB = half ? m_used : oth.x, lB = half ? l_run : oth.y;
-        const float mm = fmaxf(mA, mB);
-        const float fA = (mA == -CUDART_INF_F) ? 0.f : ex2_approx(mA - mm), fB = (mB == -CUDART_INF_F) ? 0.f : ex2_approx(mB - mm);
-        const float lsum = lA * fA + lB * fB;
-        const bool valid = t < p.T && mrow[min(t, p.T - 1)] != 0.f && lsum > 0.f;
-        const float inv = valid ? 1.0f / lsum : 0.f;
-        const float wA = fA * inv, wB = fB * inv;
-        // this thread emits output dims [32*half, 32*half + 32) of its row
-        uint32_t va[32];
-        tmem_ld32(tmem_O + lane_addr + half * 32, va);
-        tmem_ld32(tmem_O + 64 + lane_addr + half * 32, v);
-        tmem_ld_wait();
-        if (t < p.T) {
-            const long o = ((long)bb * p.T + t) * p.H + h * DH + half * 32;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(va[c * 8 + e]) * wA + __uint_as_float(v[c * 8 + e]) * wB;
-                const long oc = o + c * 8;
-                if (p.out_f32) {
-                    *reinterpret_cast<float4*>(p.out_f32 + oc) = make_float4(f[0], f[1], f[2], f[3]);
-                    *reinterpret_cast<float4*>(p.out_f32 + oc + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                }
-                if (p.out_hi) {
-                    uint32_t h4[4], l4[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) split_bf16x2(f[2 * e], f[2 * e + 1], h4[e], l4[e]);
-                    *reinterpret_cast<uint4*>(p.out_hi + oc) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-                    *reinterpret_cast<uint4*>(p.out_lo + oc) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc_1sm<TMEM_COLS_ATT>(tmem_base);
-    }
 }
 
 // ==============================================================================================
@@ -692,7 +417,7 @@ attention_tc5_kernel(const __grid_constant__ AttMaps maps, const AttParams p) {
 
 std::mutex g_att_mu;
 long long* g_att_trace = nullptr;
-std::atomic<uint64_t> g_att_attr4{0}, g_att_attr5{0};   // one bit per device
+std::atomic<uint64_t> g_att_attr5{0};   // one bit per device
 std::string g_att_err;
 
 }  // namespace
@@ -737,17 +462,12 @@ cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t s) {
         cudaMemsetAsync(g_att_trace, 0, 32 * 16 * sizeof(long long), s);
         p.trace = g_att_trace;
     }
-    static int use_v4 = -1;
-    if (use_v4 < 0) { const char* e = getenv("STABLETTS_B200_ATT_V4"); use_v4 = (e && !strcmp(e, "1")) ? 1 : 0; }
     {
-        cudaError_t e = ensure_dyn_smem(attention_tc4_kernel, ATT4_SMEM, g_att_attr4);
-        if (e == cudaSuccess) e = ensure_dyn_smem(attention_tc5_kernel, ATT5_SMEM, g_att_attr5);
+        cudaError_t e = ensure_dyn_smem(attention_tc5_kernel, ATT5_SMEM, g_att_attr5);
         if (e != cudaSuccess) { g_att_err = "cudaFuncSetAttribute failed for the attention kernels"; return e; }
     }
     dim3 grid((a.T + AQ - 1) / AQ, a.n_heads, a.BB);
-    if (use_v4)        // A/B only: Q tile in shared memory, O_A / O_B (v4)
-        return launch_k(attention_tc4_kernel, grid, dim3(A_THREADS), (size_t)ATT4_SMEM, s, maps, p);
-    return launch_k(attention_tc5_kernel, grid, dim3(A_THREADS), (size_t)ATT5_SMEM, s, maps, p);   // default (v5)
+    return launch_k(attention_tc5_kernel, grid, dim3(A_THREADS), (size_t)ATT5_SMEM, s, maps, p);
 }
 
 }  // namespace st

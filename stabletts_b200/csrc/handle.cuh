@@ -39,7 +39,7 @@ struct st_handle {
     void* vocos = nullptr;             // kind 2: st::VocosState (vocos_api.cu)
     int n_vocab = 0; float* emb = nullptr;
     int device = 0, engine = ST_ENGINE_TCGEN05, num_sms = 148;
-    int precision = ST_PRECISION_DEFAULT;
+    int precision = ST_PRECISION_FFN_FP16X2;
     std::string err;
     std::map<std::string, std::pair<float*, int64_t>> raw;   // name -> (device copy, numel)
     bool finalized = false;
