@@ -77,11 +77,12 @@ int st_set_engine(st_handle* h, int engine);
 /* Precision of the tensor-core engine's operands.
  *   ST_PRECISION_FFN_FP16X2 (the default since round 2): every contraction runs split-bf16 x 3 (hi / lo planes of both
  *     operands, three MMA passes, ~16 mantissa bits) EXCEPT the two k = 3 FFN convs of every DiT block
- *     (models/diffusion_transformer.py:20-30; 48-55 % of the FLOPs), which take their activations as ONE fp16 plane against
- *     fp16 hi / lo weights: two MMA passes and half the hidden-activation traffic.  Measured against the reference:
- *     2.0e-4 per estimator call, 1.3e-4 on the cfg1 solve, 2.9e-4 at n_mel = 128 / T = 1000, 2.4e-4 at T = 2000,
- *     4.1e-5 on the 150-evaluation cfg2 solve (tests/test_gpu_parity.py::test_ffn_fp16x2_margin_at_maximum_sizes holds
- *     every one of them under 5e-4 = 2x margin below the 1e-3 bar); -15 % time per solve.  Applies to problems large
+ *     (models/diffusion_transformer.py:20-30; 48-55 % of the FLOPs) and the three U-Net long-skip convs
+ *     (models/estimator.py:131-132), which take their activations as ONE fp16 plane against fp16 hi / lo weights: two MMA
+ *     passes and half the operand traffic.  Measured against the reference: 2.1e-4 per estimator call, 1.3e-4 on the cfg1
+ *     solve, 3.7e-4 at n_mel = 128 / T = 1000, 2.5e-4 at T = 2000, 4.3e-5 on the 150-evaluation cfg2 solve
+ *     (tests/test_gpu_parity.py::test_ffn_fp16x2_margin_at_maximum_sizes holds every one of them under 5e-4 = 2x margin
+ *     below the 1e-3 bar); -17 % time per solve.  Applies to problems large
  *     enough for the 2-CTA kernel; smaller ones run three passes everywhere.
  *   ST_PRECISION_BF16X3: three passes everywhere (measured 1e-5 .. 2.5e-5): the round-1 behaviour, for callers who want
  *     the widest margin.  The environment variable STABLETTS_B200_PRECISION=bf16x3|ffn_fp16x2 sets the initial mode. */

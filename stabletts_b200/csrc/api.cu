@@ -309,7 +309,7 @@ struct NextLn {                 // the LayerNorm that directly follows this bloc
 // `ln` describes LN1 for the separate kernel (plain, or FiLM·mask fused); with `ln1_done` the previous GEMM's epilogue has
 // already written U.  `fuse`: LN2 rides in O's epilogue, and `next` (if any) in conv_2's.
 int dit_block_core(st_handle* h, Workspace& w, int l, LnArgs ln, const float* ada_l, long ada_bs, int xb, const float* mask,
-                   cudaStream_t s, bool fuse = false, bool ln1_done = false, const NextLn* next = nullptr) {
+                   cudaStream_t s, bool fuse = false, bool ln1_done = false, const NextLn* next = nullptr, bool x16 = false) {
     const st_dims& d = h->d;
     const int H = d.hidden;
     const bool f16 = ffn16_on(h, w);   // LN2's U and the hidden activation travel as ONE fp16 plane (in the hi buffers)
@@ -364,6 +364,7 @@ int dit_block_core(st_handle* h, Workspace& w, int l, LnArgs ln, const float* ad
         GemmArgs g = base(EPI_BIAS | EPI_MASK | EPI_GATE | EPI_RESID);
         g.gate = ada_l + 5 * H; g.gate_bstride = ada_bs; g.resid = w.X[xb].f32;
         if (f16) g.prec = 1;
+        if (f16 && x16) g.out16 = 1;   // the residual stream's operand plane feeds a two-pass long-skip conv: ONE fp16 plane
         if (fuse && next) {
             g.ln = 1; g.ln_mask_out = 0; g.ln_shift = next->shift; g.ln_scale = next->scale;
             g.film2 = next->film2; g.film2_bstride = next->film2_bs; g.out2_f32 = next->x2_out;
@@ -388,11 +389,16 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
         return g;
     };
     const bool fuse = ln_fusion_on(h, w);
+    // two-pass precision: the long-skip convs (models/estimator.py:131-132) take their two A sources — the residual stream
+    // and the popped skip — as fp16 planes too, so every producer of those planes (in_proj, conv_2 of blocks 0..L-2) emits
+    // ONE fp16 plane; the last block's conv_2 keeps hi / lo for the three-pass final_proj
+    const bool f16 = ffn16_on(h, w);
     auto set_u = [&](GemmArgs& g) { g.ada_bstride = ada_bs; g.u_hi = w.U.hi; g.u_lo = w.U.lo; };
     // in_proj: x-half GEMM + hoisted P (cond rows P[b], uncond rows P[B])  [+ block 0's FiLM·mask and LN1 in the epilogue]
     {
         GemmArgs g = base(EPI_RESID);
         g.a_bmod = w.B; g.resid = w.P.f32; g.resid_clamp = w.B;
+        g.out16 = f16;
         if (fuse) {
             set_u(g);
             g.ln = 1; g.ln_shift = w.ada; g.ln_scale = w.ada + H;
@@ -419,6 +425,7 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
             xb = (cur == n_lsc) ? n_lsc + 1 : n_lsc;
             GemmArgs g = base(EPI_BIAS | EPI_FILM | EPI_MASK);
             g.film = film_l; g.film_bstride = film_bstride;
+            if (f16) g.prec = 1;
             if (fuse) { set_u(g); g.ln = 1; g.ln_shift = ada_l; g.ln_scale = ada_l + H; }
             Act out = w.X[xb]; out.hi = nullptr; out.lo = nullptr;     // consumed by LN only
             if (run_gemm(h, g, h->lsc[l - n_lsc], &w.X[cur], &w.X[sk], out, s, ST_PROF_GEMM_LSC)) return 1;
@@ -431,7 +438,7 @@ int estimator_eval(st_handle* h, Workspace& w, const Act& xin, const float* mask
             nx.film2 = film + (size_t)(l + 1) * 2 * H; nx.film2_bs = film_bstride; nx.x2_out = w.X[xb + 1].f32;
             nx.shift = w.ada + (size_t)(l + 1) * 6 * H; nx.scale = nx.shift + H;
         }
-        if (dit_block_core(h, w, l, ln, ada_l, ada_bs, xb, mask, s, fuse, fuse, has_next ? &nx : nullptr)) return 1;
+        if (dit_block_core(h, w, l, ln, ada_l, ada_bs, xb, mask, s, fuse, fuse, has_next ? &nx : nullptr, /*x16=*/l + 1 < L)) return 1;
         cur = xb;
     }
     {   // final_proj(x * mask) * mask (:136-137); x is already masked at this point
@@ -653,7 +660,10 @@ int st_finalize_weights(st_handle* h, void* stream) {
         if (get_raw(h, p + "block.adaLN_modulation.2.bias", 6 * H, &h->ada_b[l])) return 1;
     }
     for (int i = 0; i < L / 2; ++i)
+    {
         if (pack_gemm(h, &h->lsc[i], {"lsc_layers." + std::to_string(i)}, H, 2 * H, k, 0, 2 * H, true, s)) return 1;
+        if (pack_f16_planes(h, &h->lsc[i], s)) return 1;
+    }
     if (get_raw(h, "time_mlp.layer.0.weight", (int64_t)F * H, &h->tm0_w)) return 1;
     if (get_raw(h, "time_mlp.layer.0.bias", F, &h->tm0_b)) return 1;
     if (get_raw(h, "time_mlp.layer.2.weight", (int64_t)H * F, &h->tm2_w)) return 1;

@@ -272,7 +272,8 @@ static cudaError_t launch_tc2_bn(const Maps2& maps, const EpiMaps& em, Params2& 
             case EM_SILU:  return launch_tc2_inst<BN2, EM_SILU, 0, 1>(maps, em, p, pairs, s);
             case EM_LN:    return launch_tc2_inst<BN2, EM_LN, 0, 1>(maps, em, p, pairs, s);
             case EM_RESID: return launch_tc2_inst<BN2, EM_RESID, 0, 1>(maps, em, p, pairs, s);
-            default: g_err2 = "the two-pass fp16 precision is built for the FFN convs only (SiLU / residual epilogues)"; return cudaErrorInvalidValue;
+            case EM_PLAIN: return launch_tc2_inst<BN2, EM_PLAIN, 0, 1>(maps, em, p, pairs, s);      // long-skip conv without the fused LayerNorm
+            default: g_err2 = "the two-pass fp16 precision is built for the FFN and long-skip convs only"; return cudaErrorInvalidValue;
         }
     }
     switch (p.mode) {
