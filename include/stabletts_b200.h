@@ -142,6 +142,11 @@ int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const
                   const float* c_host, const float* fake_content_host, const float* fake_speaker_host,
                   float cfg_strength, const float* t_span_host, int n_steps, int method, int B, int T,
                   void* stream);
+/* The same with separate noise input and sample output buffers (a serving loop keeps its request buffers intact). */
+int st_solve_host_io(st_handle* h, const float* z_in_host, float* out_host, const float* mu_host, const float* mask_host,
+                     const float* c_host, const float* fake_content_host, const float* fake_speaker_host,
+                     float cfg_strength, const float* t_span_host, int n_steps, int method, int B, int T,
+                     void* stream);
 
 /* ---- caller-side glue: StableTTS.synthesise's duration -> alignment -> mu_y ----
  * Replaces models/model.py:83-85 + the cumsum of generate_path (:19):

@@ -18,7 +18,7 @@ ST_PROF_NCAT = len(ST_PROF_NAMES)
 EXPORTS = [
     "st_create", "st_destroy", "st_last_error", "st_version", "st_load_weight", "st_finalize_weights",
     "st_set_engine", "st_set_precision", "st_workspace_bytes", "st_attach_workspace", "st_estimator_forward", "st_cfm_loss", "st_solve",
-    "st_solve_host", "st_solve_adaptive", "st_solve_adaptive_ex", "st_align_lengths", "st_align_expand", "st_create_text_encoder", "st_text_encoder_forward", "st_create_vocos", "st_vocos_forward", "st_launch_count", "st_profile_begin", "st_profile_end", "st_test_gemm", "st_test_conv", "st_test_attention", "st_test_attention_trace", "st_test_gemm_trace", "st_bench_conv",
+    "st_solve_host", "st_solve_host_io", "st_solve_adaptive", "st_solve_adaptive_ex", "st_align_lengths", "st_align_expand", "st_create_text_encoder", "st_text_encoder_forward", "st_create_vocos", "st_vocos_forward", "st_launch_count", "st_profile_begin", "st_profile_end", "st_test_gemm", "st_test_conv", "st_test_attention", "st_test_attention_trace", "st_test_gemm_trace", "st_bench_conv",
 ]
 
 
@@ -77,6 +77,7 @@ def load_library() -> C.CDLL:
     lib.st_cfm_loss.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, C.c_float, f32p, f32p, i32, i32, vp]
     lib.st_solve.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, C.c_float, C.POINTER(C.c_float), i32, i32, i32, i32, vp]
     lib.st_solve_host.argtypes = lib.st_solve.argtypes
+    lib.st_solve_host_io.argtypes = [vp, f32p] + lib.st_solve.argtypes[1:]
     lib.st_solve_adaptive.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, C.c_float, C.c_double, C.c_double, C.c_double, C.c_double,
                                       i32, i32, i32, vp, C.POINTER(C.c_int64)]
     lib.st_solve_adaptive_ex.argtypes = [vp, i32] + lib.st_solve_adaptive.argtypes[1:]

@@ -1113,13 +1113,13 @@ int st_solve_adaptive(st_handle* h, float* z_inout, const float* mu, const float
                                 rtol, atol, max_steps, B, T, stream, stats);
 }
 
-int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const float* mask_host, const float* c_host,
+int st_solve_host_io(st_handle* h, const float* z_in_host, float* out_host, const float* mu_host, const float* mask_host, const float* c_host,
                   const float* fake_content_host, const float* fake_speaker_host, float cfg_strength,
                   const float* t_span_host, int n_steps, int method, int B, int T, void* stream) {
     if (!h) return 1;
     ST_ENTER(h);
     if (check_common(h, B, T)) return 1;
-    if (!z_inout_host || !mu_host || !mask_host || !c_host) return fail(h, "st_solve_host: null pointer");
+    if (!z_in_host || !out_host || !mu_host || !mask_host || !c_host) return fail(h, "st_solve_host: null pointer");
     const int cfg = (fake_content_host && fake_speaker_host) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     Workspace w;
@@ -1135,27 +1135,26 @@ int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const
         return at.type == cudaMemoryTypeHost;
     };
     const size_t sizes[6] = {n * 4, n * 4, (size_t)B * T * 4, (size_t)B * d.gin * 4, (size_t)d.n_mel * 4, (size_t)d.gin * 4};
-    const void* src[6] = {z_inout_host, mu_host, mask_host, c_host, cfg ? fake_content_host : nullptr, cfg ? fake_speaker_host : nullptr};
+    const void* src[6] = {z_in_host, mu_host, mask_host, c_host, cfg ? fake_content_host : nullptr, cfg ? fake_speaker_host : nullptr};
     void* dst[6] = {w.h_z, w.h_mu, w.h_mask, w.h_c, w.h_fc, w.h_fs};
     size_t need = 0;
     bool pinned_in[6];
     for (int i = 0; i < 6; ++i) { pinned_in[i] = !src[i] || is_pinned(src[i]); if (!pinned_in[i]) need += (sizes[i] + 255) & ~size_t(255); }
-    const bool z_pinned = pinned_in[0];
-    if (!z_pinned && need < ((n * 4 + 255) & ~size_t(255))) need = (n * 4 + 255) & ~size_t(255);
+    const bool out_pinned = is_pinned(out_host);
+    size_t out_off = 0;
+    if (!out_pinned) { out_off = need; need += (n * 4 + 255) & ~size_t(255); }     // the result is staged too
     if (need > h->pin_bytes) {
         if (h->pin_buf) { ST_CUDA(cudaStreamSynchronize(s)); cudaFreeHost(h->pin_buf); h->pin_buf = nullptr; h->pin_bytes = 0; }
         ST_CUDA(cudaMallocHost((void**)&h->pin_buf, need));
         h->pin_bytes = need;
     }
     size_t off = 0;
-    char* z_stage = nullptr;
     for (int i = 0; i < 6; ++i) {
         if (!src[i]) continue;
         const void* from = src[i];
         if (!pinned_in[i]) {
             memcpy(h->pin_buf + off, src[i], sizes[i]);
             from = h->pin_buf + off;
-            if (i == 0) z_stage = h->pin_buf + off;
             off += (sizes[i] + 255) & ~size_t(255);
         }
         ST_CUDA(cudaMemcpyAsync(dst[i], from, sizes[i], cudaMemcpyHostToDevice, s));
@@ -1163,10 +1162,17 @@ int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const
     if (st_solve(h, w.h_z, w.h_mu, w.h_mask, w.h_c, cfg ? w.h_fc : nullptr, cfg ? w.h_fs : nullptr, cfg_strength, t_span_host,
                  n_steps, method, B, T, stream))
         return 1;
-    ST_CUDA(cudaMemcpyAsync(z_pinned ? (void*)z_inout_host : (void*)z_stage, w.h_z, n * 4, cudaMemcpyDeviceToHost, s));
+    ST_CUDA(cudaMemcpyAsync(out_pinned ? (void*)out_host : (void*)(h->pin_buf + out_off), w.h_z, n * 4, cudaMemcpyDeviceToHost, s));
     ST_CUDA(cudaStreamSynchronize(s));
-    if (!z_pinned) memcpy(z_inout_host, z_stage, n * 4);
+    if (!out_pinned) memcpy(out_host, h->pin_buf + out_off, n * 4);
     return 0;
+}
+
+int st_solve_host(st_handle* h, float* z_inout_host, const float* mu_host, const float* mask_host, const float* c_host,
+                  const float* fake_content_host, const float* fake_speaker_host, float cfg_strength,
+                  const float* t_span_host, int n_steps, int method, int B, int T, void* stream) {
+    return st_solve_host_io(h, z_inout_host, z_inout_host, mu_host, mask_host, c_host, fake_content_host, fake_speaker_host, cfg_strength,
+                            t_span_host, n_steps, method, B, T, stream);
 }
 
 // ---- caller-side glue of the path; stateless: errors go to st_last_error(NULL) ----

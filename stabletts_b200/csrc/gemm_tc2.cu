@@ -202,7 +202,8 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiM
             if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);      // the LEADER's barrier gates the next MMA
             acc_phase ^= 1;
         }
-        if (lane == 0) bulk_wait0();                   // the TMA unit has drained this warp's staging before the CTA exits
+        if (lane == 0) bulk_wait_read0();              // the TMA unit has read this warp's staging before the CTA exits (the
+                                                       // global writes themselves complete with the grid)
     }
 
     tc_fence_before();

@@ -137,11 +137,12 @@ class CFMDecoder(nn.Module):
             out = torch.empty((B, M, T), dtype=torch.float32).pin_memory() if B * T > 0 else torch.empty((B, M, T))
         if tuple(out.shape) != (B, M, T) or out.dtype != torch.float32 or not out.is_contiguous() or out.device.type != "cpu":
             raise ValueError("out must be a contiguous fp32 CPU tensor of shape (B, n_mel, T)")
-        out.copy_(z.to(torch.float32).reshape(B, M, T))
         if B == 0 or T == 0:
+            out.copy_(z.to(torch.float32).reshape(B, M, T))
             return out
         f32 = lambda t, shape: t.detach().to(torch.float32).reshape(shape).contiguous()
         mu_, mask_, c_ = f32(mu, (B, M, T)), f32(mask, (B, T)), f32(c, (B, est.gin_channels))
+        z_ = f32(z, (B, M, T))                              # (no copy when z already is contiguous fp32: read in place)
         t_span = torch.linspace(0, 1, n_timesteps + 1, dtype=torch.float32)         # :46
         t_host = (C.c_float * (n_timesteps + 1))(*t_span.tolist())
         fc = fs = None
@@ -152,10 +153,10 @@ class CFMDecoder(nn.Module):
             strength = float(cfg_kwargs["cfg_strength"])
         with torch.cuda.device(dev):
             lib, h, stream = est._prepare(torch.empty(0, device=dev), B, T, 0 if fc is None else 1)
-            rc = lib.st_solve_host(h, out.data_ptr(), mu_.data_ptr(), mask_.data_ptr(), c_.data_ptr(),
+            rc = lib.st_solve_host_io(h, z_.data_ptr(), out.data_ptr(), mu_.data_ptr(), mask_.data_ptr(), c_.data_ptr(),
                                    None if fc is None else fc.data_ptr(), None if fs is None else fs.data_ptr(),
                                    strength, t_host, n_timesteps, method, B, T, stream)
-        _lib.check(lib, h, rc, "st_solve_host")
+        _lib.check(lib, h, rc, "st_solve_host_io")
         return out
 
     @torch.inference_mode()
