@@ -85,7 +85,9 @@ int st_set_engine(st_handle* h, int engine);
  *     below the 1e-3 bar); -17 % time per solve.  Applies to problems large
  *     enough for the 2-CTA kernel; smaller ones run three passes everywhere.
  *   ST_PRECISION_BF16X3: three passes everywhere (measured 1e-5 .. 2.5e-5): the round-1 behaviour, for callers who want
- *     the widest margin.  The environment variable STABLETTS_B200_PRECISION=bf16x3|ffn_fp16x2 sets the initial mode. */
+ *     the widest margin.  The environment variable STABLETTS_B200_PRECISION=bf16x3|ffn_fp16x2 sets the initial mode.
+ *   The adaptive solvers (st_solve_adaptive[_ex]) always evaluate the vector field in ST_PRECISION_BF16X3: their step-size
+ *   controller compares an error estimate with rtol = atol = 1e-5, below the two-pass mode's evaluation noise. */
 enum { ST_PRECISION_BF16X3 = 0, ST_PRECISION_FFN_FP16X2 = 1 };
 int st_set_precision(st_handle* h, int precision);
 

@@ -994,6 +994,14 @@ int st_solve_adaptive_ex(st_handle* h, int method, float* z_inout, const float* 
     const AdTab tb = adaptive_tableau(method);
     const int S = tb.S;
     int64_t nfe = 0, n_acc = 0, n_rej = 0;
+    // The step-size controller compares an embedded error estimate with rtol = atol = 1e-5: the two-pass FFN mode's
+    // evaluation noise (~2e-4 relative) would feed straight into that estimate, so adaptive solves evaluate the vector
+    // field with three passes everywhere, whatever the handle's precision mode (restored on every return path).
+    struct PrecisionGuard {
+        st_handle* h; int saved;
+        explicit PrecisionGuard(st_handle* h_) : h(h_), saved(h_->precision) { h->precision = ST_PRECISION_BF16X3; }
+        ~PrecisionGuard() { h->precision = saved; }
+    } precision_guard(h);
 
     if (precompute_cond(h, w, mu, mask, c, fake_content, fake_speaker, s)) return 1;
     // state buffers (token-major): y, y1 and S+1 stage derivatives rotate through Kst[]

@@ -175,3 +175,35 @@ def test_cuda_other_adaptive_solvers_vs_oracle(method, stages):
     assert max(e) < 1e-3, (method, e, stats, got)
     assert abs(got["accepted"] - stats["accepted"]) <= max(2, stats["accepted"] // 10), (stats, got)
     assert got["nfe"] == 2 + stages * (got["accepted"] + got["rejected"]) and got["solver"] == method
+
+
+@pytest.mark.gpu
+def test_adaptive_solves_ignore_the_two_pass_precision_mode():
+    """The adaptive controller compares an error estimate with rtol = atol = 1e-5, below the two-pass FFN mode's evaluation
+    noise: st_solve_adaptive_ex therefore evaluates the vector field with three passes whatever the handle's mode.  At a
+    batch large enough for the 2-CTA kernel the default-mode result must be BIT-identical to the bf16x3-mode result (and the
+    fixed-grid solve of the same problem must differ between the modes: proof that the mode is otherwise active)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as ge
+    ge.build()
+    from stabletts_b200 import CFMDecoder
+    dev = torch.device("cuda:0")
+    st = weights.make_state(cases.WEIGHT_SEED, 80)
+    for k in list(st):
+        if k.startswith("final_proj"):
+            st[k] = st[k] * 0.05
+    m = CFMDecoder(80, 80, 256, 80, 1024, 4, 6, 3, 0.1, 256).eval()
+    m.estimator.load_state_dict(st, strict=True)
+    m = m.to(dev)
+    inp = weights.make_inputs(63, [1024] * 19 + [700], 1024, 80)
+    a = [inp[k].to(dev) for k in ("mu", "mask", "c", "x")]
+    outs, fixed = {}, {}
+    for mode in ("ffn_fp16x2", "bf16x3"):
+        m.estimator.set_precision(mode)
+        outs[mode] = m(a[0], a[1], 10, 1.0, a[2], None, None, z=a[3]).cpu()
+        stats = dict(m.last_solver_stats)
+        fixed[mode] = m(a[0], a[1], 2, 1.0, a[2], "euler", None, z=a[3]).cpu()
+    assert torch.equal(outs["ffn_fp16x2"], outs["bf16x3"]), stats
+    assert not torch.equal(fixed["ffn_fp16x2"], fixed["bf16x3"])
+    assert stats["accepted"] >= 2 and torch.isfinite(outs["bf16x3"]).all()
