@@ -149,6 +149,9 @@ struct EpiCtx {
     // residual tiles through the TMA unit (kernels with a shallow main loop have the shared memory for it): two 4 KB
     // buffers per warp, one mbarrier each; phase bits persist across tiles (rphase is owned by the kernel's tile loop)
     uint32_t rbuf; uint64_t* rbar; uint32_t* rphase; int rb;
+    // single-wave launches (every CTA has at most one tile: the latency-bound small problems) let BOTH warp groups drain the
+    // same tile: group g takes chunks g, g + 2, ... (kstep = 2); otherwise a group owns whole tiles (kstep = 1)
+    int kstep;
 };
 
 template <bool ON>
@@ -243,8 +246,8 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const EpiMaps& em, 
         for (int q = 0; q < 8; ++q) bq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     tmem_ld_wait();
-    const bool has_next = kc + 1 < NCH && nb + 32 < p.N;
-    if (has_next) tmem_ld32(c.tacc + (uint32_t)(c0 + 32), vnext);     // next chunk's accumulator flies during this chunk's math
+    const bool has_next = kc + c.kstep < NCH && nb + 32 * c.kstep < p.N;
+    if (has_next) tmem_ld32(c.tacc + (uint32_t)(c0 + 32 * c.kstep), vnext);     // next chunk's accumulator flies during this chunk's math
     if (nb >= p.N) return;                             // warp-uniform: tile wider than the remaining columns
     if constexpr (RES && TRES) {                       // this chunk's residual tile has landed in shared memory (TMA)
         if (c.has_resid) {
@@ -318,7 +321,7 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const EpiMaps& em, 
             }
         }
         // the residual registers are dead now: the next chunk's residual row flies during the staging below
-        if constexpr (!TRES) { if (has_next) epi_load_resid<RES>(p, c, r, nb + 32); }
+        if constexpr (!TRES) { if (has_next) epi_load_resid<RES>(p, c, r, nb + 32 * c.kstep); }
     }
     if (trace) tk2 = clock64();
     if (p.has_f32) epi_store_f32(&em.o_f32, c, nb, x);
@@ -393,7 +396,8 @@ struct ResidPipe { uint32_t buf = 0; uint64_t* bar = nullptr; uint32_t phase = 0
 
 template <int BN, int MODE, bool TRES, class WaitFn>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& em, int bb, int t0, int n0, uint32_t tacc,
-                                              uint32_t stg, int lane, int tile_it, ResidPipe& rp, WaitFn wait_accumulator) {
+                                              uint32_t stg, int lane, int tile_it, ResidPipe& rp, int split_group,
+                                              WaitFn wait_accumulator) {
     using namespace ptx;
     using namespace epi;
     constexpr int NCH = BN / 32;
@@ -409,6 +413,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& 
     c.m = 1.f; c.mrow = 1.f; c.film = nullptr; c.gate = nullptr; c.resid_row = nullptr;
     c.s1 = 0.f; c.s2 = 0.f; c.kshift = 0.f;
     c.rbuf = rp.buf; c.rbar = rp.bar; c.rphase = &rp.phase; c.rb = min(bb, p.resid_clamp);
+    const int k0 = split_group >= 0 ? split_group : 0;          // first chunk of this warp
+    c.kstep = split_group >= 0 ? 2 : 1;
     float cs[32];                                      // RoPE: (cos, sin) x 16 of this frame
     float ra[32];                                      // residual row chunk, read by its own thread (16 B x 8 of one 128-byte line)
     if constexpr (ROPE) {
@@ -430,7 +436,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& 
                 if (NCH > 1 && n0 + 32 < p.N) epi_resid_issue(p, em, c, 1);
             }
         } else {
-            epi_load_resid<RES>(p, c, ra, n0);
+            epi_load_resid<RES>(p, c, ra, n0 + 32 * k0);
         }
     }
 
@@ -441,11 +447,11 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiMaps& 
     if (trace_tile) tt1 = clock64();
 
     uint32_t va[32], vb[32];
-    tmem_ld32(tacc, va);
+    tmem_ld32(tacc + (uint32_t)(32 * k0), va);
 #pragma unroll 1
-    for (int kc = 0; kc < NCH; kc += 2) {
+    for (int kc = k0; kc < NCH; kc += 2 * c.kstep) {
         epi_chunk<BN, MODE, TRES>(p, em, c, cs, kc, va, vb, ra);
-        epi_chunk<BN, MODE, TRES>(p, em, c, cs, kc + 1, vb, va, ra);
+        epi_chunk<BN, MODE, TRES>(p, em, c, cs, kc + c.kstep, vb, va, ra);
     }
 
     if constexpr (LN) {

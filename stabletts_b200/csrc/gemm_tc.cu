@@ -169,16 +169,18 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ EpiM
         if (lane == 0) {
             prefetch_tmap(&em.o_f32); prefetch_tmap(&em.o_hi); prefetch_tmap(&em.o_lo);
         }
-        const int acc = grp;
+        // single-wave launch (at most one tile per CTA): both groups drain THE tile, chunk-interleaved (latency, not throughput)
+        const bool split = p.total_tiles <= (int)gridDim.x;
+        const int acc = split ? 0 : grp;
         ResidPipe rp;                                  // unused here: residual rows are read by their own threads
-        int tile_it = grp; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, tile_it += 2) {
+        int tile_it = split ? 0 : grp; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x + (split ? 0 : grp * gridDim.x); tile < p.total_tiles; tile += 2 * gridDim.x, tile_it += 2) {
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
             const int bb = m_tile / p.m_tiles_per_b, t0 = (m_tile % p.m_tiles_per_b) * BLOCK_M + wq * 32;
             const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN);
             uint64_t* fb = &tmem_full[acc];
             const uint32_t ph = acc_phase;
-            epilogue_tile<BN, MODE, false>(p, em, bb, t0, n_tile * BN, tacc, stg, lane, tile_it, rp, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
+            epilogue_tile<BN, MODE, false>(p, em, bb, t0, n_tile * BN, tacc, stg, lane, tile_it, rp, split ? grp : -1, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);

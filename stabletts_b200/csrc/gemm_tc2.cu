@@ -187,16 +187,18 @@ gemm_tc2_kernel(const __grid_constant__ Maps2 maps, const __grid_constant__ EpiM
         }
         ResidPipe rp;
         if (SHALLOW) { rp.buf = smem_u32(smem + CF::RESID_OFF + (warp - 4) * 2 * 4096); rp.bar = resid_bar + 2 * (warp - 4); }
-        const int acc = grp;
-        int tile_it = grp; uint32_t acc_phase = 0;
-        for (int tile = cluster_id + grp * num_clusters; tile < p.total_tiles; tile += 2 * num_clusters, tile_it += 2) {
+        // single-wave launch (at most one tile per cluster): both groups drain THE tile, chunk-interleaved (latency, not throughput)
+        const bool split = MODE != EM_LN && !SHALLOW && p.total_tiles <= num_clusters;
+        const int acc = split ? 0 : grp;
+        int tile_it = split ? 0 : grp; uint32_t acc_phase = 0;
+        for (int tile = cluster_id + (split ? 0 : grp * num_clusters); tile < p.total_tiles; tile += 2 * num_clusters, tile_it += 2) {
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
             const int bb = m_tile / p.m_tiles_per_b;
             const int t0 = (m_tile % p.m_tiles_per_b) * (2 * BM) + (int)rank * BM + wq * 32;
             const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN2);
             uint64_t* fb = &tmem_full[acc];
             const uint32_t ph = acc_phase;
-            epilogue_tile<BN2, MODE, SHALLOW != 0>(p, em, bb, t0, n_tile * BN2, tacc, stg, lane, tile_it, rp, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
+            epilogue_tile<BN2, MODE, SHALLOW != 0>(p, em, bb, t0, n_tile * BN2, tacc, stg, lane, tile_it, rp, split ? grp : -1, [fb, ph]() { mbar_wait(fb, ph); tc_fence_after(); });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);      // the LEADER's barrier gates the next MMA
