@@ -220,10 +220,43 @@ int st::run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const
     g.taps = w.taps; g.N = w.N; g.Ktot = w.K;
     g.out_f32 = out.f32; g.out_hi = out.hi; g.out_lo = out.lo;
     if (out.C != w.N) return fail(h, "internal: GEMM N mismatch");
+    // Latency-bound small problems (the 1-CTA kernel with a handful of tiles, e.g. one 300-frame utterance): a long K loop
+    // on 12 SMs is serial time; cut it into slices that run side by side and sum them in a fixed order afterwards.
+    g.ksplit = 1; g.part = nullptr;    // callers reuse one GemmArgs for several GEMMs: the decision is per call
+    if (tc && !g.ln && !g.prec && !(g.flags & EPI_ROPE) && g.N % 4 == 0 && !gemm_tc2_runs(g, h->num_sms)) {
+        static int env = -1;
+        if (env < 0) { const char* e = getenv("STABLETTS_B200_SPLITK"); env = e ? atoi(e) : 1; }   // 0: off, 1: auto, 2..4: only that factor
+        const int kb = g.taps * ((g.Cs[0] + 63) / 64 + (g.n_src > 1 ? (g.Cs[1] + 63) / 64 : 0));
+        const long tiles = (long)g.BB * ((g.T + 127) / 128) * ((g.N + 127) / 128);
+        int S = 1;
+        for (int cand = 4; cand >= 2 && env; --cand)
+            if ((env == 1 || env == cand) && kb % cand == 0 && kb / cand >= 3 && tiles * cand <= h->num_sms) { S = cand; break; }
+        if (S > 1) {
+            const size_t need = (size_t)S * g.BB * g.T * g.N * sizeof(float);
+            if (need > h->part_bytes) {
+                if (h->part_buf) { ST_CUDA(cudaStreamSynchronize(s)); cudaFree(h->part_buf); h->part_buf = nullptr; h->part_bytes = 0; }
+                ST_CUDA(cudaMalloc((void**)&h->part_buf, need));
+                h->part_bytes = need;
+            }
+            g.ksplit = S; g.part = h->part_buf;
+            h->launches++;             // the reduce + epilogue kernel
+            if (getenv("STABLETTS_B200_DEBUG"))
+                fprintf(stderr, "[stabletts_b200] split-K x%d: BB %d T %d N %d K %d taps %d n_src %d a_bmod %d flags 0x%x\n", S, g.BB, g.T, g.N,
+                        g.Ktot, g.taps, g.n_src, g.a_bmod, g.flags);
+        }
+    }
     st_handle::ProfRec pr{prof_cat, 2.0 * g.BB * g.T * (double)g.N * g.Ktot * g.taps,
                           (double)g.BB * g.T * ((double)g.Ktot * 4 + (double)g.N * ((out.f32 ? 4 : 0) + (out.hi ? 4 : 0))), nullptr, nullptr};
     if (h->prof_on) { pr.e0 = h->take_event(); pr.e1 = h->take_event(); cudaEventRecord(pr.e0, s); }
     h->launches++;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("STABLETTS_B200_DEBUG"); dbg = e ? atoi(e) : 0; }
+    if (dbg >= 2) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        fprintf(stderr, "[stabletts_b200] gemm BB %d T %d N %d K %d taps %d flags 0x%x ln %d prec %d ksplit %d (before: %s) ... ", g.BB, g.T, g.N,
+                g.Ktot, g.taps, g.flags, g.ln ? 1 : 0, g.prec, g.ksplit, cudaGetErrorString(e));
+        fflush(stderr);
+    }
     if (tc) {
         cudaError_t e = launch_gemm_tc(g, h->num_sms, s);
         if (e != cudaSuccess) return fail(h, std::string("tcgen05 GEMM launch failed: ") + cudaGetErrorString(e) + " / " + gemm_tc_last_error());
@@ -231,6 +264,7 @@ int st::run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const
         cudaError_t e = launch_gemm_simt(g, s);
         if (e != cudaSuccess) return fail(h, std::string("SIMT GEMM launch failed: ") + cudaGetErrorString(e));
     }
+    if (dbg >= 2) { cudaError_t e = cudaStreamSynchronize(s); fprintf(stderr, "%s\n", cudaGetErrorString(e)); }
     if (h->prof_on) { cudaEventRecord(pr.e1, s); h->prof.push_back(pr); }
     return 0;
 }
@@ -540,6 +574,7 @@ int st_destroy(st_handle* h) {
     for (void* p : h->owned) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->kind == 2) vocos_free(h);
+    if (h->part_buf) cudaFree(h->part_buf);
     if (h->ws_ptr && h->ws_owned) cudaFree(h->ws_ptr);
     if (h->pin_buf) cudaFreeHost(h->pin_buf);
     }

@@ -73,10 +73,16 @@ struct GemmArgs {
     // each k-step issues A16·Wlo + A16·Whi (kind::f16 with fp16 operands).  out16: the split output becomes one fp16 plane
     // written to out_hi (out_lo ignored); u16: likewise for the fused LayerNorm output u_hi.
     int prec = 0, out16 = 0, u16 = 0;
+    // split-K for latency-bound small problems (1-CTA kernel): the K loop (taps x channel blocks) is cut into `ksplit`
+    // slices that run as ksplit x BB "batches" writing raw fp32 partial tiles into `part` ((ksplit*BB, T, N)); a reduce
+    // kernel then sums the slices in a fixed order and applies this GemmArgs' epilogue (launch_splitk_reduce).  Deterministic.
+    int ksplit = 1; float* part = nullptr;
 };
 
 // engines
 cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t s);
+// out = epilogue(sum_s part[s]) with g's flags (bias, SiLU / GELU, FiLM, mask, gate, residual) -> fp32 and / or split planes
+cudaError_t launch_splitk_reduce(const GemmArgs& g, cudaStream_t s);
 // returns cudaErrorNotSupported if the tensor-map driver entry point is unavailable
 cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s);
 const char* gemm_tc_last_error();

@@ -43,6 +43,7 @@ struct TcParams {
     int ln_mask_out, has_film2;
     const float *ln_shift, *ln_scale, *film2;
     long ada_bstride, film2_bstride;
+    int ksplit, split_bb;             // split-K (1-CTA kernel): batch index = slice * split_bb + real batch; slice picks the K range
     long long* dbg;                   // debug: clock64 stamps of one epilogue warp (STABLETTS_B200_EPI_TRACE=1), else nullptr
 };
 
@@ -67,6 +68,7 @@ inline void fill_tc_params(TcParams& p, const GemmArgs& g) {
     p.ln_shift = g.ln_shift; p.ln_scale = g.ln_scale; p.film2 = g.film2;
     p.ada_bstride = g.ada_bstride; p.film2_bstride = g.film2_bstride;
     p.dbg = nullptr;
+    p.ksplit = 1; p.split_bb = g.BB;
     static int tap_outer = -1;
     if (tap_outer < 0) { const char* e = getenv("STABLETTS_B200_TAP_OUTER"); tap_outer = (e && e[0] == '1') ? 1 : 0; }
     p.tap_outer = tap_outer;

@@ -88,6 +88,57 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
     }
 }
 
+// Second half of a split-K conv-GEMM: sums the ksplit raw partial tiles in slice order (deterministic) and applies the
+// epilogue of the SIMT engine above; one thread per 4 consecutive channels of a frame.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmArgs g) {
+    pdl_trigger(); pdl_wait();
+    const long n4 = g.N / 4;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)g.BB * g.T * n4) return;
+    const int n = (int)(i % n4) * 4;
+    const long row = i / n4;
+    const int bb = (int)(row / g.T), t = (int)(row - (long)bb * g.T);
+    const long o = row * g.N + n;
+    const long slice = (long)g.BB * g.T * g.N;
+    float4 a = *reinterpret_cast<const float4*>(g.part + o);
+    for (int s = 1; s < g.ksplit; ++s) {
+        const float4 b = *reinterpret_cast<const float4*>(g.part + s * slice + o);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float v[4] = {a.x, a.y, a.z, a.w};
+    const int mb = bb % g.B;
+    const float m = (g.flags & EPI_MASK) ? g.mask[(long)mb * g.T + t] : 1.f;
+    const float* film = (g.flags & EPI_FILM) ? g.film + (long)mb * g.film_bstride : nullptr;
+    const float* gate = (g.flags & EPI_GATE) ? g.gate + (long)min(bb, g.c_clamp) * g.gate_bstride : nullptr;
+    const float* resid = (g.flags & EPI_RESID) ? g.resid + ((long)min(bb, g.resid_clamp) * g.T + t) * g.N : nullptr;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float x = v[e];
+        if (g.flags & EPI_BIAS) x += g.bias[n + e];
+        if (g.flags & EPI_SILU) x = silu_f(x);
+        else if (g.flags & EPI_GELU) x = gelu_f(x);
+        if (g.flags & EPI_FILM) x = film[n + e] * x + film[g.film_H + n + e];
+        if (g.flags & EPI_MASK) x *= m;
+        if (g.flags & EPI_GATE) x *= gate[n + e];
+        if (g.flags & EPI_RESID) x += resid[n + e];
+        v[e] = x;
+    }
+    if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+    if (g.out_hi) {
+        uint32_t h01, l01, h23, l23;
+        split_bf16x2(v[0], v[1], h01, l01); split_bf16x2(v[2], v[3], h23, l23);
+        *reinterpret_cast<uint2*>(g.out_hi + o) = make_uint2(h01, h23);
+        *reinterpret_cast<uint2*>(g.out_lo + o) = make_uint2(l01, l23);
+    }
+}
+
+cudaError_t launch_splitk_reduce(const GemmArgs& g, cudaStream_t s) {
+    if (g.N % 4 || !g.part || g.ksplit < 2) return cudaErrorInvalidValue;
+    const long n = (long)g.BB * g.T * (g.N / 4);
+    if (n == 0) return cudaSuccess;
+    return launch_k(splitk_reduce_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, g);
+}
+
 cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t s) {
     if (g.BB == 0 || g.T == 0) return cudaSuccess;
     for (int i = 0; i < g.n_src; ++i)

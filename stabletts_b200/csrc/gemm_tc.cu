@@ -105,11 +105,13 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ EpiM
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
                 const int bb = m_tile / p.m_tiles_per_b, t0 = (m_tile % p.m_tiles_per_b) * BLOCK_M;
-                const int ab = bb % p.a_bmod, n0 = n_tile * BN;
+                const int ab = (bb % p.split_bb) % p.a_bmod, n0 = n_tile * BN;
+                const int it_per = (num_kb + p.ksplit - 1) / p.ksplit;         // split-K: this "batch" owns one slice of the K loop
+                const int it0 = (bb / p.split_bb) * it_per, it1 = min(num_kb, it0 + it_per);
                 // channel block OUTER, tap INNER: the k taps of one channel block read the same A rows shifted by one
                 // frame, back to back, so taps 1.. hit L2 (tap-outer order re-read the whole A slab from HBM per tap)
                 // (p.tap_outer = 1 restores the old order for A/B runs: STABLETTS_B200_TAP_OUTER=1)
-                for (int it = 0; it < num_kb; ++it) {
+                for (int it = it0; it < it1; ++it) {
                     {
                         const int kb = p.tap_outer ? it % kb_per_tap : it / p.taps;
                         const int tap = p.tap_outer ? it / kb_per_tap : it % p.taps;
@@ -137,7 +139,14 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ EpiM
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            int n_it = num_kb;
+            if (p.ksplit > 1) {
+                const int bb = (tile / p.n_tiles) / p.m_tiles_per_b;
+                const int it_per = (num_kb + p.ksplit - 1) / p.ksplit;
+                const int it0 = (bb / p.split_bb) * it_per;
+                n_it = min(num_kb, it0 + it_per) - it0;
+            }
+            for (int kb = 0; kb < n_it; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 if (elect_one()) {
@@ -154,7 +163,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ EpiM
                     }
                     // commits are issued by the SAME thread that issued the MMAs
                     umma_commit(&empty_bar[stage]);                       // frees this smem stage when its MMAs retire
-                    if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
+                    if (kb == n_it - 1) umma_commit(&tmem_full[acc]);     // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -274,7 +283,7 @@ cudaError_t launch_inst(const TcMaps& maps, const EpiMaps& em, const TcParams& p
 }
 
 template <int BN>
-cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t s) {
+cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t s, int split_bb = 0) {
     using C = Cfg<BN>;
     TcMaps maps;
     for (int i = 0; i < g.n_src; ++i) {
@@ -288,6 +297,7 @@ cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t s) {
     if (!build_epi_maps(g, &em)) { if (g_err.empty()) g_err = "epilogue store maps: missing output plane"; return cudaErrorInvalidValue; }
     TcParams p;
     fill_tc_params(p, g);
+    if (split_bb > 0) { p.ksplit = g.ksplit; p.split_bb = split_bb; }
     p.m_tiles_per_b = (g.T + BLOCK_M - 1) / BLOCK_M;
     p.n_tiles = (g.N + BN - 1) / BN;
     p.total_tiles = g.BB * p.m_tiles_per_b * p.n_tiles;
@@ -414,6 +424,18 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s) {
     if (!g.W_hi || !g.W_lo || g.Ktot % 8 || g.N % 8) { g_err = "bad weight operand"; return cudaErrorInvalidValue; }
     // one tile shape here: 128 x 128 (a 128 x 256 1-CTA tile with two smem stages was TMA-latency bound, profiles/r1a;
     // the wide tile is the 2-CTA kernel's)
+    if (g.ksplit > 1) {                // split-K: raw fp32 partial tiles of ksplit x BB "batches", then the reduce + epilogue kernel
+        if (!g.part || (g.flags & EPI_ROPE)) { g_err = "split-K needs a partial buffer and a non-RoPE epilogue"; return cudaErrorInvalidValue; }
+        const int nkb = g.taps * ((g.Cs[0] + BLOCK_K - 1) / BLOCK_K + (g.n_src > 1 ? (g.Cs[1] + BLOCK_K - 1) / BLOCK_K : 0));
+        if (nkb % g.ksplit) {          // an empty K slice would never complete its accumulator: refuse instead of hanging
+            g_err = "split-K factor does not divide the K loop"; return cudaErrorInvalidValue;
+        }
+        GemmArgs q = g;
+        q.BB = g.ksplit * g.BB; q.flags = 0; q.out_f32 = g.part; q.out_hi = nullptr; q.out_lo = nullptr; q.ksplit = g.ksplit;
+        cudaError_t e = launch_bn<128>(q, num_sms, s, g.BB);
+        if (e != cudaSuccess) return e;
+        return launch_splitk_reduce(g, s);
+    }
     return launch_bn<128>(g, num_sms, s);
 }
 

@@ -56,6 +56,7 @@ struct st_handle {
     std::vector<std::string> graph_seen;   // keys enqueued directly once (kernels loaded, attributes set) before capture
     double* pinned = nullptr;          // 16 B of pinned host memory: norm read-back of the adaptive controller
     char* pin_buf = nullptr; size_t pin_bytes = 0;   // pinned staging of st_solve_host for callers with pageable buffers
+    float* part_buf = nullptr; size_t part_bytes = 0;   // split-K partial tiles of latency-bound small GEMMs (run_gemm)
     cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the caller's may be the legacy stream)
     int graph_mode = -1;               // -1: read STABLETTS_B200_GRAPH on first use; 0 off; 1 always; 2 auto (small problems)
     void drop_graphs() { for (auto& g : graphs) cudaGraphExecDestroy(g.exec); graphs.clear(); }

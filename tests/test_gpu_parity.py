@@ -256,6 +256,24 @@ def test_long_and_wide_shapes_vs_oracle(dev):
         assert float((out.cpu() * (1 - inp["mask"])).abs().max()) == 0.0
 
 
+def test_split_k_small_problems_vs_oracle(dev):
+    """Latency-bound small problems run their long-K GEMMs (FFN conv_2, long-skip and cond convs) as split-K slices plus a
+    reduce kernel; the factor follows the tile count: T = 300 alone -> 4, two utterances at T = 1316 -> 3 (the case whose
+    stale factor once left an empty K slice and hung), four utterances at T = 1000 -> 2.  Each against the oracle, and bit-identical when
+    repeated (the slices are summed in a fixed order)."""
+    st = weights.make_state(cases.WEIGHT_SEED, 80)
+    m = model_for(80, "tcgen05", dev)
+    for lengths, T, seed in [([300], 300, 71), ([1316, 1207], 1316, 72), ([1000, 990, 700, 512], 1000, 73)]:
+        inp = weights.make_inputs(seed, lengths, T, 80, t_per_sample=True)
+        with torch.inference_mode():
+            ref = R.estimator_forward(st, inp["t"], inp["x"], inp["mask"], inp["mu"], inp["c"])
+        args = [inp[k].to(dev) for k in ("t", "x", "mask", "mu", "c")]
+        out = m.estimator(*args)
+        e = rel_errs(out, ref)
+        assert max(e) < 1e-3, (lengths, e)
+        assert torch.equal(out, m.estimator(*args))
+
+
 def test_empty_and_zero_length_inputs(dev):
     """Edge cases: an empty batch and zero frames return empty tensors like the reference's modules do; an utterance
     of length 0 inside a batch (all-zero mask row) yields exact zeros for that row and leaves the others untouched."""
