@@ -231,13 +231,20 @@ int st::run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const
         int S = 1;
         for (int cand = 4; cand >= 2 && env; --cand)
             if ((env == 1 || env == cand) && kb % cand == 0 && kb / cand >= 3 && tiles * cand <= h->num_sms) { S = cand; break; }
-        if (S > 1) {
-            const size_t need = (size_t)S * g.BB * g.T * g.N * sizeof(float);
-            if (need > h->part_bytes) {
-                if (h->part_buf) { ST_CUDA(cudaStreamSynchronize(s)); cudaFree(h->part_buf); h->part_buf = nullptr; h->part_bytes = 0; }
-                ST_CUDA(cudaMalloc((void**)&h->part_buf, need));
-                h->part_bytes = need;
+        if (S > 1 && !h->part_buf) {
+            // S x tiles <= num_sms tiles of at most 128 x 128 fp32: one buffer of num_sms x 64 KB (9.7 MB) covers every
+            // eligible shape, so it is allocated once and never moves (captured graphs keep pointing at it).  Not inside a
+            // stream capture (cudaMalloc is not capturable): that call runs unsplit.
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            ST_CUDA(cudaStreamIsCapturing(s, &cap));
+            if (cap != cudaStreamCaptureStatusNone) S = 1;
+            else {
+                h->part_bytes = (size_t)h->num_sms * 128 * 128 * sizeof(float);
+                ST_CUDA(cudaMalloc((void**)&h->part_buf, h->part_bytes));
             }
+        }
+        if (S > 1) {
+            if ((size_t)S * g.BB * g.T * g.N * sizeof(float) > h->part_bytes) return fail(h, "internal: split-K partial buffer too small");
             g.ksplit = S; g.part = h->part_buf;
             h->launches++;             // the reduce + epilogue kernel
             if (getenv("STABLETTS_B200_DEBUG"))

@@ -272,6 +272,15 @@ def test_split_k_small_problems_vs_oracle(dev):
         e = rel_errs(out, ref)
         assert max(e) < 1e-3, (lengths, e)
         assert torch.equal(out, m.estimator(*args))
+    # graph replay of a split-K solve stays valid while other small shapes use the (fixed, never re-allocated) partial buffer
+    a = weights.make_inputs(74, [300], 300)
+    b = weights.make_inputs(75, [700, 650], 700)
+    solve = lambda i: m(i["mu"].to(dev), i["mask"].to(dev), 3, 1.0, i["c"].to(dev), "euler", None, z=i["x"].to(dev)).cpu()
+    first = [solve(a) for _ in range(3)]                     # direct, capture, replay
+    other = solve(b)
+    again = solve(a)                                        # replay after another shape ran in between
+    assert all(torch.equal(first[0], o) for o in first[1:] + [again])
+    assert torch.equal(other, solve(b))
 
 
 def test_empty_and_zero_length_inputs(dev):
