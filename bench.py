@@ -480,8 +480,10 @@ def run_config(args, name, model, dev, rank, world, steps, warmup, flush, *, ful
         n = _lib.ST_PROF_NCAT
         ms_a, fl_a, by_a, ln_a = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
         lib.st_profile_end(h, ms_a, fl_a, by_a, ln_a)
-        prof = {nm: dict(ms=ms_a[i], flops=fl_a[i], bytes=by_a[i], launches=int(ln_a[i])) for i, nm in enumerate(_lib.ST_PROF_NAMES)}
-        prof["gemm"] = {k: sum(v[k] for n_, v in prof.items() if n_.startswith("gemm_")) for k in ("ms", "flops", "bytes", "launches")}
+        is_a = (C.c_double * n)()
+        lib.st_profile_issued(h, is_a)
+        prof = {nm: dict(ms=ms_a[i], flops=fl_a[i], bytes=by_a[i], launches=int(ln_a[i]), issued=is_a[i]) for i, nm in enumerate(_lib.ST_PROF_NAMES)}
+        prof["gemm"] = {k: sum(v[k] for n_, v in prof.items() if n_.startswith("gemm_")) for k in ("ms", "flops", "bytes", "launches", "issued")}
         res["prof"] = prof
     if world > 1:
         dist.barrier()
@@ -667,6 +669,10 @@ def main():
                      "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
                      "traffic_note": "dram__bytes_read+write per launch, mean over the ncu --set full capture in profiles/gemm_traffic.json",
                      "achieved_per_launch_gflop": gm["flops"] / max(gm["launches"], 1) / 1e9,
+                     "issued_tflops": gm.get("issued", 0.0) / max(gm["ms"], 1e-9) / 1e9,
+                     "issued_frac": gm.get("issued", 0.0) / max(gm["ms"], 1e-9) / 1e9 / peak_tf,
+                     "issued_note": "tensor-core FLOPs actually issued (MMA passes x algorithmic, st_profile_issued) / the same time / the same "
+                                    "peak: the tensor-pipe utilisation behind the algorithmic `frac`",
                      "peak_source": peak_src, "launches": gm["launches"], "kernel_ms_per_step": gm["ms"],
                      "note": "algorithmic FLOPs (2*rows*N*K*taps); the bf16x3 split issues 3 MMAs per algorithmic MAC"
                              + (", the FFN convs 2 (fp16 activations x fp16 hi/lo weights)" if args.precision == "ffn_fp16x2" else ""),
@@ -694,7 +700,8 @@ def main():
                 "precision": other["precision"], "value": other["frames"] * n2 / (other["ms_dev"] * 1e-3), "unit": "frames/s",
                 "ms_per_step": other["ms_dev"] / n2, "e2e_ms_per_step": other["ms_e2e"] / n2, "parity": other.get("parity"),
                 "roofline": {"achieved": o_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": o_tf / peak_tf,
-                             "note": "same algorithmic FLOPs; the FFN convs issue 2 MMAs per MAC in ffn_fp16x2 mode, 3 in default"},
+                             "issued_frac": og.get("issued", 0.0) / max(og["ms"], 1e-9) / 1e9 / peak_tf,
+                             "note": "same algorithmic FLOPs; the FFN and long-skip convs issue 2 MMAs per MAC in ffn_fp16x2 mode, 3 in bf16x3"},
                 "breakdown_ms_per_step": {k: round(v["ms"], 3) for k, v in other["prof"].items()},
                 "note": "the other st_set_precision mode measured on the same box right after the headline run; the headline (value, e2e) is the --precision mode"}
     print(json.dumps(line), flush=True)

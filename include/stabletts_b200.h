@@ -198,6 +198,11 @@ enum { ST_PROF_GEMM = 0 /* in_proj, final_proj, test hooks */, ST_PROF_ATTN = 1 
        ST_PROF_GEMM_COND = 8 /* per-solve cond_proj + in_proj mu-half */, ST_PROF_NCAT = 9 };
 int st_profile_begin(st_handle* h);
 int st_profile_end(st_handle* h, double* ms, double* flops, double* bytes, int64_t* launches);
+/* Tensor-core FLOPs ISSUED per class by the launches of the last st_profile_begin/end bracket (ST_PROF_NCAT entries):
+ * algorithmic FLOPs x the number of MMA passes of the operand precision (3 for split-bf16, 2 for the fp16 two-pass
+ * convs; 0 for classes without tcgen05 GEMM launches).  issued / time against the bf16 peak is the tensor-pipe
+ * utilisation; flops / time is the algorithmic roofline figure. */
+int st_profile_issued(st_handle* h, double* issued);
 
 /* ---- kernel-level test hooks (used by tests/ only; same kernels the path uses) ------------- */
 

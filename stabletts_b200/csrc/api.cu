@@ -254,6 +254,7 @@ int st::run_gemm(st_handle* h, GemmArgs& g, const GemmW& w, const Act* a0, const
     }
     st_handle::ProfRec pr{prof_cat, 2.0 * g.BB * g.T * (double)g.N * g.Ktot * g.taps,
                           (double)g.BB * g.T * ((double)g.Ktot * 4 + (double)g.N * ((out.f32 ? 4 : 0) + (out.hi ? 4 : 0))), nullptr, nullptr};
+    if (tc) pr.issued = pr.flops * (g.prec ? 2.0 : 3.0);   // split operands: A_lo*W_hi + A_hi*W_lo + A_hi*W_hi, or A16*W_lo + A16*W_hi
     if (h->prof_on) { pr.e0 = h->take_event(); pr.e1 = h->take_event(); cudaEventRecord(pr.e0, s); }
     h->launches++;
     static int dbg = -1;
@@ -618,13 +619,20 @@ int st_profile_end(st_handle* h, double* ms, double* flops, double* bytes, int64
     h->prof_on = false;
     ST_ENTER(h);
     ST_CUDA(cudaDeviceSynchronize());
-    for (int i = 0; i < ST_PROF_NCAT; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+    for (int i = 0; i < ST_PROF_NCAT; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; h->prof_issued[i] = 0; }
     for (auto& r : h->prof) {
         float t = 0.f;
         ST_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
         ms[r.cat] += t; flops[r.cat] += r.flops; bytes[r.cat] += r.bytes; launches[r.cat] += 1;
+        h->prof_issued[r.cat] += r.issued;
     }
     h->prof.clear(); h->ev_used = 0;
+    return 0;
+}
+
+int st_profile_issued(st_handle* h, double* issued) {
+    if (!h || !issued) return 1;
+    for (int i = 0; i < ST_PROF_NCAT; ++i) issued[i] = h->prof_issued[i];
     return 0;
 }
 

@@ -62,7 +62,9 @@ struct st_handle {
     void drop_graphs() { for (auto& g : graphs) cudaGraphExecDestroy(g.exec); graphs.clear(); }
     // optional per-launch CUDA-event profiling (bench.py roofline): category, flops, bytes, event pair
     bool prof_on = false;
-    struct ProfRec { int cat; double flops, bytes; cudaEvent_t e0, e1; };
+    struct ProfRec { int cat; double flops, bytes; cudaEvent_t e0, e1; double issued = 0; };   // issued: tensor-core FLOPs actually
+                                                                                             // issued (passes x algorithmic), 0 = not an MMA launch
+    double prof_issued[16] = {0};                       // per class, filled by st_profile_end (st_profile_issued reads it)
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
     cudaEvent_t take_event() {
