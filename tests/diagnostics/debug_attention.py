@@ -1,5 +1,5 @@
 import os, sys, ctypes as C
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from stabletts_b200 import CFMDecoder, _lib
 from oracle import estimator_ref as R

@@ -1,7 +1,7 @@
 """Debug helper: the 20 x 1024-frame estimator call of smoke() with STABLETTS_B200_FUSE_LN=0/1 (separate processes), error of
 each against the oracle on rows {0, 7, 19} and the difference between the two, located by frame / channel."""
 import os, subprocess, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 

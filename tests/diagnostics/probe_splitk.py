@@ -1,7 +1,7 @@
 """Debug probe for the split-K path (STABLETTS_B200_DEBUG=2 synchronises around every GEMM of a solve and prints its shape):
-python profiles/probe_splitk.py B T [cfg]   — one 2-step Euler solve of seeded inputs, prints DONE when the device finished."""
+python tests/diagnostics/probe_splitk.py B T [cfg]   — one 2-step Euler solve of seeded inputs, prints DONE when the device finished."""
 import os, sys
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch
 from oracle import cases, weights      # test infrastructure: seeded weights / inputs only
 from stabletts_b200 import CFMDecoder
