@@ -35,6 +35,21 @@ def test_tableau_matches_an_independent_implementation():
     assert abs(sum(AD.C_ERROR)) < 1e-15                               # both weight sets sum to one
 
 
+def test_bosh3_tableau_matches_scipy_rk23():
+    """Bogacki–Shampine 3(2): nodes, stage matrix, 3rd-order weights AND the embedded error weights against scipy's RK23
+    (scipy stores E = low - high, torchdiffeq high - low: equal up to the sign, which the error norm ignores)."""
+    import numpy as np
+    from scipy.integrate._ivp.rk import RK23
+    tb = AD.TABLEAUS["bosh3"]
+    assert np.allclose(RK23.C[1:], tb.alpha[:2]) and tb.alpha[2] == 1.0
+    for i, row in enumerate(tb.beta[:2]):
+        assert np.allclose(RK23.A[i + 1][:len(row)], row, rtol=0, atol=1e-15)
+    assert np.allclose(RK23.B, tb.c_sol[:3], rtol=0, atol=1e-15) and tb.c_sol[3] == 0
+    assert np.allclose(tb.beta[2], tb.c_sol[:3])                      # FSAL
+    assert np.allclose(np.abs(RK23.E), np.abs(tb.c_error), rtol=0, atol=1e-15)
+    assert np.allclose(RK23.E, -np.asarray(tb.c_error), rtol=0, atol=1e-15)
+
+
 def test_oracle_solution_agrees_with_scipy_rk45():
     """Same nonlinear system, same tolerances: both adaptive solvers must land on the same solution to a few times
     the tolerance, with step counts of the same order."""
